@@ -1,0 +1,267 @@
+"""SacCore: thin Python object over one libb200sac handle (R co-scheduled learners).
+
+Host-side plumbing only -- torch is used for device buffers / streams; all math
+runs in the CUDA library.  The reference-shaped `Learner` classes
+(distributed_sac_b200/learner.py) are built on this.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+@dataclass
+class CoreConfig:
+    state_dim: int = 8
+    act_dim: int = 2
+    actor_hidden: List[int] = field(default_factory=lambda: [256, 256])
+    critic_hidden: List[int] = field(default_factory=lambda: [256, 256])
+    batch: int = 256
+    num_tasks: int = 0
+    weighted_loss: bool = False
+    replicas: int = 1
+    precision: int = 0
+    gamma: float = 0.99
+    tau: float = 0.005
+    reward_scale: float = 1.0
+    lr_actor: float = 3e-4
+    lr_critic: float = 3e-4
+    lr_alpha: Optional[float] = None      # the reference uses lr_actor (LL/learner.py:124)
+    action_scale: float = 1.0
+    beta1: float = 0.9
+    beta2: float = 0.999
+    adam_eps: float = 1e-8
+    log_alpha_init: float = 0.0
+
+    @property
+    def obs_dim(self):
+        return self.state_dim + self.num_tasks
+
+    def to_c(self):
+        c = _lib.Cfg()
+        c.state_dim, c.act_dim, c.num_tasks = self.state_dim, self.act_dim, self.num_tasks
+        c.n_actor_hidden, c.n_critic_hidden = len(self.actor_hidden), len(self.critic_hidden)
+        if max(c.n_actor_hidden, c.n_critic_hidden) > _lib.MAX_HIDDEN:
+            raise ValueError(f"at most {_lib.MAX_HIDDEN} hidden layers")
+        for i, v in enumerate(self.actor_hidden):
+            c.actor_hidden[i] = int(v)
+        for i, v in enumerate(self.critic_hidden):
+            c.critic_hidden[i] = int(v)
+        c.batch, c.weighted_loss, c.replicas, c.precision = self.batch, int(self.weighted_loss), self.replicas, self.precision
+        c.gamma, c.tau, c.reward_scale = self.gamma, self.tau, self.reward_scale
+        c.lr_actor, c.lr_critic = self.lr_actor, self.lr_critic
+        c.lr_alpha = self.lr_actor if self.lr_alpha is None else self.lr_alpha
+        c.action_scale = self.action_scale
+        c.beta1, c.beta2, c.adam_eps = self.beta1, self.beta2, self.adam_eps
+        c.log_alpha_init = self.log_alpha_init
+        return c
+
+
+def layout(cfg: CoreConfig):
+    """Parameter layout table from the C library (pure host call, works without a GPU).
+    Returns ({name: (offset, rows, cols, trainable, opt)}, arena_floats, trainable_floats)."""
+    lib = _lib.load()
+    c = cfg.to_c()
+    n, arena, train = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+    _lib.check(lib.b200sac_layout(C.byref(c), None, 0, C.byref(n), C.byref(arena), C.byref(train)))
+    descs = (_lib.TensorDesc * n.value)()
+    _lib.check(lib.b200sac_layout(C.byref(c), descs, n.value, C.byref(n), C.byref(arena), C.byref(train)))
+    table = {d.name.decode(): (d.offset, d.rows, d.cols, d.trainable, d.opt) for d in descs}
+    return table, arena.value, train.value
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class SacCore:
+    def __init__(self, cfg: CoreConfig, device: int = 0, seed: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("SacCore needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.table, self.arena_floats, self.trainable_floats = layout(cfg)
+        self._h = C.c_void_p(0)
+        c = cfg.to_c()
+        torch.cuda.set_device(self.device)
+        _lib.check(self.lib.b200sac_create(C.byref(c), device, C.c_uint64(seed), C.byref(self._h)))
+        n = C.c_int32(0)
+        _lib.check(self.lib.b200sac_launches_per_step(self._h, C.byref(n)))
+        self.launches_per_step = n.value
+        self.steps_done = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b200sac_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ------------------------------------------------------------------------
+    def _arena_n(self, which):
+        return self.arena_floats if which == _lib.PARAMS else self.trainable_floats
+
+    def export_arena(self, which=_lib.PARAMS, replica=0) -> torch.Tensor:
+        out = torch.empty(self._arena_n(which), dtype=torch.float32)
+        _lib.check(self.lib.b200sac_export(self._h, which, replica, _ptr(out), out.numel(), _stream()))
+        return out
+
+    def import_arena(self, flat: torch.Tensor, which=_lib.PARAMS, replica=0):
+        flat = flat.detach().to(torch.float32).contiguous()
+        assert flat.numel() == self._arena_n(which)
+        _lib.check(self.lib.b200sac_import(self._h, which, replica, _ptr(flat), flat.numel(), _stream()))
+
+    def arena_view(self, which=_lib.PARAMS):
+        """(device pointer, floats per replica) of an arena (replicas contiguous)."""
+        p, n = C.c_void_p(0), C.c_int64(0)
+        _lib.check(self.lib.b200sac_arena_ptr(self._h, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def get_named(self, which=_lib.PARAMS, replica=0) -> Dict[str, torch.Tensor]:
+        flat = self.export_arena(which, replica)
+        out = {}
+        for name, (off, rows, cols, trainable, _opt) in self.table.items():
+            if which != _lib.PARAMS and not trainable:
+                continue
+            t = flat[off:off + rows * cols]
+            is_mat = name.endswith(".weight")
+            out[name] = t.reshape(rows, cols).clone() if is_mat else t.clone()
+        return out
+
+    def set_named(self, tensors: Dict[str, torch.Tensor], which=_lib.PARAMS, replica=0, strict=True):
+        flat = self.export_arena(which, replica)
+        seen = set()
+        for name, t in tensors.items():
+            if name not in self.table:
+                if strict:
+                    raise KeyError(name)
+                continue
+            off, rows, cols, trainable, _ = self.table[name]
+            if which != _lib.PARAMS and not trainable:
+                continue
+            t = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+            if t.numel() != rows * cols:
+                raise ValueError(f"{name}: expected {rows * cols} elements, got {t.numel()}")
+            flat[off:off + rows * cols] = t
+            seen.add(name)
+        if strict:
+            need = {n for n, d in self.table.items() if which == _lib.PARAMS or d[3]}
+            if need - seen:
+                raise KeyError(f"missing tensors: {sorted(need - seen)[:5]}")
+        self.import_arena(flat, which, replica)
+
+    def get_steps(self, replica=0):
+        s = (C.c_int64 * 3)()
+        _lib.check(self.lib.b200sac_get_steps(self._h, replica, s))
+        return tuple(int(x) for x in s)     # (critic, actor, alpha)
+
+    def set_steps(self, steps, replica=0):
+        s = (C.c_int64 * 3)(*[int(x) for x in steps])
+        _lib.check(self.lib.b200sac_set_steps(self._h, replica, s))
+
+    def soft_update(self, tau: float):
+        _lib.check(self.lib.b200sac_soft_update(self._h, float(tau), _stream()))
+
+    # ---- stepping -----------------------------------------------------------------------
+    def _shape_check(self, s, a, r, s2, d, eps_next, eps_cur):
+        c = self.cfg
+        R, B = c.replicas, c.batch
+        want = dict(s=c.obs_dim, a=c.act_dim, r=1, s2=c.obs_dim, d=1)
+        for k, t in dict(s=s, a=a, r=r, s2=s2, d=d).items():
+            if t.numel() != R * B * want[k]:
+                raise ValueError(f"{k}: expected {R}x{B}x{want[k]} elements, got {tuple(t.shape)}")
+        for k, t in dict(eps_next=eps_next, eps_cur=eps_cur).items():
+            if t is not None and t.numel() != R * B * c.act_dim:
+                raise ValueError(f"{k}: expected {R}x{B}x{c.act_dim} elements, got {tuple(t.shape)}")
+
+    def step(self, s, a, r, s2, d, eps_next=None, eps_cur=None):
+        """One gradient step from DEVICE tensors [R][B][w] (asynchronous)."""
+        ts = [None if t is None else t.to(self.device, torch.float32).contiguous() for t in (s, a, r, s2, d, eps_next, eps_cur)]
+        self._shape_check(*ts)
+        self._keep = ts          # keep inputs alive until the stream has consumed them
+        _lib.check(self.lib.b200sac_step(self._h, *[_ptr(t) for t in ts], _stream()))
+        self.steps_done += 1
+
+    def step_host(self, s, a, r, s2, d, eps_next=None, eps_cur=None, want_losses=True):
+        """One gradient step from HOST tensors through the pinned staging path; returns
+        losses [R][4] = (critic, actor, alpha, entropy) if want_losses (synchronises)."""
+        ts = [None if t is None else t.detach().to("cpu", torch.float32).contiguous() for t in (s, a, r, s2, d, eps_next, eps_cur)]
+        self._shape_check(*ts)
+        out = torch.empty(self.cfg.replicas, 4) if want_losses else None
+        _lib.check(self.lib.b200sac_step_host(self._h, *[_ptr(t) for t in ts], _ptr(out), _stream()))
+        self.steps_done += 1
+        return out
+
+    def step_sampled(self, replay: "Replay", n_steps: int = 1):
+        _lib.check(self.lib.b200sac_step_sampled(self._h, replay._h, int(n_steps), _stream()))
+        self.steps_done += int(n_steps)
+
+    def read_losses(self, n_last: int = 1) -> torch.Tensor:
+        out = torch.empty(n_last, self.cfg.replicas, 4)
+        _lib.check(self.lib.b200sac_read_losses(self._h, n_last, _ptr(out), _stream()))
+        return out
+
+    def debug(self, name: str, replica=0) -> torch.Tensor:
+        cap = self.cfg.batch * max(2 * self.cfg.act_dim, 1)
+        out = torch.empty(cap)
+        n = C.c_int64(0)
+        _lib.check(self.lib.b200sac_debug_read(self._h, name.encode(), replica, _ptr(out), cap, C.byref(n), _stream()))
+        return out[:n.value].clone()
+
+
+class Replay:
+    """Replay ring in HBM (where='device') or pinned host DRAM (where='host')."""
+
+    def __init__(self, core: SacCore, capacity: int, where: str = "device", seed: int = 0):
+        self.core = core
+        self.lib = core.lib
+        self._h = C.c_void_p(0)
+        w = {"device": 0, "host": 1}[where]
+        _lib.check(self.lib.b200sac_replay_create(core._h, int(capacity), w, C.c_uint64(seed), C.byref(self._h)))
+        self.where = where
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value and self.core._h.value:
+            self.lib.b200sac_replay_destroy(self._h)
+        self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push(self, s, a, r, s2, d, replica=0):
+        ts = [np.ascontiguousarray(np.asarray(t, dtype=np.float32)) for t in (s, a, r, s2, d)]
+        n = ts[2].size
+        _lib.check(self.lib.b200sac_replay_push(self._h, replica, n, *[C.c_void_p(t.ctypes.data) for t in ts]))
+
+    def fill_synthetic(self, n: int, seed: int = 1234):
+        _lib.check(self.lib.b200sac_replay_fill_synthetic(self._h, int(n), C.c_uint64(seed), _stream()))
+
+    def size(self, replica=0) -> int:
+        n = C.c_int64(0)
+        _lib.check(self.lib.b200sac_replay_size(self._h, replica, C.byref(n)))
+        return n.value
+
+    def sample(self, replica=0, with_indices=False):
+        c = self.core.cfg
+        B = c.batch
+        s, a, r = torch.empty(B, c.obs_dim), torch.empty(B, c.act_dim), torch.empty(B, 1)
+        s2, d = torch.empty(B, c.obs_dim), torch.empty(B, 1)
+        idx = torch.empty(B, dtype=torch.int64)
+        _lib.check(self.lib.b200sac_replay_sample(self._h, replica, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(d), _ptr(idx)))
+        return (s, a, r, s2, d, idx) if with_indices else (s, a, r, s2, d)

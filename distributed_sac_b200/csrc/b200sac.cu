@@ -1,0 +1,1224 @@
+// libb200sac: C-ABI implementation (see include/b200sac.h) -- host orchestration of the
+// sm_100a SAC gradient step.  One handle = R independent learners of one shape stepped
+// together; one step = a fixed list of grouped launches captured once into a CUDA graph.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <new>
+#include <random>
+#include <string>
+#include <tuple>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/b200sac.h"
+#include "gemm_simt.cuh"
+#include "sac_kernels.cuh"
+
+using namespace bsac;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(B200SAC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* b200sac_last_error(void) { return g_err; }
+extern "C" const char* b200sac_version(void) { return "b200sac 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------
+struct LayerOff { int64_t w, b; int in, out; };
+struct Layout {
+  std::vector<b200sac_tensor_desc> descs;
+  std::vector<LayerOff> actor, q[2], qt[2];
+  int64_t off_alpha = 0, arena = 0, trainable = 0;
+  int64_t actor_begin = 0, actor_n = 0, critic_begin = 0, critic_n = 0, target_delta = 0;
+};
+
+static int64_t pad4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+static int check_cfg(const b200sac_cfg* c) {
+  if (!c) return fail(B200SAC_ERR_INVALID, "cfg is NULL");
+  if (c->state_dim < 1 || c->act_dim < 1 || c->act_dim > kMaxAct)
+    return fail(B200SAC_ERR_INVALID, "state_dim >= 1 and 1 <= act_dim <= %d required", kMaxAct);
+  if (c->num_tasks < 0 || c->num_tasks > 64) return fail(B200SAC_ERR_INVALID, "0 <= num_tasks <= 64 required");
+  if (c->n_actor_hidden < 1 || c->n_actor_hidden > B200SAC_MAX_HIDDEN || c->n_critic_hidden < 1 ||
+      c->n_critic_hidden > B200SAC_MAX_HIDDEN)
+    return fail(B200SAC_ERR_INVALID, "1..%d hidden layers required", B200SAC_MAX_HIDDEN);
+  for (int i = 0; i < c->n_actor_hidden; ++i)
+    if (c->actor_hidden[i] < 1) return fail(B200SAC_ERR_INVALID, "actor_hidden[%d] < 1", i);
+  for (int i = 0; i < c->n_critic_hidden; ++i)
+    if (c->critic_hidden[i] < 1) return fail(B200SAC_ERR_INVALID, "critic_hidden[%d] < 1", i);
+  if (c->batch < 1 || c->batch > 2048) return fail(B200SAC_ERR_INVALID, "1 <= batch <= 2048 required");
+  if (c->num_tasks > 0 && c->batch % c->num_tasks != 0)
+    return fail(B200SAC_ERR_INVALID, "batch must be a multiple of num_tasks");
+  if (c->replicas < 1 || c->replicas > 4096) return fail(B200SAC_ERR_INVALID, "1 <= replicas <= 4096 required");
+  if (c->precision != 0) return fail(B200SAC_ERR_INVALID, "precision %d not available in this build", c->precision);
+  return 0;
+}
+
+static void build_layout(const b200sac_cfg* c, Layout& L) {
+  const int obs = c->state_dim + c->num_tasks;
+  int64_t off = 0;
+  auto add = [&](const char* net, int i, const char* kind, int rows, int cols, int trainable, int opt) {
+    b200sac_tensor_desc d;
+    memset(&d, 0, sizeof(d));
+    if (i >= 0) snprintf(d.name, sizeof(d.name), "%s.%d.%s", net, i, kind);
+    else snprintf(d.name, sizeof(d.name), "%s", net);
+    d.offset = off; d.rows = rows; d.cols = cols; d.trainable = trainable; d.opt = opt;
+    L.descs.push_back(d);
+    int64_t o = off;
+    off = pad4(off + (int64_t)rows * cols);
+    return o;
+  };
+  auto add_net = [&](const char* net, std::vector<LayerOff>& v, int in0, const int* hid, int nh, int out, int tr, int opt) {
+    int in = in0;
+    for (int i = 0; i <= nh; ++i) {
+      int o = (i < nh) ? hid[i] : out;
+      LayerOff lo;
+      lo.in = in; lo.out = o;
+      lo.w = add(net, i, "weight", o, in, tr, opt);
+      lo.b = add(net, i, "bias", o, 1, tr, opt);
+      v.push_back(lo);
+      in = o;
+    }
+  };
+  L.actor_begin = off;
+  add_net("actor", L.actor, obs, c->actor_hidden, c->n_actor_hidden, 2 * c->act_dim, 1, 1);
+  L.actor_n = off - L.actor_begin;
+  L.critic_begin = off;
+  add_net("q1", L.q[0], obs + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0);
+  add_net("q2", L.q[1], obs + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0);
+  L.critic_n = off - L.critic_begin;
+  L.off_alpha = add("log_alpha", -1, "", c->num_tasks > 0 ? c->num_tasks : 1, 1, 1, 2);
+  L.trainable = off;
+  int64_t tb = off;
+  add_net("q1_target", L.qt[0], obs + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1);
+  add_net("q2_target", L.qt[1], obs + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1);
+  L.target_delta = tb - L.critic_begin;
+  L.arena = off;
+}
+
+extern "C" int b200sac_layout(const b200sac_cfg* cfg, b200sac_tensor_desc* out, int32_t cap, int32_t* n,
+                              int64_t* arena_floats, int64_t* trainable_floats) {
+  if (int rc = check_cfg(cfg)) return rc;
+  Layout L;
+  build_layout(cfg, L);
+  if (n) *n = (int32_t)L.descs.size();
+  if (arena_floats) *arena_floats = L.arena;
+  if (trainable_floats) *trainable_floats = L.trainable;
+  if (out)
+    for (int i = 0; i < (int)L.descs.size() && i < cap; ++i) out[i] = L.descs[i];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct Buf {           // [R][n] fp32 (or int32) slab slice
+  float* p = nullptr;
+  long long rs = 0;    // replica stride in floats
+};
+
+enum LaunchKind { L_GEMM_BIG, L_GEMM_SMALL, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
+
+struct Launch {
+  LaunchKind kind;
+  dim3 grid, block;
+  size_t smem = 0;
+  // payloads (only the one matching `kind` is used)
+  const GemmProb* probs = nullptr; int G = 0;
+  PolicyHeadArgs pol;
+  CriticHeadArgs ch;
+  ActorQHeadArgs aq;
+  HeadBwdArgs hb;
+  AdamArgs ad;
+};
+
+struct GraphKey {
+  int variant;
+  const void* p[9];
+  bool operator<(const GraphKey& o) const {
+    if (variant != o.variant) return variant < o.variant;
+    return memcmp(p, o.p, sizeof(p)) < 0;
+  }
+};
+
+struct b200sac_replay;
+
+struct b200sac {
+  b200sac_cfg cfg;
+  int device = 0;
+  Layout L;
+  StepConst K;
+  int R = 1;
+  // arenas
+  float *params = nullptr, *adam_m = nullptr, *adam_v = nullptr, *grads = nullptr;
+  Counters* cnt = nullptr;
+  float* losses = nullptr;        // [kLossSlots][R][4]
+  long long host_steps = 0;       // steps enqueued so far
+  // work slab
+  float* slab = nullptr;
+  size_t slab_floats = 0;
+  Buf XA, XQ, XT, XP, r, d, tid, eps, pout, psave, act_out, logp, logstd, y, q, dq, lq, dqa, la, qmin, dxP,
+      dout_dbg, dact_dbg;
+  std::vector<Buf> hA, dhA;       // per actor hidden layer
+  std::vector<Buf> hQ, hT, hP, dhQ;   // per critic hidden layer, [2][B][H]
+  GemmProb* d_probs = nullptr;
+  std::vector<GemmProb> h_probs;
+  std::vector<Launch> plan;
+  IngestOut ing;
+  int use_eps_buf_idx = -1;       // index of the policy launch in plan (its use_eps_buf flag varies)
+  // graphs
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  // host staging for step_host / pinned replay
+  float* stage_h[2] = {nullptr, nullptr};
+  float* stage_d[2] = {nullptr, nullptr};
+  size_t stage_floats = 0;
+  int row_w = 0, row_stride = 0;
+  cudaStream_t side = nullptr;
+  cudaStream_t own = nullptr;     // used when the caller hands us the legacy default stream (not capturable)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  int stage_slot = 0;
+  bool stage_used[2] = {false, false};
+  float* loss_h = nullptr;        // pinned [R][4]
+};
+
+struct b200sac_replay {
+  b200sac* h = nullptr;
+  int where = 0;
+  long long cap = 0, cap_per_task = 0;
+  int Teff = 1;
+  float* rows = nullptr;          // [R][cap][row_stride] device or pinned host
+  long long rs_rows = 0;
+  std::vector<long long> fill, head;   // [R][Teff]
+  long long* d_fill = nullptr;    // device copy (device ring)
+  int* d_idx = nullptr;           // [R][B]
+  unsigned long long seed = 0;
+  std::mt19937_64 rng;
+  std::mutex mu;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Buf carve(size_t& cursor, size_t n_per_rep, int R) {
+  Buf b;
+  size_t n = align_up(n_per_rep, 64);
+  b.rs = (long long)n;
+  b.p = (float*)(uintptr_t)(cursor * sizeof(float));   // offset for now; rebased after allocation
+  cursor += n * (size_t)R;
+  return b;
+}
+
+static void rebase(Buf& b, float* base) { b.p = base + (size_t)(uintptr_t)b.p / sizeof(float); }
+
+static int destroy_impl(b200sac* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  cudaFree(h->params); cudaFree(h->adam_m); cudaFree(h->adam_v); cudaFree(h->grads);
+  cudaFree(h->cnt); cudaFree(h->losses); cudaFree(h->slab); cudaFree(h->d_probs);
+  for (int i = 0; i < 2; ++i) {
+    if (h->stage_h[i]) cudaFreeHost(h->stage_h[i]);
+    cudaFree(h->stage_d[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+  }
+  if (h->loss_h) cudaFreeHost(h->loss_h);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->own) cudaStreamDestroy(h->own);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  delete h;
+  return 0;
+}
+
+// Build the launch list of one gradient step (everything after the ingest kernel).
+static int build_plan(b200sac* h) {
+  const b200sac_cfg& c = h->cfg;
+  const Layout& L = h->L;
+  const int B = c.batch, R = h->R, A = c.act_dim;
+  const int La = c.n_actor_hidden, Lc = c.n_critic_hidden;
+  const long long rsP = L.arena, rsG = L.trainable;
+  std::vector<std::vector<GemmProb>> groups;
+  struct Pending { int group; };
+  auto W = [&](int64_t off) { return h->params + off; };
+  auto Gp = [&](int64_t off) { return h->grads + off; };
+
+  auto gemm_launch = [&](std::vector<GemmProb> ps) {
+    Launch l;
+    int maxM = 0, maxN = 0;
+    for (auto& p : ps) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; }
+    bool big = ((long long)maxM * maxN) >= (long long)512 * 256;
+    if (const char* e = getenv("B200SAC_TILE")) big = (e[0] == 'b');
+    const int bm = big ? 64 : 32, bn = big ? 64 : 32;
+    l.kind = big ? L_GEMM_BIG : L_GEMM_SMALL;
+    l.grid = dim3((maxN + bn - 1) / bn, (maxM + bm - 1) / bm, (unsigned)(ps.size() * R));
+    l.block = dim3(256);
+    l.G = (int)ps.size();
+    l.probs = (const GemmProb*)(uintptr_t)h->h_probs.size();   // index for now; rebased later
+    for (auto& p : ps) h->h_probs.push_back(p);
+    h->plan.push_back(l);
+  };
+  auto fwd = [&](const float* Ain, long long rsA, int M, const LayerOff& lo, bool target_or_local_params, float* out,
+                 long long rsOut) {
+    (void)target_or_local_params;
+    GemmProb p;
+    memset(&p, 0, sizeof(p));
+    p.A = Ain; p.rsA = rsA; p.lda = lo.in;
+    p.B = W(lo.w); p.rsB = rsP; p.ldb = lo.in;
+    p.bias = W(lo.b); p.rsBias = rsP;
+    p.C = out; p.rsC = rsOut; p.ldc = lo.out;
+    p.M = M; p.N = lo.out; p.K = lo.in; p.mode = GEMM_FWD; p.relu = 1;
+    return p;
+  };
+  auto wgrad = [&](const float* dZ, long long rsdZ, const float* X, long long rsX, const LayerOff& lo) {
+    GemmProb p;
+    memset(&p, 0, sizeof(p));
+    p.A = dZ; p.rsA = rsdZ; p.lda = lo.out;
+    p.B = X; p.rsB = rsX; p.ldb = lo.in;
+    p.C = Gp(lo.w); p.rsC = rsG; p.ldc = lo.in;
+    p.C2 = Gp(lo.b); p.rsC2 = rsG;
+    p.M = lo.out; p.N = lo.in; p.K = B; p.mode = GEMM_WGRAD;
+    return p;
+  };
+  auto dgrad = [&](const float* dZ, long long rsdZ, const LayerOff& lo, const float* mask, long long rsMask, float* out,
+                   long long rsOut) {
+    GemmProb p;
+    memset(&p, 0, sizeof(p));
+    p.A = dZ; p.rsA = rsdZ; p.lda = lo.out;
+    p.B = W(lo.w); p.rsB = rsP; p.ldb = lo.in;
+    p.mask = mask; p.rsMask = rsMask; p.ldmask = lo.in;
+    p.C = out; p.rsC = rsOut; p.ldc = lo.in;
+    p.M = B; p.N = lo.in; p.K = lo.out; p.mode = GEMM_DGRAD;
+    return p;
+  };
+  auto netp = [&](const Buf& b, int net, int H) { return b.p + (long long)net * B * H; };
+
+  // ---- Phase A: actor over [s2; s] and Q1,Q2 over (s,a), layer by layer -----------------
+  for (int l = 0; l < (La > Lc ? La : Lc); ++l) {
+    std::vector<GemmProb> ps;
+    if (l < La) {
+      const LayerOff& lo = L.actor[l];
+      ps.push_back(fwd(l == 0 ? h->XA.p : h->hA[l - 1].p, l == 0 ? h->XA.rs : h->hA[l - 1].rs, 2 * B, lo, true,
+                       h->hA[l].p, h->hA[l].rs));
+    }
+    if (l < Lc)
+      for (int net = 0; net < 2; ++net) {
+        const LayerOff& lo = L.q[net][l];
+        ps.push_back(fwd(l == 0 ? h->XQ.p : netp(h->hQ[l - 1], net, lo.in), l == 0 ? h->XQ.rs : h->hQ[l - 1].rs, B, lo,
+                         true, netp(h->hQ[l], net, lo.out), h->hQ[l].rs));
+      }
+    gemm_launch(ps);
+  }
+  {  // policy head
+    Launch l;
+    l.kind = L_POLICY;
+    l.grid = dim3((2 * B + 7) / 8, R);
+    l.block = dim3(256);
+    PolicyHeadArgs& P = l.pol;
+    memset(&P, 0, sizeof(P));
+    const LayerOff& lo = L.actor[La];
+    P.h = h->hA[La - 1].p; P.rsH = h->hA[La - 1].rs; P.ldh = lo.in;
+    P.W = W(lo.w); P.b = W(lo.b); P.rsP = rsP;
+    P.eps = h->eps.p; P.rsEps = h->eps.rs; P.use_eps_buf = 0;
+    P.pout = h->pout.p; P.rsPout = h->pout.rs;
+    P.psave = h->psave.p; P.rsSave = h->psave.rs;
+    P.XT = h->XT.p; P.XP = h->XP.p; P.rsX = h->XT.rs;
+    P.act_out = h->act_out.p; P.rsAct = h->act_out.rs;
+    P.logp = h->logp.p; P.rsLogp = h->logp.rs;
+    P.logstd_sum = h->logstd.p;
+    P.cnt = h->cnt;
+    h->use_eps_buf_idx = (int)h->plan.size();
+    h->plan.push_back(l);
+  }
+  // ---- Phase B: target critics over (s2, a') ---------------------------------------------
+  for (int l = 0; l < Lc; ++l) {
+    std::vector<GemmProb> ps;
+    for (int net = 0; net < 2; ++net) {
+      const LayerOff& lo = L.qt[net][l];
+      ps.push_back(fwd(l == 0 ? h->XT.p : netp(h->hT[l - 1], net, lo.in), l == 0 ? h->XT.rs : h->hT[l - 1].rs, B, lo,
+                       true, netp(h->hT[l], net, lo.out), h->hT[l].rs));
+    }
+    gemm_launch(ps);
+  }
+  const int Hc = c.critic_hidden[Lc - 1], Ha = c.actor_hidden[La - 1];
+  {  // critic heads: y, Q1, Q2, dQ
+    Launch l;
+    l.kind = L_CHEADS;
+    l.grid = dim3((B + 7) / 8, R);
+    l.block = dim3(256);
+    CriticHeadArgs& P = l.ch;
+    memset(&P, 0, sizeof(P));
+    P.hT = h->hT[Lc - 1].p; P.hQ = h->hQ[Lc - 1].p; P.rsHnet = (long long)B * Hc; P.rsHrep = h->hT[Lc - 1].rs; P.ldh = Hc;
+    for (int net = 0; net < 2; ++net) {
+      P.Wt[net] = W(L.qt[net][Lc].w); P.bt[net] = W(L.qt[net][Lc].b);
+      P.Wq[net] = W(L.q[net][Lc].w); P.bq[net] = W(L.q[net][Lc].b);
+    }
+    P.rsP = rsP;
+    P.r = h->r.p; P.d = h->d.p; P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
+    P.logp = h->logp.p; P.rsLogp = h->logp.rs;
+    P.log_alpha = W(L.off_alpha);
+    P.y = h->y.p; P.q = h->q.p; P.dq = h->dq.p; P.lq = h->lq.p; P.rsY = h->y.rs;
+    h->plan.push_back(l);
+  }
+  auto head_bwd = [&](bool policy, bool want_wgrad) {
+    Launch l;
+    l.kind = L_HEADBWD;
+    HeadBwdArgs& P = l.hb;
+    memset(&P, 0, sizeof(P));
+    P.M = B;
+    P.rsP = rsP; P.rsG = rsG;
+    if (!policy) {
+      P.NO = 1; P.Kdim = Hc; P.nets = 2;
+      for (int net = 0; net < 2; ++net) {
+        P.W[net] = W(L.q[net][Lc].w);
+        P.dW[net] = want_wgrad ? Gp(L.q[net][Lc].w) : nullptr;
+        P.db[net] = want_wgrad ? Gp(L.q[net][Lc].b) : nullptr;
+      }
+      const Buf& hb = want_wgrad ? h->hQ[Lc - 1] : h->hP[Lc - 1];
+      const Buf& dq = want_wgrad ? h->dq : h->dqa;
+      P.dout = dq.p; P.rsDoutNet = B; P.rsDoutRep = 2 * h->y.rs;
+      P.h = hb.p; P.rsHnet = (long long)B * Hc; P.rsHrep = hb.rs; P.ldh = Hc;
+      P.dh = h->dhQ[Lc - 1].p; P.rsDhNet = (long long)B * Hc; P.rsDhRep = h->dhQ[Lc - 1].rs; P.lddh = Hc;
+    } else {
+      P.NO = 2 * A; P.Kdim = Ha; P.nets = 1; P.policy_mode = 1;
+      const LayerOff& lo = L.actor[La];
+      P.W[0] = W(lo.w); P.dW[0] = Gp(lo.w); P.db[0] = Gp(lo.b);
+      P.h = h->hA[La - 1].p + (long long)B * Ha; P.rsHrep = h->hA[La - 1].rs; P.ldh = Ha;   // rows B..2B-1 (= s half)
+      P.dh = h->dhA[La - 1].p; P.rsDhRep = h->dhA[La - 1].rs; P.lddh = Ha;
+      P.dx = h->dxP.p; P.rsDxNet = (long long)B * h->K.xw; P.rsDxRep = h->dxP.rs; P.lddx = h->K.xw;
+      P.psave = h->psave.p + (long long)B * A * kSaveW; P.rsSave = h->psave.rs;
+      P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
+      P.log_alpha = W(L.off_alpha);
+      P.dout_dbg = h->dout_dbg.p; P.dact_dbg = h->dact_dbg.p; P.rsDbg = h->dout_dbg.rs;
+    }
+    l.grid = dim3((P.Kdim + 31) / 32, P.nets, R);
+    l.block = dim3(256);
+    l.smem = ((size_t)B * P.NO + 256 * (size_t)P.NO) * sizeof(float);
+    h->plan.push_back(l);
+  };
+  // ---- Phase C: critic backward + Adam/Polyak ----------------------------------------------
+  head_bwd(false, true);
+  for (int l = Lc - 1; l >= 0; --l) {
+    std::vector<GemmProb> ps;
+    for (int net = 0; net < 2; ++net) {
+      const LayerOff& lo = L.q[net][l];
+      const float* X = l == 0 ? h->XQ.p : netp(h->hQ[l - 1], net, lo.in);
+      const long long rsX = l == 0 ? h->XQ.rs : h->hQ[l - 1].rs;
+      ps.push_back(wgrad(netp(h->dhQ[l], net, lo.out), h->dhQ[l].rs, X, rsX, lo));
+    }
+    if (l > 0)
+      for (int net = 0; net < 2; ++net) {
+        const LayerOff& lo = L.q[net][l];
+        ps.push_back(dgrad(netp(h->dhQ[l], net, lo.out), h->dhQ[l].rs, lo, netp(h->hQ[l - 1], net, lo.in), h->hQ[l - 1].rs,
+                           netp(h->dhQ[l - 1], net, lo.in), h->dhQ[l - 1].rs));
+      }
+    gemm_launch(ps);
+  }
+  auto adam = [&](int which) {
+    Launch l;
+    l.kind = L_ADAM;
+    AdamArgs& P = l.ad;
+    memset(&P, 0, sizeof(P));
+    const int64_t beg = which == 0 ? L.critic_begin : L.actor_begin;
+    const int64_t n = which == 0 ? L.critic_n : L.actor_n;
+    P.p = h->params + beg; P.m = h->adam_m + beg; P.v = h->adam_v + beg; P.g = h->grads + beg;
+    P.rsP = rsP; P.rsM = rsG; P.n = n;
+    P.target_delta = which == 0 ? L.target_delta : 0;
+    P.which = which;
+    P.lr = which == 0 ? c.lr_critic : c.lr_actor;
+    P.cnt = h->cnt;
+    P.tail = which == 0 ? TAIL_CRITIC_LOSS : TAIL_ALPHA_AND_LOSSES;
+    P.lq = h->lq.p; P.la = h->la.p; P.rsY = h->y.rs;
+    P.logp_cur = h->logp.p + B; P.logstd_sum = h->logstd.p + B; P.rsLogp = h->logp.rs;
+    P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
+    P.log_alpha = h->params + L.off_alpha;
+    P.m_alpha = h->adam_m + L.off_alpha; P.v_alpha = h->adam_v + L.off_alpha; P.g_alpha = h->grads + L.off_alpha;
+    P.losses = h->losses; P.R = R;
+    int nb = (int)((n + 256 * 4 - 1) / (256 * 4));
+    if (nb < 1) nb = 1;
+    if (nb > 592) nb = 592;
+    l.grid = dim3(nb + 1, R);
+    l.block = dim3(256);
+    h->plan.push_back(l);
+  };
+  adam(0);
+  // ---- Phase D: actor pass through the updated critics ---------------------------------------
+  for (int l = 0; l < Lc; ++l) {
+    std::vector<GemmProb> ps;
+    for (int net = 0; net < 2; ++net) {
+      const LayerOff& lo = L.q[net][l];
+      ps.push_back(fwd(l == 0 ? h->XP.p : netp(h->hP[l - 1], net, lo.in), l == 0 ? h->XP.rs : h->hP[l - 1].rs, B, lo, true,
+                       netp(h->hP[l], net, lo.out), h->hP[l].rs));
+    }
+    gemm_launch(ps);
+  }
+  {
+    Launch l;
+    l.kind = L_AQHEADS;
+    l.grid = dim3((B + 7) / 8, R);
+    l.block = dim3(256);
+    ActorQHeadArgs& P = l.aq;
+    memset(&P, 0, sizeof(P));
+    P.hP = h->hP[Lc - 1].p; P.rsHnet = (long long)B * Hc; P.rsHrep = h->hP[Lc - 1].rs; P.ldh = Hc;
+    for (int net = 0; net < 2; ++net) { P.Wq[net] = W(L.q[net][Lc].w); P.bq[net] = W(L.q[net][Lc].b); }
+    P.rsP = rsP;
+    P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
+    P.logp = h->logp.p + B; P.rsLogp = h->logp.rs;
+    P.log_alpha = W(L.off_alpha);
+    P.dqa = h->dqa.p; P.la = h->la.p; P.qmin = h->qmin.p; P.rsY = h->y.rs;
+    h->plan.push_back(l);
+  }
+  head_bwd(false, false);
+  for (int l = Lc - 1; l >= 0; --l) {
+    std::vector<GemmProb> ps;
+    for (int net = 0; net < 2; ++net) {
+      const LayerOff& lo = L.q[net][l];
+      if (l > 0)
+        ps.push_back(dgrad(netp(h->dhQ[l], net, lo.out), h->dhQ[l].rs, lo, netp(h->hP[l - 1], net, lo.in), h->hP[l - 1].rs,
+                           netp(h->dhQ[l - 1], net, lo.in), h->dhQ[l - 1].rs));
+      else
+        ps.push_back(dgrad(netp(h->dhQ[0], net, lo.out), h->dhQ[0].rs, lo, nullptr, 0,
+                           h->dxP.p + (long long)net * B * h->K.xw, h->dxP.rs));
+    }
+    gemm_launch(ps);
+  }
+  // ---- Phase E: policy backward + Adam + temperature -----------------------------------------
+  head_bwd(true, true);
+  for (int l = La - 1; l >= 0; --l) {
+    std::vector<GemmProb> ps;
+    const LayerOff& lo = L.actor[l];
+    const float* X = l == 0 ? h->XA.p + (long long)B * lo.in : h->hA[l - 1].p + (long long)B * lo.in;
+    const long long rsX = l == 0 ? h->XA.rs : h->hA[l - 1].rs;
+    ps.push_back(wgrad(h->dhA[l].p, h->dhA[l].rs, X, rsX, lo));
+    if (l > 0)
+      ps.push_back(dgrad(h->dhA[l].p, h->dhA[l].rs, lo, h->hA[l - 1].p + (long long)B * lo.in, h->hA[l - 1].rs,
+                         h->dhA[l - 1].p, h->dhA[l - 1].rs));
+    gemm_launch(ps);
+  }
+  adam(1);
+
+  // upload problem tables and rebase
+  CU(cudaMalloc(&h->d_probs, h->h_probs.size() * sizeof(GemmProb)));
+  CU(cudaMemcpy(h->d_probs, h->h_probs.data(), h->h_probs.size() * sizeof(GemmProb), cudaMemcpyHostToDevice));
+  for (auto& l : h->plan)
+    if (l.kind == L_GEMM_BIG || l.kind == L_GEMM_SMALL) l.probs = h->d_probs + (size_t)(uintptr_t)l.probs;
+  size_t max_smem = 0;
+  for (auto& l : h->plan)
+    if (l.kind == L_HEADBWD && l.smem > max_smem) max_smem = l.smem;
+  if (max_smem > 200 * 1024) return fail(B200SAC_ERR_INVALID, "batch * head width too large for head_bwd smem");
+  CU(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  return 0;
+}
+
+static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf) {
+  for (size_t i = 0; i < h->plan.size(); ++i) {
+    Launch& l = h->plan[i];
+    switch (l.kind) {
+      case L_GEMM_BIG:
+        gemm_simt_kernel<64, 64, 4, 4><<<l.grid, l.block, 0, st>>>(l.probs, l.G);
+        break;
+      case L_GEMM_SMALL:
+        gemm_simt_kernel<32, 32, 2, 2><<<l.grid, l.block, 0, st>>>(l.probs, l.G);
+        break;
+      case L_POLICY: {
+        PolicyHeadArgs P = l.pol;
+        P.use_eps_buf = use_eps_buf ? 1 : 0;
+        policy_head_kernel<<<l.grid, l.block, 0, st>>>(h->K, P);
+        break;
+      }
+      case L_CHEADS:
+        critic_heads_kernel<<<l.grid, l.block, 0, st>>>(h->K, l.ch);
+        break;
+      case L_AQHEADS:
+        actor_q_heads_kernel<<<l.grid, l.block, 0, st>>>(h->K, l.aq);
+        break;
+      case L_HEADBWD:
+        head_bwd_kernel<<<l.grid, l.block, l.smem, st>>>(h->K, l.hb);
+        break;
+      case L_ADAM:
+        adam_kernel<<<l.grid, l.block, 0, st>>>(h->K, l.ad);
+        break;
+    }
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200sac_launches_per_step(b200sac_t* h, int32_t* n) {
+  if (!h || !n) return fail(B200SAC_ERR_INVALID, "null argument");
+  *n = (int32_t)h->plan.size() + 1;   // + ingest (the sampled-device path adds one more: index sampling)
+  return 0;
+}
+
+extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t seed, b200sac_t** out) {
+  if (!out) return fail(B200SAC_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (int rc = check_cfg(cfg)) return rc;
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(B200SAC_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  b200sac* h = new (std::nothrow) b200sac();
+  if (!h) return fail(B200SAC_ERR_NOMEM, "out of host memory");
+  h->cfg = *cfg;
+  h->device = device;
+  h->R = cfg->replicas;
+  build_layout(cfg, h->L);
+  const Layout& L = h->L;
+  const int B = cfg->batch, R = h->R, A = cfg->act_dim, obs = cfg->state_dim + cfg->num_tasks, xw = obs + A;
+  StepConst& K = h->K;
+  memset(&K, 0, sizeof(K));
+  K.B = B; K.obs = obs; K.act = A; K.T = cfg->num_tasks; K.xw = xw;
+  K.Ha = cfg->actor_hidden[cfg->n_actor_hidden - 1];
+  K.Hc = cfg->critic_hidden[cfg->n_critic_hidden - 1];
+  K.gamma = (float)cfg->gamma; K.reward_scale = (float)cfg->reward_scale; K.action_scale = (float)cfg->action_scale;
+  K.c_loss = (float)(1.0 / B / (cfg->weighted_loss ? (double)B : 1.0));
+  K.inv_B = (float)(1.0 / B);
+  K.tau = (float)cfg->tau; K.one_minus_tau = (float)(1.0 - cfg->tau);
+  K.hbar = -(float)A;
+  K.lr_actor = cfg->lr_actor; K.lr_critic = cfg->lr_critic; K.lr_alpha = cfg->lr_alpha;
+  K.beta1 = cfg->beta1; K.beta2 = cfg->beta2; K.adam_eps = cfg->adam_eps;
+  K.seed = seed;
+
+#define CUH(call)                                                                                            \
+  do {                                                                                                       \
+    cudaError_t e__ = (call);                                                                                \
+    if (e__ != cudaSuccess) {                                                                                \
+      int rc__ = fail(e__ == cudaErrorMemoryAllocation ? B200SAC_ERR_NOMEM : B200SAC_ERR_CUDA, "%s failed: %s", #call, \
+                      cudaGetErrorString(e__));                                                              \
+      destroy_impl(h);                                                                                       \
+      return rc__;                                                                                           \
+    }                                                                                                        \
+  } while (0)
+
+  CUH(cudaMalloc(&h->params, sizeof(float) * L.arena * R));
+  CUH(cudaMalloc(&h->adam_m, sizeof(float) * L.trainable * R));
+  CUH(cudaMalloc(&h->adam_v, sizeof(float) * L.trainable * R));
+  CUH(cudaMalloc(&h->grads, sizeof(float) * L.trainable * R));
+  CUH(cudaMalloc(&h->cnt, sizeof(Counters) * R));
+  CUH(cudaMalloc(&h->losses, sizeof(float) * kLossSlots * R * 4));
+  CUH(cudaMemset(h->params, 0, sizeof(float) * L.arena * R));
+  CUH(cudaMemset(h->adam_m, 0, sizeof(float) * L.trainable * R));
+  CUH(cudaMemset(h->adam_v, 0, sizeof(float) * L.trainable * R));
+  CUH(cudaMemset(h->grads, 0, sizeof(float) * L.trainable * R));
+  CUH(cudaMemset(h->cnt, 0, sizeof(Counters) * R));
+  CUH(cudaMemset(h->losses, 0, sizeof(float) * kLossSlots * R * 4));
+
+  // work slab
+  size_t cur = 0;
+  const int La = cfg->n_actor_hidden, Lc = cfg->n_critic_hidden;
+  h->XA = carve(cur, (size_t)2 * B * obs, R);
+  h->XQ = carve(cur, (size_t)B * xw, R);
+  h->XT = carve(cur, (size_t)B * xw, R);
+  h->XP = carve(cur, (size_t)B * xw, R);
+  h->XT.rs = h->XP.rs = h->XQ.rs;
+  h->r = carve(cur, B, R);
+  h->d = carve(cur, B, R);
+  h->tid = carve(cur, B, R);
+  h->eps = carve(cur, (size_t)2 * B * A, R);
+  h->pout = carve(cur, (size_t)2 * B * 2 * A, R);
+  h->psave = carve(cur, (size_t)2 * B * A * kSaveW, R);
+  h->act_out = carve(cur, (size_t)2 * B * A, R);
+  h->logp = carve(cur, (size_t)2 * B, R);
+  h->logstd = carve(cur, (size_t)2 * B, R);
+  h->y = carve(cur, B, R);
+  h->lq = carve(cur, B, R);
+  h->la = carve(cur, B, R);
+  h->qmin = carve(cur, B, R);
+  // q, dq, dqa are [2][B] with replica stride 2 * y.rs
+  h->q = carve(cur, (size_t)2 * h->y.rs, R);
+  h->dq = carve(cur, (size_t)2 * h->y.rs, R);
+  h->dqa = carve(cur, (size_t)2 * h->y.rs, R);
+  h->dxP = carve(cur, (size_t)2 * B * xw, R);
+  h->dout_dbg = carve(cur, (size_t)B * 2 * A, R);
+  h->dact_dbg = carve(cur, (size_t)B * 2 * A, R);
+  h->dact_dbg.rs = h->dout_dbg.rs;
+  for (int l = 0; l < La; ++l) {
+    h->hA.push_back(carve(cur, (size_t)2 * B * cfg->actor_hidden[l], R));
+    h->dhA.push_back(carve(cur, (size_t)B * cfg->actor_hidden[l], R));
+  }
+  for (int l = 0; l < Lc; ++l) {
+    h->hQ.push_back(carve(cur, (size_t)2 * B * cfg->critic_hidden[l], R));
+    h->hT.push_back(carve(cur, (size_t)2 * B * cfg->critic_hidden[l], R));
+    h->hP.push_back(carve(cur, (size_t)2 * B * cfg->critic_hidden[l], R));
+    h->dhQ.push_back(carve(cur, (size_t)2 * B * cfg->critic_hidden[l], R));
+  }
+  h->slab_floats = cur;
+  CUH(cudaMalloc(&h->slab, cur * sizeof(float)));
+  CUH(cudaMemset(h->slab, 0, cur * sizeof(float)));
+  for (Buf* b : {&h->XA, &h->XQ, &h->XT, &h->XP, &h->r, &h->d, &h->tid, &h->eps, &h->pout, &h->psave, &h->act_out, &h->logp,
+                 &h->logstd, &h->y, &h->lq, &h->la, &h->qmin, &h->q, &h->dq, &h->dqa, &h->dxP, &h->dout_dbg, &h->dact_dbg})
+    rebase(*b, h->slab);
+  for (auto* v : {&h->hA, &h->dhA, &h->hQ, &h->hT, &h->hP, &h->dhQ})
+    for (auto& b : *v) rebase(b, h->slab);
+  if (h->q.rs != 2 * h->y.rs || h->dq.rs != 2 * h->y.rs || h->dqa.rs != 2 * h->y.rs) {
+    destroy_impl(h);
+    return fail(B200SAC_ERR_INVALID, "internal: q stride");
+  }
+
+  IngestOut& O = h->ing;
+  O.XA = h->XA.p; O.XQ = h->XQ.p; O.XT = h->XT.p; O.XP = h->XP.p; O.r = h->r.p; O.d = h->d.p; O.eps = h->eps.p;
+  O.tid = (int*)h->tid.p; O.cnt = h->cnt;
+  O.rsXA = h->XA.rs; O.rsXQ = h->XQ.rs; O.rsR = h->r.rs; O.rsEps = h->eps.rs;
+  if (h->d.rs != h->r.rs || h->tid.rs != h->r.rs || h->lq.rs != h->y.rs || h->la.rs != h->y.rs || h->qmin.rs != h->y.rs ||
+      h->logstd.rs != h->logp.rs) {
+    destroy_impl(h);
+    return fail(B200SAC_ERR_INVALID, "internal: stride mismatch");
+  }
+
+  // parameter init: Xavier-uniform weights, zero biases, log_alpha = cfg; targets = locals
+  {
+    int tag = 0;
+    for (const auto* net : {&L.actor, &L.q[0], &L.q[1]})
+      for (const auto& lo : *net) {
+        xavier_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, lo.out, lo.in, seed, tag++);
+      }
+    std::vector<float> la((size_t)(cfg->num_tasks > 0 ? cfg->num_tasks : 1), (float)cfg->log_alpha_init);
+    for (int rep = 0; rep < R; ++rep)
+      CUH(cudaMemcpy(h->params + (size_t)rep * L.arena + L.off_alpha, la.data(), la.size() * sizeof(float), cudaMemcpyHostToDevice));
+    polyak_kernel<<<dim3(128, R), 256>>>(h->params + L.critic_begin, L.arena, L.critic_n, L.target_delta, 1.0f, 0.0f);
+    CUH(cudaGetLastError());
+  }
+
+  // staging (pinned host <-> device), side stream
+  h->row_w = 2 * obs + A + 2;
+  h->row_stride = (h->row_w + 31) / 32 * 32;   // 128-byte aligned transition rows
+  h->stage_floats = (size_t)R * B * h->row_stride + (size_t)2 * R * B * A;   // rows + eps_next/eps_cur
+  for (int i = 0; i < 2; ++i) {
+    CUH(cudaMallocHost(&h->stage_h[i], h->stage_floats * sizeof(float)));
+    CUH(cudaMalloc(&h->stage_d[i], h->stage_floats * sizeof(float)));
+    CUH(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+    CUH(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
+  }
+  CUH(cudaMallocHost(&h->loss_h, sizeof(float) * R * 4 * kLossSlots));
+  CUH(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CUH(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
+  CUH(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+  CUH(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+
+  if (int rc = build_plan(h)) {
+    destroy_impl(h);
+    return rc;
+  }
+  CUH(cudaDeviceSynchronize());
+  *out = h;
+  return 0;
+}
+
+extern "C" int b200sac_destroy(b200sac_t* h) { return destroy_impl(h); }
+
+static int arena_of(b200sac* h, int which, float** p, int64_t* n) {
+  switch (which) {
+    case B200SAC_PARAMS: *p = h->params; *n = h->L.arena; return 0;
+    case B200SAC_ADAM_M: *p = h->adam_m; *n = h->L.trainable; return 0;
+    case B200SAC_ADAM_V: *p = h->adam_v; *n = h->L.trainable; return 0;
+    case B200SAC_GRADS: *p = h->grads; *n = h->L.trainable; return 0;
+  }
+  return fail(B200SAC_ERR_INVALID, "unknown arena %d", which);
+}
+
+extern "C" int b200sac_arena_ptr(b200sac_t* h, int32_t which, float** dev_ptr, int64_t* floats_per_replica) {
+  if (!h || !dev_ptr || !floats_per_replica) return fail(B200SAC_ERR_INVALID, "null argument");
+  return arena_of(h, which, dev_ptr, floats_per_replica);
+}
+
+extern "C" int b200sac_export(b200sac_t* h, int32_t which, int32_t replica, float* buf, int64_t n_floats, void* stream) {
+  if (!h || !buf) return fail(B200SAC_ERR_INVALID, "null argument");
+  float* p; int64_t n;
+  if (int rc = arena_of(h, which, &p, &n)) return rc;
+  if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica %d out of range", replica);
+  if (n_floats != n) return fail(B200SAC_ERR_INVALID, "arena %d holds %lld floats per replica, got %lld", which, (long long)n, (long long)n_floats);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(buf, p + (size_t)replica * n, n * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int b200sac_import(b200sac_t* h, int32_t which, int32_t replica, const float* buf, int64_t n_floats, void* stream) {
+  if (!h || !buf) return fail(B200SAC_ERR_INVALID, "null argument");
+  float* p; int64_t n;
+  if (int rc = arena_of(h, which, &p, &n)) return rc;
+  if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica %d out of range", replica);
+  if (n_floats != n) return fail(B200SAC_ERR_INVALID, "arena %d holds %lld floats per replica, got %lld", which, (long long)n, (long long)n_floats);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(p + (size_t)replica * n, buf, n * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int b200sac_get_steps(b200sac_t* h, int32_t replica, int64_t steps[3]) {
+  if (!h || !steps || replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(h->device));
+  Counters c;
+  CU(cudaMemcpy(&c, h->cnt + replica, sizeof(c), cudaMemcpyDeviceToHost));
+  steps[0] = c.v[0]; steps[1] = c.v[1]; steps[2] = c.v[2];
+  return 0;
+}
+
+extern "C" int b200sac_set_steps(b200sac_t* h, int32_t replica, const int64_t steps[3]) {
+  if (!h || !steps || replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(h->device));
+  Counters c;
+  CU(cudaMemcpy(&c, h->cnt + replica, sizeof(c), cudaMemcpyDeviceToHost));
+  c.v[0] = steps[0]; c.v[1] = steps[1]; c.v[2] = steps[2];
+  CU(cudaMemcpy(h->cnt + replica, &c, sizeof(c), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// The legacy default stream cannot be captured into a graph.  When the caller passes it (NULL,
+// which is also torch's default current stream) the step runs on the handle's own stream,
+// ordered after everything already queued on the caller's stream, and the caller's stream is
+// made to wait for it afterwards -- same ordering semantics, capturable.
+struct StreamBridge {
+  b200sac* h;
+  cudaStream_t user, run;
+  bool bridged;
+  StreamBridge(b200sac* h_, void* s) : h(h_), user((cudaStream_t)s) {
+    bridged = (user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread);
+    run = bridged ? h->own : user;
+  }
+  int begin() {
+    if (!bridged) return 0;
+    CU(cudaEventRecord(h->ev_in, user));
+    CU(cudaStreamWaitEvent(run, h->ev_in, 0));
+    return 0;
+  }
+  int end() {
+    if (!bridged) return 0;
+    CU(cudaEventRecord(h->ev_out, run));
+    CU(cudaStreamWaitEvent(user, h->ev_out, 0));
+    return 0;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// step variants.  variant 0: split device arrays; 1: packed rows (dense, staged); 2: replay gather
+// ------------------------------------------------------------------------------------------
+static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* const* p, b200sac_replay* rb) {
+  const int B = h->cfg.batch, R = h->R;
+  dim3 grid((B + 7) / 8, R), block(256);
+  if (grid.x > 64) grid.x = 64;
+  bool use_eps = false;
+  if (variant == 0) {
+    use_eps = p[5] != nullptr;
+    ingest_split_kernel<<<grid, block, 0, st>>>(h->K, h->ing, (const float*)p[0], (const float*)p[1], (const float*)p[2],
+                                                (const float*)p[3], (const float*)p[4], (const float*)p[5], (const float*)p[6]);
+  } else if (variant == 1) {
+    const float* rows = (const float*)p[0];
+    const float* e = (const float*)p[1];
+    use_eps = e != nullptr;
+    if (use_eps) {
+      // eps staged as [R][B][A] next, then [R][B][A] cur: reuse the split ingest just for the noise
+      // (rows carry the transition itself)
+    }
+    ingest_rows_kernel<<<grid, block, 0, st>>>(h->K, h->ing, rows, (long long)B * h->row_stride, h->row_stride, nullptr, 0);
+    if (use_eps) {
+      const size_t n = (size_t)B * h->cfg.act_dim * sizeof(float);
+      for (int rep = 0; rep < R; ++rep) {
+        CU(cudaMemcpyAsync(h->eps.p + rep * h->eps.rs, e + (size_t)rep * B * h->cfg.act_dim, n, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(h->eps.p + rep * h->eps.rs + (size_t)B * h->cfg.act_dim,
+                           e + (size_t)(R + rep) * B * h->cfg.act_dim, n, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+  } else {
+    sample_indices_kernel<<<R, 256, 0, st>>>(h->K, h->cnt, rb->d_fill, rb->cap_per_task, rb->d_idx, B, rb->seed);
+    ingest_rows_kernel<<<grid, block, 0, st>>>(h->K, h->ing, rb->rows, rb->rs_rows, h->row_stride, rb->d_idx, B);
+  }
+  CU(cudaGetLastError());
+  return run_plan(h, st, use_eps);
+}
+
+static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* const* p, int np, b200sac_replay* rb) {
+  GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.variant = variant;
+  for (int i = 0; i < np && i < 9; ++i) key.p[i] = p[i];
+  if (rb) key.p[8] = rb;
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    if (h->graphs.size() >= 64) {   // bound the cache: drop everything (pointers churn)
+      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+      h->graphs.clear();
+    }
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_body(h, st, variant, p, rb);
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(B200SAC_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    cudaGraphExec_t ge = nullptr;
+    e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(B200SAC_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    it = h->graphs.emplace(key, ge).first;
+  }
+  CU(cudaGraphLaunch(it->second, st));
+  h->host_steps += 1;
+  return 0;
+}
+
+extern "C" int b200sac_step(b200sac_t* h, const float* s, const float* a, const float* r, const float* s2, const float* d,
+                            const float* eps_next, const float* eps_cur, void* stream) {
+  if (!h || !s || !a || !r || !s2 || !d) return fail(B200SAC_ERR_INVALID, "null minibatch pointer");
+  if ((eps_next == nullptr) != (eps_cur == nullptr)) return fail(B200SAC_ERR_INVALID, "eps_next and eps_cur must both be given or both NULL");
+  CU(cudaSetDevice(h->device));
+  const void* p[7] = {s, a, r, s2, d, eps_next, eps_cur};
+  StreamBridge sb(h, stream);
+  if (int rc = sb.begin()) return rc;
+  if (int rc = launch_step(h, sb.run, 0, p, 7, nullptr)) return rc;
+  return sb.end();
+}
+
+// pack one replica-major minibatch into packed rows in pinned staging
+static void pack_rows(const b200sac* h, float* dst, const float* s, const float* a, const float* r, const float* s2,
+                      const float* d) {
+  const int B = h->cfg.batch, R = h->R, obs = h->K.obs, A = h->K.act, rs = h->row_stride;
+  for (long long i = 0; i < (long long)R * B; ++i) {
+    float* row = dst + i * rs;
+    memcpy(row, s + i * obs, obs * sizeof(float));
+    memcpy(row + obs, a + i * A, A * sizeof(float));
+    row[obs + A] = r[i];
+    memcpy(row + obs + A + 1, s2 + i * obs, obs * sizeof(float));
+    row[2 * obs + A + 1] = d[i];
+  }
+}
+
+// stage slot -> device on the side stream, make `st` wait for it, run the step from the staged rows
+static int staged_step(b200sac* h, cudaStream_t st, int slot, bool with_eps) {
+  const size_t rows_f = (size_t)h->R * h->cfg.batch * h->row_stride;
+  const size_t eps_f = (size_t)2 * h->R * h->cfg.batch * h->cfg.act_dim;
+  CU(cudaMemcpyAsync(h->stage_d[slot], h->stage_h[slot], (rows_f + (with_eps ? eps_f : 0)) * sizeof(float),
+                     cudaMemcpyHostToDevice, h->side));
+  CU(cudaEventRecord(h->ev_copied[slot], h->side));
+  CU(cudaStreamWaitEvent(st, h->ev_copied[slot], 0));
+  const void* p[2] = {h->stage_d[slot], with_eps ? h->stage_d[slot] + rows_f : nullptr};
+  if (int rc = launch_step(h, st, 1, p, 2, nullptr)) return rc;
+  CU(cudaEventRecord(h->ev_consumed[slot], st));
+  h->stage_used[slot] = true;
+  return 0;
+}
+
+static int acquire_slot(b200sac* h, int* slot) {
+  int s = h->stage_slot;
+  h->stage_slot ^= 1;
+  if (h->stage_used[s]) {
+    CU(cudaEventSynchronize(h->ev_consumed[s]));          // host may overwrite the pinned slot
+    CU(cudaStreamWaitEvent(h->side, h->ev_consumed[s], 0));   // and the side stream the device slot
+  }
+  *slot = s;
+  return 0;
+}
+
+static int fetch_losses(b200sac* h, cudaStream_t st, int n_last, float* out) {
+  if (n_last < 1 || n_last > kLossSlots || n_last > h->host_steps)
+    return fail(B200SAC_ERR_INVALID, "n_last=%d out of range (steps so far %lld, ring %d)", n_last, h->host_steps, kLossSlots);
+  const size_t per = (size_t)h->R * 4;
+  for (int i = 0; i < n_last; ++i) {
+    const long long step = h->host_steps - n_last + i;
+    const long long slot = step % kLossSlots;
+    CU(cudaMemcpyAsync(h->loss_h + (size_t)i * per, h->losses + (size_t)slot * per, per * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  memcpy(out, h->loss_h, (size_t)n_last * per * sizeof(float));
+  return 0;
+}
+
+extern "C" int b200sac_step_host(b200sac_t* h, const float* s, const float* a, const float* r, const float* s2,
+                                 const float* d, const float* eps_next, const float* eps_cur, float* out_losses, void* stream) {
+  if (!h || !s || !a || !r || !s2 || !d) return fail(B200SAC_ERR_INVALID, "null minibatch pointer");
+  if ((eps_next == nullptr) != (eps_cur == nullptr)) return fail(B200SAC_ERR_INVALID, "eps_next and eps_cur must both be given or both NULL");
+  CU(cudaSetDevice(h->device));
+  StreamBridge sb(h, stream);
+  if (int rc = sb.begin()) return rc;
+  cudaStream_t st = sb.run;
+  int slot;
+  if (int rc = acquire_slot(h, &slot)) return rc;
+  pack_rows(h, h->stage_h[slot], s, a, r, s2, d);
+  if (eps_next) {
+    const size_t rows_f = (size_t)h->R * h->cfg.batch * h->row_stride;
+    const size_t n = (size_t)h->R * h->cfg.batch * h->cfg.act_dim;
+    memcpy(h->stage_h[slot] + rows_f, eps_next, n * sizeof(float));
+    memcpy(h->stage_h[slot] + rows_f + n, eps_cur, n * sizeof(float));
+  }
+  if (int rc = staged_step(h, st, slot, eps_next != nullptr)) return rc;
+  if (out_losses)
+    if (int rc = fetch_losses(h, st, 1, out_losses)) return rc;
+  return sb.end();
+}
+
+extern "C" int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host, void* stream) {
+  if (!h || !out_host) return fail(B200SAC_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  return fetch_losses(h, (cudaStream_t)stream, n_last, out_host);
+}
+
+extern "C" int b200sac_soft_update(b200sac_t* h, double tau, void* stream) {
+  if (!h) return fail(B200SAC_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(h->device));
+  polyak_kernel<<<dim3(128, h->R), 256, 0, (cudaStream_t)stream>>>(h->params + h->L.critic_begin, h->L.arena, h->L.critic_n,
+                                                                   h->L.target_delta, (float)tau, (float)(1.0 - tau));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200sac_debug_read(b200sac_t* h, const char* name, int32_t replica, float* out_host, int64_t cap_floats,
+                                  int64_t* n_floats, void* stream) {
+  if (!h || !name || !out_host) return fail(B200SAC_ERR_INVALID, "null argument");
+  if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica out of range");
+  CU(cudaSetDevice(h->device));
+  const int B = h->cfg.batch, A = h->cfg.act_dim;
+  const float* src = nullptr;
+  int64_t n = 0;
+  std::string nm(name);
+  if (nm == "y") { src = h->y.p + replica * h->y.rs; n = B; }
+  else if (nm == "q1") { src = h->q.p + replica * h->q.rs; n = B; }
+  else if (nm == "q2") { src = h->q.p + replica * h->q.rs + B; n = B; }
+  else if (nm == "a_next") { src = h->act_out.p + replica * h->act_out.rs; n = (int64_t)B * A; }
+  else if (nm == "a_cur") { src = h->act_out.p + replica * h->act_out.rs + (int64_t)B * A; n = (int64_t)B * A; }
+  else if (nm == "logp_next") { src = h->logp.p + replica * h->logp.rs; n = B; }
+  else if (nm == "logp_cur") { src = h->logp.p + replica * h->logp.rs + B; n = B; }
+  else if (nm == "r") { src = h->r.p + replica * h->r.rs; n = B; }
+  else if (nm == "d") { src = h->d.p + replica * h->d.rs; n = B; }
+  else if (nm == "qmin") { src = h->qmin.p + replica * h->qmin.rs; n = B; }
+  else if (nm == "d_action") { src = h->dact_dbg.p + replica * h->dact_dbg.rs; n = (int64_t)B * A; }
+  else if (nm == "d_head") { src = h->dout_dbg.p + replica * h->dout_dbg.rs; n = (int64_t)B * 2 * A; }
+  else return fail(B200SAC_ERR_INVALID, "unknown debug tensor '%s'", name);
+  if (n_floats) *n_floats = n;
+  if (cap_floats < n) return fail(B200SAC_ERR_INVALID, "buffer too small: need %lld floats", (long long)n);
+  CU(cudaMemcpyAsync(out_host, src, n * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// replay ring
+// ------------------------------------------------------------------------------------------
+extern "C" int b200sac_replay_create(b200sac_t* h, int64_t capacity, int32_t where, uint64_t seed, b200sac_replay_t** out) {
+  if (!h || !out) return fail(B200SAC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (where != 0 && where != 1) return fail(B200SAC_ERR_INVALID, "where must be 0 (device) or 1 (pinned host)");
+  const int Teff = h->cfg.num_tasks > 0 ? h->cfg.num_tasks : 1;
+  if (capacity / Teff < 4LL * (h->cfg.batch / Teff))
+    return fail(B200SAC_ERR_INVALID, "capacity %lld too small for batch %d", (long long)capacity, h->cfg.batch);
+  if ((long long)capacity > 0x7fffffffLL) return fail(B200SAC_ERR_INVALID, "capacity must fit in int32");
+  CU(cudaSetDevice(h->device));
+  b200sac_replay* rb = new (std::nothrow) b200sac_replay();
+  if (!rb) return fail(B200SAC_ERR_NOMEM, "out of host memory");
+  rb->h = h; rb->where = where; rb->Teff = Teff;
+  rb->cap_per_task = capacity / Teff;
+  rb->cap = rb->cap_per_task * Teff;
+  rb->rs_rows = rb->cap * h->row_stride;
+  rb->seed = seed;
+  rb->rng.seed(seed);
+  rb->fill.assign((size_t)h->R * Teff, 0);
+  rb->head.assign((size_t)h->R * Teff, 0);
+  const size_t bytes = (size_t)h->R * rb->rs_rows * sizeof(float);
+  cudaError_t e = where == 0 ? cudaMalloc(&rb->rows, bytes) : cudaMallocHost(&rb->rows, bytes);
+  if (e != cudaSuccess) { delete rb; return fail(B200SAC_ERR_NOMEM, "replay allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); }
+  if (where == 0) {
+    if (cudaMalloc(&rb->d_fill, sizeof(long long) * h->R * Teff) != cudaSuccess ||
+        cudaMalloc(&rb->d_idx, sizeof(int) * h->R * h->cfg.batch) != cudaSuccess ||
+        cudaMemset(rb->d_fill, 0, sizeof(long long) * h->R * Teff) != cudaSuccess) {
+      cudaFree(rb->rows); cudaFree(rb->d_fill); cudaFree(rb->d_idx);
+      delete rb;
+      return fail(B200SAC_ERR_NOMEM, "replay index allocation failed");
+    }
+  }
+  *out = rb;
+  return 0;
+}
+
+extern "C" int b200sac_replay_destroy(b200sac_replay_t* rb) {
+  if (!rb) return 0;
+  cudaSetDevice(rb->h->device);
+  // graphs that captured this ring's pointers must go
+  for (auto it = rb->h->graphs.begin(); it != rb->h->graphs.end();) {
+    if (it->first.p[8] == rb) { cudaGraphExecDestroy(it->second); it = rb->h->graphs.erase(it); }
+    else ++it;
+  }
+  if (rb->where == 0) cudaFree(rb->rows); else cudaFreeHost(rb->rows);
+  cudaFree(rb->d_fill); cudaFree(rb->d_idx);
+  delete rb;
+  return 0;
+}
+
+extern "C" int b200sac_replay_push(b200sac_replay_t* rb, int32_t replica, int64_t n, const float* s, const float* a,
+                                   const float* r, const float* s2, const float* d) {
+  if (!rb || !s || !a || !r || !s2 || !d) return fail(B200SAC_ERR_INVALID, "null argument");
+  b200sac* h = rb->h;
+  if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica out of range");
+  CU(cudaSetDevice(h->device));
+  const int obs = h->K.obs, A = h->K.act, T = h->cfg.num_tasks, rs = h->row_stride;
+  std::vector<float> row((size_t)rs, 0.f);
+  std::lock_guard<std::mutex> lk(rb->mu);
+  for (int64_t i = 0; i < n; ++i) {
+    memcpy(row.data(), s + i * obs, obs * sizeof(float));
+    memcpy(row.data() + obs, a + i * A, A * sizeof(float));
+    row[obs + A] = r[i];
+    memcpy(row.data() + obs + A + 1, s2 + i * obs, obs * sizeof(float));
+    row[2 * obs + A + 1] = d[i];
+    int task = 0;
+    if (T > 0) {
+      float best = row[obs - T];
+      for (int q = 1; q < T; ++q)
+        if (row[obs - T + q] > best) { best = row[obs - T + q]; task = q; }
+    }
+    long long& hd = rb->head[(size_t)replica * rb->Teff + task];
+    long long& fl = rb->fill[(size_t)replica * rb->Teff + task];
+    float* dst = rb->rows + (size_t)replica * rb->rs_rows + ((size_t)task * rb->cap_per_task + hd) * rs;
+    if (rb->where == 0) CU(cudaMemcpy(dst, row.data(), rs * sizeof(float), cudaMemcpyHostToDevice));
+    else memcpy(dst, row.data(), rs * sizeof(float));
+    hd = (hd + 1) % rb->cap_per_task;
+    if (fl < rb->cap_per_task) fl += 1;
+  }
+  if (rb->where == 0)
+    CU(cudaMemcpy(rb->d_fill + (size_t)replica * rb->Teff, rb->fill.data() + (size_t)replica * rb->Teff,
+                  sizeof(long long) * rb->Teff, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int b200sac_replay_fill_synthetic(b200sac_replay_t* rb, int64_t n, uint64_t seed, void* stream) {
+  if (!rb) return fail(B200SAC_ERR_INVALID, "null argument");
+  b200sac* h = rb->h;
+  CU(cudaSetDevice(h->device));
+  long long per = n / rb->Teff;
+  if (per > rb->cap_per_task) per = rb->cap_per_task;
+  if (per < 1) return fail(B200SAC_ERR_INVALID, "n too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dev_rows = rb->rows;
+  float* tmp = nullptr;
+  if (rb->where == 1) {   // generate on the device, copy down into the pinned ring
+    CU(cudaMalloc(&tmp, (size_t)h->R * rb->rs_rows * sizeof(float)));
+    dev_rows = tmp;
+  }
+  CU(cudaMemsetAsync(dev_rows, 0, (size_t)h->R * rb->rs_rows * sizeof(float), st));
+  fill_synthetic_kernel<<<dim3(592, h->R), 256, 0, st>>>(dev_rows, rb->rs_rows, h->row_stride, per, rb->cap_per_task,
+                                                        h->cfg.state_dim, h->cfg.act_dim, h->cfg.num_tasks, seed);
+  CU(cudaGetLastError());
+  if (rb->where == 1) {
+    CU(cudaMemcpyAsync(rb->rows, tmp, (size_t)h->R * rb->rs_rows * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaFree(tmp));
+  }
+  std::lock_guard<std::mutex> lk(rb->mu);
+  for (auto& f : rb->fill) f = per;
+  for (auto& hd : rb->head) hd = per % rb->cap_per_task;
+  if (rb->where == 0)
+    CU(cudaMemcpyAsync(rb->d_fill, rb->fill.data(), sizeof(long long) * rb->fill.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int b200sac_replay_size(b200sac_replay_t* rb, int32_t replica, int64_t* n) {
+  if (!rb || !n || replica < 0 || replica >= rb->h->R) return fail(B200SAC_ERR_INVALID, "bad argument");
+  std::lock_guard<std::mutex> lk(rb->mu);
+  long long mn = rb->fill[(size_t)replica * rb->Teff];
+  for (int t = 1; t < rb->Teff; ++t) mn = std::min(mn, rb->fill[(size_t)replica * rb->Teff + t]);
+  *n = rb->Teff > 1 ? mn : rb->fill[(size_t)replica * rb->Teff];
+  return 0;
+}
+
+// host-side index draw: uniform without replacement, per task (random.sample semantics)
+static int host_draw(b200sac_replay* rb, int replica, std::vector<long long>& idx) {
+  const int B = rb->h->cfg.batch, per = B / rb->Teff;
+  idx.clear();
+  for (int t = 0; t < rb->Teff; ++t) {
+    const long long n = rb->fill[(size_t)replica * rb->Teff + t];
+    if (n < per) return fail(B200SAC_ERR_STATE, "replay holds %lld transitions for task %d, need %d", n, t, per);
+    std::unordered_set<long long> seen;
+    while ((int)seen.size() < per) {
+      const long long v = (long long)(rb->rng() % (unsigned long long)n);
+      if (seen.insert(v).second) idx.push_back((long long)t * rb->cap_per_task + v);
+    }
+  }
+  if (rb->Teff > 1) std::shuffle(idx.begin(), idx.end(), rb->rng);   // MS/replay_buffers.py:83-84
+  return 0;
+}
+
+extern "C" int b200sac_replay_sample(b200sac_replay_t* rb, int32_t replica, float* s, float* a, float* r, float* s2,
+                                     float* d, int64_t* idx_out) {
+  if (!rb || !s || !a || !r || !s2 || !d) return fail(B200SAC_ERR_INVALID, "null argument");
+  b200sac* h = rb->h;
+  if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica out of range");
+  CU(cudaSetDevice(h->device));
+  const int B = h->cfg.batch, obs = h->K.obs, A = h->K.act, rs = h->row_stride;
+  std::vector<long long> idx;
+  std::vector<float> row((size_t)rs);
+  std::lock_guard<std::mutex> lk(rb->mu);
+  if (int rc = host_draw(rb, replica, idx)) return rc;
+  for (int i = 0; i < B; ++i) {
+    const float* src = rb->rows + (size_t)replica * rb->rs_rows + (size_t)idx[i] * rs;
+    if (rb->where == 0) { CU(cudaMemcpy(row.data(), src, rs * sizeof(float), cudaMemcpyDeviceToHost)); src = row.data(); }
+    memcpy(s + (size_t)i * obs, src, obs * sizeof(float));
+    memcpy(a + (size_t)i * A, src + obs, A * sizeof(float));
+    r[i] = src[obs + A];
+    memcpy(s2 + (size_t)i * obs, src + obs + A + 1, obs * sizeof(float));
+    d[i] = src[2 * obs + A + 1];
+    if (idx_out) idx_out[i] = idx[i];
+  }
+  return 0;
+}
+
+extern "C" int b200sac_step_sampled(b200sac_t* h, b200sac_replay_t* rb, int32_t n_steps, void* stream) {
+  if (!h || !rb || rb->h != h) return fail(B200SAC_ERR_INVALID, "bad handle");
+  if (n_steps < 1) return fail(B200SAC_ERR_INVALID, "n_steps < 1");
+  CU(cudaSetDevice(h->device));
+  StreamBridge sb(h, stream);
+  if (int rc = sb.begin()) return rc;
+  cudaStream_t st = sb.run;
+  const int B = h->cfg.batch, per = B / rb->Teff;
+  {
+    std::lock_guard<std::mutex> lk(rb->mu);
+    for (auto f : rb->fill)
+      if (f < 4LL * per)
+        return fail(B200SAC_ERR_STATE, "replay not ready: a ring holds %lld transitions, need >= %d (4 x per-task batch)", f, 4 * per);
+  }
+  if (rb->where == 0) {
+    const void* p[1] = {rb->rows};
+    for (int i = 0; i < n_steps; ++i)
+      if (int rc = launch_step(h, st, 2, p, 1, rb)) return rc;
+    return sb.end();
+  }
+  // pinned-host ring: draw + gather on the host into the pinned slot, H2D on the side stream
+  std::vector<long long> idx;
+  const int rs = h->row_stride;
+  for (int i = 0; i < n_steps; ++i) {
+    int slot;
+    if (int rc = acquire_slot(h, &slot)) return rc;
+    {
+      std::lock_guard<std::mutex> lk(rb->mu);
+      for (int rep = 0; rep < h->R; ++rep) {
+        if (int rc = host_draw(rb, rep, idx)) return rc;
+        float* dst = h->stage_h[slot] + (size_t)rep * B * rs;
+        const float* base = rb->rows + (size_t)rep * rb->rs_rows;
+        for (int j = 0; j < B; ++j) memcpy(dst + (size_t)j * rs, base + (size_t)idx[j] * rs, rs * sizeof(float));
+      }
+    }
+    if (int rc = staged_step(h, st, slot, false)) return rc;
+  }
+  return sb.end();
+}

@@ -1,0 +1,64 @@
+// Shared device/host helpers for the B200 SAC learner kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bsac {
+
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_D __device__ __forceinline__
+
+constexpr int kWarp = 32;
+
+// ---------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (in-kernel noise + replay index sampling).
+// ---------------------------------------------------------------------------------
+struct Philox {
+  uint32_t key[2];
+  B200_HD Philox(uint64_t seed) {
+    key[0] = (uint32_t)seed;
+    key[1] = (uint32_t)(seed >> 32);
+  }
+  B200_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  // counter = (c0, c1, c2, c3) -> 4 x 32 random bits
+  B200_HD void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
+    uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(0xD2511F53u, c0, hi0, lo0);
+      mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+
+B200_HD float u01(uint32_t x) {  // (0, 1]
+  return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+// two independent N(0,1) from two 32-bit words (Box-Muller)
+B200_D void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  float u = u01(a), v = u01(b);
+  float r = sqrtf(-2.0f * logf(u));
+  float s, c;
+  sincosf(6.28318530717958647692f * v, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+B200_D float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace bsac

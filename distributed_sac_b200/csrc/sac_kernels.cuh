@@ -1,0 +1,727 @@
+// Fused non-GEMM stages of the SAC gradient step: minibatch ingest / replay sampling,
+// policy head (reparameterise + tanh squash + log-prob), critic heads (TD target, MSE
+// gradient), actor-pass heads (min-Q), small-N layer backward, Adam (+Polyak) and the
+// temperature update.  Everything that the reference evaluates in fp32 in an
+// ill-conditioned way (1 - tanh^2 + 1e-6, u - mu) is evaluated in the SAME order here,
+// transcendental functions are computed in fp64 and rounded once (== torch CPU's result on
+// >98 % of inputs) and the file is compiled with -fmad=false so that only explicit fmaf()
+// fuses.  Math reference: oracle/sac_manual.py; reference sites cited per kernel.
+#pragma once
+#include "common.cuh"
+
+namespace bsac {
+
+constexpr int kMaxAct = 8;      // act_dim <= 8  (head width 2*act <= 16)
+constexpr int kMaxHeadOut = 16;
+constexpr int kSaveW = 8;       // floats saved per (row, action) by the policy head
+constexpr int kLossSlots = 1024;
+
+// Per-learner constant block (device copy lives in the handle).
+struct StepConst {
+  int B, obs, act, T, xw;         // xw = obs + act
+  int Ha, Hc;                     // last hidden widths (actor / critic)
+  float gamma, reward_scale, action_scale;
+  float c_loss;                   // 1/B or 1/B^2 (weighted_loss)
+  float inv_B;
+  float tau, one_minus_tau;
+  float hbar;                     // -act
+  double lr_actor, lr_critic, lr_alpha, beta1, beta2, adam_eps;
+  unsigned long long seed;
+};
+
+// Mutable per-replica counters in device memory: [0..2] Adam steps critic/actor/alpha, [3] step index.
+struct Counters { long long v[4]; };
+
+// ------------------------------------------------------------------------------------------
+// Ingest: scatter one minibatch into the four pre-concatenated layer-0 inputs
+//   XA [2B][obs]   = [s2 ; s]          (actor runs once over both halves)
+//   XQ [B][obs+act] = [s | a]           critic update pass
+//   XT [B][obs+act] = [s2 | a_next]     target pass   (a_next filled by the policy head)
+//   XP [B][obs+act] = [s | a_cur]       actor pass    (a_cur  filled by the policy head)
+// plus r, d, task id (argmax of the one-hot, MT10_Distributed_MTSAC/src/model.py:105-106) and
+// the noise buffer.  Also bumps the Adam step counters (torch increments before use).
+// Replaces ReplayBuffer.sample()'s 5x vstack + .to(device) (LL/replay_buffer.py:63-73).
+// ------------------------------------------------------------------------------------------
+struct IngestOut {
+  float *XA, *XQ, *XT, *XP, *r, *d, *eps;   // replica 0 bases
+  int* tid;
+  Counters* cnt;
+  long long rsXA, rsXQ, rsR, rsEps;          // per-replica strides
+};
+
+B200_D void ingest_row(const StepConst& K, const IngestOut& O, int rep, int i, const float* s, const float* a,
+                       float r, const float* s2, float d, int lane, int nl) {
+  const int obs = K.obs, act = K.act, xw = K.xw, B = K.B;
+  float* XA = O.XA + rep * O.rsXA;
+  float* XQ = O.XQ + rep * O.rsXQ;
+  float* XT = O.XT + rep * O.rsXQ;
+  float* XP = O.XP + rep * O.rsXQ;
+  for (int j = lane; j < obs; j += nl) {
+    float v = s[j], v2 = s2[j];
+    XA[(long long)i * obs + j] = v2;
+    XA[(long long)(B + i) * obs + j] = v;
+    XQ[(long long)i * xw + j] = v;
+    XP[(long long)i * xw + j] = v;
+    XT[(long long)i * xw + j] = v2;
+  }
+  for (int j = lane; j < act; j += nl) XQ[(long long)i * xw + obs + j] = a[j];
+  if (lane == 0) {
+    (O.r + rep * O.rsR)[i] = r;
+    (O.d + rep * O.rsR)[i] = d;
+    int t = 0;
+    if (K.T > 0) {                       // first maximum, like torch.argmax
+      float best = s[obs - K.T];
+      for (int q = 1; q < K.T; ++q) {
+        float v = s[obs - K.T + q];
+        if (v > best) { best = v; t = q; }
+      }
+    }
+    (O.tid + rep * O.rsR)[i] = t;
+  }
+}
+
+B200_D void bump_counters(Counters* cnt, int rep) {
+  Counters* c = cnt + rep;
+  c->v[0] += 1; c->v[1] += 1; c->v[2] += 1; c->v[3] += 1;
+}
+
+// minibatch given as five separate arrays [R][B][w]
+__global__ void ingest_split_kernel(StepConst K, IngestOut O, const float* __restrict__ s,
+                                    const float* __restrict__ a, const float* __restrict__ r,
+                                    const float* __restrict__ s2, const float* __restrict__ d,
+                                    const float* __restrict__ eps_next, const float* __restrict__ eps_cur) {
+  const int rep = blockIdx.y;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
+  const int B = K.B;
+  if (blockIdx.x == 0 && threadIdx.x == 0) bump_counters(O.cnt, rep);
+  for (int i = blockIdx.x * wpb + warp; i < B; i += gridDim.x * wpb) {
+    const long long ri = (long long)rep * B + i;
+    ingest_row(K, O, rep, i, s + ri * K.obs, a + ri * K.act, r[ri], s2 + ri * K.obs, d[ri], lane, 32);
+    if (eps_next != nullptr) {
+      float* E = O.eps + rep * O.rsEps;
+      for (int j = lane; j < K.act; j += 32) {
+        E[(long long)i * K.act + j] = eps_next[ri * K.act + j];
+        E[(long long)(B + i) * K.act + j] = eps_cur[ri * K.act + j];
+      }
+    }
+  }
+}
+
+// minibatch given as packed rows [s | a | r | s2 | d] (+pad), either gathered through idx
+// (device replay ring) or dense (pinned-host staging after the H2D copy).
+__global__ void ingest_rows_kernel(StepConst K, IngestOut O, const float* __restrict__ rows, long long rs_rows,
+                                   int row_stride, const int* __restrict__ idx, long long rs_idx) {
+  const int rep = blockIdx.y;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
+  const int B = K.B;
+  if (blockIdx.x == 0 && threadIdx.x == 0) bump_counters(O.cnt, rep);
+  for (int i = blockIdx.x * wpb + warp; i < B; i += gridDim.x * wpb) {
+    const long long src = idx ? (long long)idx[rep * rs_idx + i] : (long long)i;
+    const float* row = rows + rep * rs_rows + src * row_stride;
+    ingest_row(K, O, rep, i, row, row + K.obs, row[K.obs + K.act], row + K.obs + K.act + 1,
+               row[2 * K.obs + K.act + 1], lane, 32);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Replay index sampling: uniform WITHOUT replacement (random.sample, LL/replay_buffer.py:65),
+// per task B/T when T > 0 (MS/replay_buffers.py:73-74).  One CTA per replica.  Duplicates are
+// resolved deterministically (lowest batch slot keeps a contested index, the others redraw
+// with the next Philox sub-counter), so a given (seed, step) always yields the same minibatch.
+// ------------------------------------------------------------------------------------------
+constexpr int kHashSlots = 4096;   // >= 2 * max batch (batch <= 2048)
+
+__global__ void sample_indices_kernel(StepConst K, const Counters* __restrict__ cnt, const long long* __restrict__ fill,
+                                      long long cap_per_task, int* __restrict__ idx_out, long long rs_idx,
+                                      unsigned long long seed) {
+  __shared__ int keys[kHashSlots];
+  __shared__ int owner[kHashSlots];
+  __shared__ int unresolved;
+  const int rep = blockIdx.x;
+  const int B = K.B, Teff = K.T > 0 ? K.T : 1, per = B / Teff;
+  const long long step = cnt[rep].v[3];   // value BEFORE this step's bump
+  Philox ph(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(rep + 1));
+  int* out = idx_out + rep * rs_idx;
+  for (int i = threadIdx.x; i < kHashSlots; i += blockDim.x) { keys[i] = -1; owner[i] = 0x7fffffff; }
+  // per-slot state lives in registers of the thread that owns slots i = threadIdx.x + j*blockDim.x
+  constexpr int kMaxPer = 8;     // batch <= 8 * blockDim.x
+  int cur[kMaxPer], att[kMaxPer], pos[kMaxPer];
+  bool done[kMaxPer];
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) { att[j] = 0; done[j] = false; cur[j] = -1; pos[j] = 0; }
+  __syncthreads();
+  for (int round = 0; round < 64; ++round) {
+    if (threadIdx.x == 0) unresolved = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j) {
+      const int i = threadIdx.x + j * blockDim.x;
+      if (i >= B || done[j]) continue;
+      const int task = i / per;
+      const long long n = fill[rep * Teff + (task < Teff ? task : Teff - 1)];
+      uint32_t rnd[4];
+      ph((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)i, (uint32_t)att[j], rnd);
+      const unsigned long long r64 = ((unsigned long long)rnd[0] << 32) | rnd[1];
+      const long long local = (long long)(r64 % (unsigned long long)n);
+      const int key = (int)((long long)task * cap_per_task + local);
+      cur[j] = key;
+      unsigned h = ((unsigned)key * 2654435761u) >> 20;   // 12 bits
+      int probes = 0;
+      for (; probes < kHashSlots; ++probes) {
+        int prev = atomicCAS(&keys[h], -1, key);
+        if (prev == -1 || prev == key) break;
+        h = (h + 1) & (kHashSlots - 1);
+      }
+      if (probes == kHashSlots) {     // table full (cannot happen for fill >= 4 * batch): accept the draw
+        pos[j] = -1;
+        continue;
+      }
+      pos[j] = (int)h;
+      atomicMin(&owner[h], i);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j) {
+      const int i = threadIdx.x + j * blockDim.x;
+      if (i >= B || done[j]) continue;
+      out[i] = cur[j];                 // always leave a valid index behind
+      if (pos[j] < 0 || owner[pos[j]] == i) {
+        done[j] = true;
+      } else {
+        att[j] += 1;
+        atomicAdd(&unresolved, 1);
+      }
+    }
+    __syncthreads();
+    // winners lock their table entry so that a lower slot redrawing later cannot steal it
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j) {
+      const int i = threadIdx.x + j * blockDim.x;
+      if (i < B && done[j] && pos[j] >= 0 && owner[pos[j]] == i) owner[pos[j]] = -1;
+    }
+    __syncthreads();
+    if (unresolved == 0) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Policy head: last actor layer (width 2*act) + rsample + tanh squash + log-prob, one warp per
+// row over the 2B rows [s2 ; s].  LL/model.py:38-65 (Actor.forward, get_action_log_prob),
+// MS/model.py:35-56.  Writes the action into the critic input buffers (XT for the s2 half, XP
+// for the s half) so no concat is ever materialised.
+// ------------------------------------------------------------------------------------------
+struct PolicyHeadArgs {
+  const float* h; long long rsH; int ldh;     // last hidden activations [2B][Ha]
+  const float* W; const float* b; long long rsP;   // head weight [2A][Ha], bias; param-arena replica stride
+  const float* eps; long long rsEps;          // [2B][A] (used when use_eps_buf != 0)
+  int use_eps_buf;
+  float* pout; long long rsPout;              // [2B][2A] raw head output
+  float* psave; long long rsSave;             // [2B][A][kSaveW]
+  float* XT; float* XP; long long rsX;
+  float* act_out; long long rsAct;            // [2B][A]
+  float* logp; long long rsLogp;              // [2B]
+  float* logstd_sum;                          // [2B] sum_j log(std) (entropy statistic, MS/learner.py:310)
+  const Counters* cnt;
+};
+
+struct PolicyPoint {   // everything the backward needs for one (row, action)
+  float std, diff, t, act, jac, eps, mask, logp_j, logstd;
+};
+
+B200_D PolicyPoint policy_point(float mu, float raw, float eps, float k) {
+  PolicyPoint p;
+  const float ls = fminf(fmaxf(raw, -20.f), 2.f);          // torch.clamp(x, -20, 2)
+  p.mask = (raw >= -20.f && raw <= 2.f) ? 1.f : 0.f;
+  p.std = (float)exp((double)ls);
+  p.eps = eps;
+  const float u = mu + p.std * eps;                        // Normal.rsample: loc + eps * scale
+  p.t = (float)tanh((double)u);
+  p.act = k * p.t;
+  p.diff = u - mu;                                         // as rounded, NOT std*eps
+  const float var = p.std * p.std;
+  p.logstd = (float)log((double)p.std);
+  const float gauss = -(p.diff * p.diff) / (2.f * var) - p.logstd - 0.91893853320467274178f;
+  const float q = p.act / k;
+  p.jac = k * (1.f - q * q + 1e-6f);
+  p.logp_j = gauss - (float)log((double)p.jac);
+  return p;
+}
+
+__global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
+  const int rep = blockIdx.y;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = blockIdx.x * (blockDim.x / 32) + warp;
+  const int B = K.B, A = K.act, NO = 2 * K.act, H = K.Ha;
+  if (row >= 2 * B) return;
+  const float* hr = P.h + rep * P.rsH + (long long)row * P.ldh;
+  const float* W = P.W + rep * P.rsP;
+  const float* bias = P.b + rep * P.rsP;
+  float acc[kMaxHeadOut];
+#pragma unroll
+  for (int j = 0; j < kMaxHeadOut; ++j) acc[j] = 0.f;
+  for (int k = lane; k < H; k += 32) {
+    const float hv = hr[k];
+#pragma unroll
+    for (int j = 0; j < kMaxHeadOut; ++j)
+      if (j < NO) acc[j] = fmaf(hv, __ldg(W + (long long)j * H + k), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxHeadOut; ++j)
+    if (j < NO) acc[j] = warp_sum(acc[j]) + bias[j];
+  // lane j < A owns action j
+  float mu = 0.f, raw = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxAct; ++j) {
+    if (j < A && lane == j) { mu = acc[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxAct; ++j) {
+    if (j < A && lane == j) { raw = acc[A + j]; }
+  }
+  float lp = 0.f, lsd = 0.f;
+  if (lane < A) {
+    float e;
+    if (P.use_eps_buf) {
+      e = (P.eps + rep * P.rsEps)[(long long)row * A + lane];
+    } else {
+      Philox ph(K.seed ^ (0xA0761D6478BD642Full * (unsigned long long)(rep + 1)));
+      const long long step = P.cnt[rep].v[3];
+      uint32_t rnd[4];
+      ph((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)row, 0x51u + (uint32_t)lane, rnd);
+      float z0, z1;
+      box_muller(rnd[0], rnd[1], z0, z1);
+      e = z0;
+    }
+    const PolicyPoint p = policy_point(mu, raw, e, K.action_scale);
+    lp = p.logp_j;
+    lsd = p.logstd;
+    float* sv = P.psave + rep * P.rsSave + ((long long)row * A + lane) * kSaveW;
+    sv[0] = p.std; sv[1] = p.diff; sv[2] = p.t; sv[3] = p.act; sv[4] = p.jac; sv[5] = p.eps; sv[6] = p.mask;
+    sv[7] = p.logp_j;
+    (P.act_out + rep * P.rsAct)[(long long)row * A + lane] = p.act;
+    float* pout = P.pout + rep * P.rsPout + (long long)row * NO;
+    pout[lane] = mu;
+    pout[A + lane] = raw;
+    if (row < B) (P.XT + rep * P.rsX)[(long long)row * K.xw + K.obs + lane] = p.act;
+    else (P.XP + rep * P.rsX)[(long long)(row - B) * K.xw + K.obs + lane] = p.act;
+  }
+  // sum over actions in index order (lane 0 accumulates j = 0..A-1)
+  float tot = 0.f, tls = 0.f;
+  for (int j = 0; j < A; ++j) {
+    tot += __shfl_sync(0xffffffffu, lp, j);
+    tls += __shfl_sync(0xffffffffu, lsd, j);
+  }
+  if (lane == 0) {
+    (P.logp + rep * P.rsLogp)[row] = tot;
+    (P.logstd_sum + rep * P.rsLogp)[row] = tls;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Critic heads for the critic update: scalar heads of Qt1,Qt2 (target pass) and Q1,Q2 (s,a),
+// TD target and MSE gradient in one pass, one warp per row.
+//   y = rs*r + gamma*(1-d)*(min(Qt1,Qt2) - alpha*logp')          LL/learner.py:210
+//   dL/dQk = 2c (Qk - y)                                        LL/model.py:139-140
+// ------------------------------------------------------------------------------------------
+struct CriticHeadArgs {
+  const float* hT; const float* hQ; long long rsHnet, rsHrep; int ldh;   // [net][B][Hc] per replica
+  const float* Wt[2]; const float* bt[2]; const float* Wq[2]; const float* bq[2]; long long rsP;
+  const float* r; const float* d; const int* tid; long long rsR;
+  const float* logp; long long rsLogp;   // logp[0..B) = next-state half
+  const float* log_alpha;                // param arena pointer (per replica rsP)
+  float* y; float* q; float* dq; float* lq; long long rsY;   // y[B], q[2][B], dq[2][B], lq[B]
+};
+
+B200_D float warp_dot(const float* __restrict__ x, const float* __restrict__ w, int n, int lane) {
+  float a = 0.f;
+  for (int k = lane; k < n; k += 32) a = fmaf(x[k], __ldg(w + k), a);
+  return warp_sum(a);
+}
+
+__global__ void critic_heads_kernel(StepConst K, CriticHeadArgs P) {
+  const int rep = blockIdx.y;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = blockIdx.x * (blockDim.x / 32) + warp;
+  const int B = K.B, H = K.Hc;
+  if (row >= B) return;
+  const float* hT = P.hT + rep * P.rsHrep + (long long)row * P.ldh;
+  const float* hQ = P.hQ + rep * P.rsHrep + (long long)row * P.ldh;
+  const long long po = rep * P.rsP;
+  const float qt1 = warp_dot(hT, P.Wt[0] + po, H, lane) + (P.bt[0] + po)[0];
+  const float qt2 = warp_dot(hT + P.rsHnet, P.Wt[1] + po, H, lane) + (P.bt[1] + po)[0];
+  const float q1 = warp_dot(hQ, P.Wq[0] + po, H, lane) + (P.bq[0] + po)[0];
+  const float q2 = warp_dot(hQ + P.rsHnet, P.Wq[1] + po, H, lane) + (P.bq[1] + po)[0];
+  if (lane == 0) {
+    const int t = (P.tid + rep * P.rsR)[row];
+    const float alpha = (float)exp((double)(P.log_alpha + po)[t]);
+    const float r = (P.r + rep * P.rsR)[row], d = (P.d + rep * P.rsR)[row];
+    const float lp = (P.logp + rep * P.rsLogp)[row];
+    const float t1 = K.reward_scale * r;
+    const float t2 = K.gamma * (1.f - d);
+    const float t3 = fminf(qt1, qt2) - alpha * lp;
+    const float y = t1 + t2 * t3;
+    const float e1 = y - q1, e2 = y - q2;
+    float* Y = P.y + rep * P.rsY;
+    Y[row] = y;
+    float* Q = P.q + rep * 2 * P.rsY;
+    Q[row] = q1; Q[B + row] = q2;
+    float* DQ = P.dq + rep * 2 * P.rsY;
+    DQ[row] = 2.f * K.c_loss * (q1 - y);
+    DQ[B + row] = 2.f * K.c_loss * (q2 - y);
+    (P.lq + rep * P.rsY)[row] = e1 * e1 + e2 * e2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Actor-pass heads: Q1,Q2 at (s, a~) with the already-updated critics, min and its gradient
+// routing (LL/learner.py:222-223; torch.minimum backward: the smaller head gets the gradient,
+// ties split it), plus the per-row policy-loss term (LL/model.py:84-88).
+// ------------------------------------------------------------------------------------------
+struct ActorQHeadArgs {
+  const float* hP; long long rsHnet, rsHrep; int ldh;
+  const float* Wq[2]; const float* bq[2]; long long rsP;
+  const int* tid; long long rsR;
+  const float* logp; long long rsLogp;    // +B offset applied by the host: current-state half
+  const float* log_alpha;
+  float* dqa; float* la; float* qmin; long long rsY;   // dqa[2][B], la[B], qmin[B]
+};
+
+__global__ void actor_q_heads_kernel(StepConst K, ActorQHeadArgs P) {
+  const int rep = blockIdx.y;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = blockIdx.x * (blockDim.x / 32) + warp;
+  const int B = K.B, H = K.Hc;
+  if (row >= B) return;
+  const float* hP = P.hP + rep * P.rsHrep + (long long)row * P.ldh;
+  const long long po = rep * P.rsP;
+  const float q1 = warp_dot(hP, P.Wq[0] + po, H, lane) + (P.bq[0] + po)[0];
+  const float q2 = warp_dot(hP + P.rsHnet, P.Wq[1] + po, H, lane) + (P.bq[1] + po)[0];
+  if (lane == 0) {
+    const int t = (P.tid + rep * P.rsR)[row];
+    const float alpha = (float)exp((double)(P.log_alpha + po)[t]);
+    const float lp = (P.logp + rep * P.rsLogp)[row];
+    const float qm = fminf(q1, q2);
+    float g1, g2;
+    if (q1 == q2) { g1 = g2 = -0.5f * K.c_loss; }
+    else if (q1 < q2) { g1 = -K.c_loss; g2 = 0.f; }
+    else { g1 = 0.f; g2 = -K.c_loss; }
+    float* DQ = P.dqa + rep * 2 * P.rsY;
+    DQ[row] = g1; DQ[B + row] = g2;
+    (P.la + rep * P.rsY)[row] = -(qm - alpha * lp);
+    (P.qmin + rep * P.rsY)[row] = qm;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of a narrow output layer (N_out <= 16: the scalar Q heads and the 2*act policy
+// head).  One CTA per 32-column slab of the hidden width, looping over all rows:
+//   dh[m][k] = (sum_j dout[m][j] W[j][k]) * [h[m][k] > 0]
+//   dW[j][k] = sum_m dout[m][j] h[m][k],  db[j] = sum_m dout[m][j]
+// In policy mode dout is produced on the fly from d(action) and the values saved by the
+// policy head (closed-form backward of LL/model.py:50-60, oracle/sac_manual.py).
+// ------------------------------------------------------------------------------------------
+struct HeadBwdArgs {
+  int M, NO, Kdim, nets;
+  const float* dout; long long rsDoutNet, rsDoutRep;         // [net][M][NO] (critic mode)
+  const float* W[2]; long long rsP;                          // head weights [NO][Kdim]
+  const float* h; long long rsHnet, rsHrep; int ldh;         // [net][M][Kdim]
+  float* dh; long long rsDhNet, rsDhRep; int lddh;
+  float* dW[2]; float* db[2]; long long rsG;                 // grad arena (null -> no wgrad)
+  int policy_mode;
+  const float* dx; long long rsDxNet, rsDxRep; int lddx;     // [2][B][xw] critic input grads
+  const float* psave; long long rsSave;                      // rows B..2B-1 pre-offset by host
+  const int* tid; long long rsR;
+  const float* log_alpha;
+  float* dout_dbg; long long rsDbg;                          // optional dump of dout / d_action
+  float* dact_dbg;
+};
+
+__global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs P) {
+  extern __shared__ float sm[];
+  const int net = blockIdx.y, rep = blockIdx.z;
+  const int M = P.M, NO = P.NO, KD = P.Kdim;
+  float* sd = sm;                       // [M][NO]
+  float* red = sm + (size_t)M * NO;     // [8][32][NO] / scratch
+  const int tid = threadIdx.x, tx = tid % 32, ty = tid / 32;
+
+  if (P.policy_mode) {
+    const int A = K.act;
+    const float k = K.action_scale;
+    for (int e = tid; e < M * A; e += 256) {
+      const int m = e / A, j = e % A;
+      const float* sv = P.psave + rep * P.rsSave + ((long long)m * A + j) * kSaveW;
+      const float std = sv[0], diff = sv[1], t = sv[2], act = sv[3], jac = sv[4], eps = sv[5], mask = sv[6];
+      const float* dx0 = P.dx + rep * P.rsDxRep + (long long)m * P.lddx + K.obs + j;
+      const float da = dx0[0] + dx0[P.rsDxNet];
+      const int tk = (P.tid + rep * P.rsR)[m];
+      const float alpha = (float)exp((double)(P.log_alpha + rep * P.rsP)[tk]);
+      const float glp = K.c_loss * alpha;
+      const float var = std * std;
+      const float d_act = da + glp * (2.f * (act / k) / k) * k / jac;
+      const float g_u_t = d_act * k * (1.f - t * t);
+      const float g_u = g_u_t + glp * (-(diff) / var);
+      const float dmu = g_u + glp * (diff / var);
+      const float dstd = g_u * eps + glp * ((diff * diff) / (var * std) - 1.f / std);
+      const float dls = dstd * std * mask;
+      sd[m * NO + j] = dmu;
+      sd[m * NO + A + j] = dls;
+      if (P.dout_dbg && blockIdx.x == 0) {
+        (P.dout_dbg + rep * P.rsDbg)[(long long)m * NO + j] = dmu;
+        (P.dout_dbg + rep * P.rsDbg)[(long long)m * NO + A + j] = dls;
+        (P.dact_dbg + rep * P.rsDbg)[(long long)m * A + j] = da;
+      }
+    }
+  } else {
+    const float* src = P.dout + rep * P.rsDoutRep + net * P.rsDoutNet;
+    for (int e = tid; e < M * NO; e += 256) sd[e] = src[e];
+  }
+  __syncthreads();
+
+  const int kcol = blockIdx.x * 32 + tx;
+  const bool kin = kcol < KD;
+  const float* W = P.W[net] + rep * P.rsP;
+  float w[kMaxHeadOut], gw[kMaxHeadOut];
+#pragma unroll
+  for (int j = 0; j < kMaxHeadOut; ++j) {
+    w[j] = (j < NO && kin) ? W[(long long)j * KD + kcol] : 0.f;
+    gw[j] = 0.f;
+  }
+  const float* h = P.h + rep * P.rsHrep + net * P.rsHnet;
+  float* dh = P.dh + rep * P.rsDhRep + net * P.rsDhNet;
+  for (int m = ty; m < M; m += 8) {
+    const float hv = kin ? h[(long long)m * P.ldh + kcol] : 0.f;
+    float ds = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxHeadOut; ++j) {
+      if (j < NO) {
+        const float dv = sd[m * NO + j];
+        ds = fmaf(dv, w[j], ds);
+        gw[j] = fmaf(dv, hv, gw[j]);
+      }
+    }
+    if (kin) dh[(long long)m * P.lddh + kcol] = hv > 0.f ? ds : 0.f;
+  }
+  if (P.dW[net] != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kMaxHeadOut; ++j)
+      if (j < NO) red[(ty * 32 + tx) * NO + j] = gw[j];
+    __syncthreads();
+    if (ty == 0 && kin) {
+      float* dW = P.dW[net] + rep * P.rsG;
+      for (int j = 0; j < NO; ++j) {
+        float s = 0.f;
+        for (int q = 0; q < 8; ++q) s += red[(q * 32 + tx) * NO + j];
+        dW[(long long)j * KD + kcol] = s;
+      }
+    }
+    if (blockIdx.x == 0) {             // bias gradient: fixed-order tree over rows
+      __syncthreads();
+      for (int j = 0; j < NO; ++j) {
+        float s = 0.f;
+        for (int m = tid; m < M; m += 256) s += sd[m * NO + j];
+        red[tid] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+          if (tid < o) red[tid] += red[tid + o];
+          __syncthreads();
+        }
+        if (tid == 0) (P.db[net] + rep * P.rsG)[j] = red[0];
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam (torch.optim.adam._single_tensor_adam, defaults) over a contiguous slice of the
+// trainable arena, optionally fused with the Polyak update of the matching target slice
+// (LL/learner.py:126-137,236-237).  The target critics are only read at the start of a step
+// and the local critics do not change after critic_optimizer.step(), so doing the Polyak
+// write here is exactly equivalent to the reference's end-of-step soft_update.
+// The extra last CTA runs a "tail job": scalar reductions that must be deterministic.
+// ------------------------------------------------------------------------------------------
+enum { TAIL_NONE = 0, TAIL_CRITIC_LOSS = 1, TAIL_ALPHA_AND_LOSSES = 2 };
+
+struct AdamArgs {
+  float* p; float* m; float* v; const float* g;     // slice bases (replica 0)
+  long long rsP, rsM;                                // replica strides: param arena / trainable arena
+  long long n;
+  long long target_delta;                            // p[i + target_delta] is the Polyak target (0 = none)
+  int which;                                         // counter index (0 critic, 1 actor)
+  double lr;
+  const Counters* cnt;
+  int tail;
+  // tail inputs
+  const float* lq; const float* la; const float* logp_cur; const float* logstd_sum; const int* tid;
+  long long rsY, rsLogp, rsR;
+  float* log_alpha; float* m_alpha; float* v_alpha; float* g_alpha;   // arena pointers
+  float* losses;                                     // [kLossSlots][R][4]
+  int R;
+};
+
+B200_D void adam_scalars(double lr, double b1, double b2, long long step, float& step_size, float& bc2_sqrt) {
+  const double bc1 = 1.0 - pow(b1, (double)step);
+  const double bc2 = 1.0 - pow(b2, (double)step);
+  step_size = (float)(lr / bc1);
+  bc2_sqrt = (float)sqrt(bc2);
+}
+
+B200_D void adam_one(float& p, float& m, float& v, float g, float w1, float b2, float omb2, float step_size,
+                     float bc2_sqrt, float eps) {
+  m = m + w1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * b2 + omb2 * g * g;                  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+  const float denom = sqrtf(v) / bc2_sqrt + eps;
+  p = p - step_size * (m / denom);            // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
+  const int rep = blockIdx.y;
+  __shared__ float red[256];
+  __shared__ float s_ss, s_bc;
+  const bool is_tail = (P.tail != TAIL_NONE) && (blockIdx.x == gridDim.x - 1);
+  if (!is_tail) {
+    if (threadIdx.x == 0) {
+      float a, b;
+      adam_scalars(P.lr, K.beta1, K.beta2, P.cnt[rep].v[P.which], a, b);
+      s_ss = a; s_bc = b;
+    }
+    __syncthreads();
+    const float step_size = s_ss, bc2_sqrt = s_bc;
+    const float w1 = (float)(1.0 - K.beta1), b2 = (float)K.beta2, omb2 = (float)(1.0 - K.beta2);
+    const float eps = (float)K.adam_eps;
+    const int nb = (P.tail != TAIL_NONE) ? gridDim.x - 1 : gridDim.x;
+    float* p = P.p + rep * P.rsP;
+    float* m = P.m + rep * P.rsM;
+    float* v = P.v + rep * P.rsM;
+    const float* g = P.g + rep * P.rsM;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < P.n; i += (long long)nb * 256) {
+      float pi = p[i], mi = m[i], vi = v[i];
+      adam_one(pi, mi, vi, g[i], w1, b2, omb2, step_size, bc2_sqrt, eps);
+      p[i] = pi; m[i] = mi; v[i] = vi;
+      if (P.target_delta != 0) {
+        const float t = p[i + P.target_delta];
+        p[i + P.target_delta] = K.tau * pi + K.one_minus_tau * t;
+      }
+    }
+    return;
+  }
+  // ---- tail jobs (one CTA per replica) ----
+  const int tid = threadIdx.x, B = K.B;
+  auto block_sum = [&](float x) -> float {
+    red[tid] = x;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) red[tid] += red[tid + o];
+      __syncthreads();
+    }
+    const float r = red[0];
+    __syncthreads();
+    return r;
+  };
+  const long long slot = (P.cnt[rep].v[3] - 1) % kLossSlots;
+  float* L = P.losses + ((long long)slot * P.R + rep) * 4;
+  if (P.tail == TAIL_CRITIC_LOSS) {
+    float s = 0.f;
+    for (int i = tid; i < B; i += 256) s += (P.lq + rep * P.rsY)[i];
+    s = block_sum(s);
+    if (tid == 0) L[0] = s * K.c_loss;
+    return;
+  }
+  // TAIL_ALPHA_AND_LOSSES: actor loss, entropy, temperature gradient + its Adam step
+  {
+    float s = 0.f, e = 0.f;
+    for (int i = tid; i < B; i += 256) {
+      s += (P.la + rep * P.rsY)[i];
+      e += (P.logstd_sum + rep * P.rsLogp)[i];
+    }
+    s = block_sum(s);
+    e = block_sum(e);
+    if (tid == 0) {
+      L[1] = s * K.c_loss;
+      L[3] = 0.5f * K.act * (1.0f + 1.8378770664093453f) + e * K.inv_B;   // 0.5 A (1+log 2pi) + mean(sum log_std)
+    }
+    const int Teff = K.T > 0 ? K.T : 1;
+    float* la = P.log_alpha + rep * P.rsP;
+    float aloss = 0.f;
+    for (int t = 0; t < Teff; ++t) {
+      float gs = 0.f;
+      for (int i = tid; i < B; i += 256) {
+        if ((P.tid + rep * P.rsR)[i] == t) gs += (P.logp_cur + rep * P.rsLogp)[i] + K.hbar;
+      }
+      gs = block_sum(gs);
+      if (tid == 0) {
+        const float grad = -gs * K.inv_B;            // d/dlog_alpha[t] of -mean(log_alpha_i (logp_i + Hbar))
+        aloss += la[t] * grad;                       // loss value = sum_t log_alpha[t] * grad[t]
+        (P.g_alpha + rep * P.rsM)[t] = grad;
+        float ss, bc;
+        adam_scalars(K.lr_alpha, K.beta1, K.beta2, P.cnt[rep].v[2], ss, bc);
+        float pi = la[t], mi = (P.m_alpha + rep * P.rsM)[t], vi = (P.v_alpha + rep * P.rsM)[t];
+        adam_one(pi, mi, vi, grad, (float)(1.0 - K.beta1), (float)K.beta2, (float)(1.0 - K.beta2), ss, bc,
+                 (float)K.adam_eps);
+        la[t] = pi; (P.m_alpha + rep * P.rsM)[t] = mi; (P.v_alpha + rep * P.rsM)[t] = vi;
+      }
+    }
+    if (tid == 0) L[2] = aloss;
+  }
+}
+
+// Stand-alone Polyak (Learner.soft_update outside a step; tau = 1 -> hard copy).
+__global__ void polyak_kernel(float* p, long long rsP, long long n, long long target_delta, float tau,
+                              float one_minus_tau) {
+  float* q = p + blockIdx.y * rsP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    q[i + target_delta] = tau * q[i] + one_minus_tau * q[i + target_delta];
+}
+
+// Synthetic replay fill (bench helper): rows [s | a | r | s2 | d | pad], SURVEY 8(d) distributions.
+__global__ void fill_synthetic_kernel(float* rows, long long rs_rows, int row_stride, long long n_per_task,
+                                      long long cap_per_task, int state_dim, int act, int T,
+                                      unsigned long long seed) {
+  const int rep = blockIdx.y;
+  const int Teff = T > 0 ? T : 1;
+  const int obs = state_dim + T;
+  Philox ph(seed + 77ull * (unsigned long long)(rep + 1));
+  const long long total = n_per_task * Teff;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int task = (int)(e / n_per_task);
+    const long long local = e % n_per_task;
+    float* row = rows + rep * rs_rows + (task * cap_per_task + local) * row_stride;
+    const int nrand = 2 * state_dim + act + 2;
+    for (int c = 0; c < nrand; c += 4) {
+      uint32_t rnd[4];
+      ph((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)c, 0xF111u, rnd);
+      float z[4];
+      box_muller(rnd[0], rnd[1], z[0], z[1]);
+      box_muller(rnd[2], rnd[3], z[2], z[3]);
+      for (int q = 0; q < 4 && c + q < nrand; ++q) {
+        const int j = c + q;
+        if (j < state_dim) row[j] = z[q];                                                 // s
+        else if (j < state_dim + act) row[obs + (j - state_dim)] = 2.f * u01(rnd[q]) - 1.f;   // a
+        else if (j == state_dim + act) row[obs + act] = z[q];                                 // r
+        else if (j < 2 * state_dim + act + 1) row[obs + act + 1 + (j - state_dim - act - 1)] = z[q];   // s2
+        else row[2 * obs + act + 1] = (u01(rnd[q]) < 0.01f) ? 1.f : 0.f;                      // d
+      }
+    }
+    for (int q = 0; q < T; ++q) {
+      const float oh = (q == task) ? 1.f : 0.f;
+      row[state_dim + q] = oh;
+      row[obs + act + 1 + state_dim + q] = oh;
+    }
+  }
+}
+
+// Xavier-uniform init of one [out][in] matrix (nn.init.xavier_uniform_, gain 1), bias zero.
+__global__ void xavier_kernel(float* w, long long rsP, int rows, int cols, unsigned long long seed, int tag) {
+  const int rep = blockIdx.y;
+  Philox ph(seed + (unsigned long long)rep);
+  const float bound = sqrtf(6.f / (float)(rows + cols));
+  const long long n = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t rnd[4];
+    ph((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)tag, 0x1417u, rnd);
+    (w + rep * rsP)[i] = (2.f * u01(rnd[0]) - 1.f) * bound;
+  }
+}
+
+}  // namespace bsac

@@ -1,0 +1,171 @@
+/*
+ * b200sac.h -- C ABI of the B200-native SAC learner hot path.
+ *
+ * The reference (SKSKSK94/Distributed_SAC) is pure Python and has no FFI; the seam
+ * this library sits behind is the Python method surface of `Learner` /
+ * `ReplayBuffer`.  Each entry point below names the reference code it replaces
+ * (paths relative to the reference checkout):
+ *
+ *   b200sac_step*            Learner.update() -> update_SAC()
+ *                            LunarLander_Distributed_SAC/src/learner.py:246-264,203-239
+ *                            MT1_Distributed_VSAC/src/learner.py:205-244,251-269
+ *                            MT10_Distributed_MTSAC/src/learner.py:253-325,332-352
+ *   b200sac_replay_*         ReplayBuffer.sample()/__len__ and the append in run()
+ *                            LunarLander_Distributed_SAC/src/replay_buffer.py:43-77
+ *                            MT10_Distributed_MTSAC/src/replay_buffers.py:47-107
+ *   b200sac_layout/export/import
+ *                            build_model/build_optimizer/get_parameters/save_checkpoint
+ *                            LunarLander_Distributed_SAC/src/learner.py:100-124,144-163,272-276
+ *   b200sac_soft_update      Learner.soft_update()            learner.py:126-137
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Every function
+ * returns 0 on success or a negative b200sac_status; a message for the calling
+ * thread is available from b200sac_last_error().  No exceptions cross the
+ * boundary.  All device work is enqueued on the caller's stream (a
+ * cudaStream_t passed as void*; NULL = legacy default stream).  A handle is
+ * single-caller (not re-entrant); distinct handles are independent.
+ * `replicas` independent learners of the same shape can live in one handle and
+ * are stepped together (grouped launches); every per-learner array then has a
+ * leading replica dimension.
+ */
+#ifndef B200SAC_H_
+#define B200SAC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SAC_MAX_HIDDEN 8
+
+typedef enum b200sac_status {
+  B200SAC_OK = 0,
+  B200SAC_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  B200SAC_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+  B200SAC_ERR_NOMEM = -3,
+  B200SAC_ERR_STATE = -4      /* call not valid in this state (e.g. replay too small) */
+} b200sac_status;
+
+/* Mirrors the cfg JSON + hard-coded dims of the reference learners
+ * (cfg/*.json; LL/learner.py:62-81; MS/learner.py:62-98). */
+typedef struct b200sac_cfg {
+  int32_t state_dim;                 /* raw state width (8 / 39) */
+  int32_t act_dim;                   /* 2 / 4 */
+  int32_t num_tasks;                 /* 0 = single task; T>0 = one-hot appended to the state (mtobs) */
+  int32_t n_actor_hidden;            /* number of hidden layers */
+  int32_t n_critic_hidden;
+  int32_t actor_hidden[B200SAC_MAX_HIDDEN];
+  int32_t critic_hidden[B200SAC_MAX_HIDDEN];
+  int32_t batch;                     /* minibatch per learner */
+  int32_t weighted_loss;             /* MTSAC use_weighted_loss (== extra 1/batch) */
+  int32_t replicas;                  /* independent learners in this handle (>= 1) */
+  int32_t precision;                 /* 0 = fp32 FFMA; 1 = 3xTF32 on tcgen05 for hidden layers */
+  int32_t reserved0;
+  double gamma, tau, reward_scale;
+  double lr_actor, lr_critic, lr_alpha;
+  double action_scale;               /* k = (hi - lo) / 2 */
+  double beta1, beta2, adam_eps;
+  double log_alpha_init;
+} b200sac_cfg;
+
+typedef struct b200sac_tensor_desc {
+  char name[48];                     /* canonical name, e.g. "q1_target.2.weight" */
+  int64_t offset;                    /* in floats, inside one replica's parameter arena */
+  int32_t rows, cols;                /* weight: (out, in) row-major; bias/log_alpha: (n, 1) */
+  int32_t trainable;                 /* 1 -> has Adam m/v at the same offset in the m/v arenas */
+  int32_t opt;                       /* 0 critic, 1 actor, 2 alpha, -1 none (targets) */
+} b200sac_tensor_desc;
+
+typedef struct b200sac b200sac_t;               /* learner handle */
+typedef struct b200sac_replay b200sac_replay_t; /* replay ring handle */
+
+/* arenas addressable through export/import */
+enum { B200SAC_PARAMS = 0, B200SAC_ADAM_M = 1, B200SAC_ADAM_V = 2, B200SAC_GRADS = 3 };
+
+const char* b200sac_last_error(void);
+const char* b200sac_version(void);
+
+/* Pure host function (no GPU needed): parameter layout for a cfg.
+ * Writes up to `cap` descriptors, returns the total count in *n and the arena
+ * size (floats per replica; trainable prefix length) in *arena_floats / *trainable_floats. */
+int b200sac_layout(const b200sac_cfg* cfg, b200sac_tensor_desc* out, int32_t cap, int32_t* n,
+                   int64_t* arena_floats, int64_t* trainable_floats);
+
+/* Create a learner on CUDA device `device`.  Parameters are Xavier-uniform /
+ * zero-bias initialised from `seed` (replica r uses seed + r); targets = locals. */
+int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t seed, b200sac_t** out);
+int b200sac_destroy(b200sac_t* h);
+
+/* Copy one replica's arena out / in.  `buf` may be a host or a device pointer. */
+int b200sac_export(b200sac_t* h, int32_t which, int32_t replica, float* buf, int64_t n_floats, void* stream);
+int b200sac_import(b200sac_t* h, int32_t which, int32_t replica, const float* buf, int64_t n_floats, void* stream);
+/* Device address of an arena (replica 0; replicas are contiguous, stride = arena floats).  For
+ * zero-copy views and for the one-time NCCL broadcast of initial weights done by the host shim. */
+int b200sac_arena_ptr(b200sac_t* h, int32_t which, float** dev_ptr, int64_t* floats_per_replica);
+/* Adam step counters {critic, actor, alpha} of one replica. */
+int b200sac_get_steps(b200sac_t* h, int32_t replica, int64_t steps[3]);
+int b200sac_set_steps(b200sac_t* h, int32_t replica, const int64_t steps[3]);
+
+/* One gradient step from caller-provided DEVICE minibatches, each
+ * [replicas][batch][width] fp32: s,s2 width obs(=state_dim+num_tasks), a width act, r,d width 1.
+ * eps_next / eps_cur: [replicas][batch][act] standard-normal noise for the two
+ * rsample() calls (next-state actor first), or NULL to draw in-kernel (Philox).
+ * Losses land in an internal device ring; fetch with b200sac_read_losses. */
+int b200sac_step(b200sac_t* h, const float* s, const float* a, const float* r, const float* s2,
+                 const float* d, const float* eps_next, const float* eps_cur, void* stream);
+
+/* Same, from HOST buffers (any host memory; staged through the handle's pinned
+ * double buffer with cudaMemcpyAsync on a side stream).  out_losses (host,
+ * [replicas][4] = critic, actor, alpha-loss, entropy) may be NULL; if given the call
+ * synchronises and fills it -- this is the reference's `update()` contract. */
+int b200sac_step_host(b200sac_t* h, const float* s, const float* a, const float* r, const float* s2,
+                      const float* d, const float* eps_next, const float* eps_cur, float* out_losses,
+                      void* stream);
+
+/* n_steps gradient steps, each sampling its own minibatch from the replay ring
+ * (uniform without replacement; per-task B/T when num_tasks > 0) with in-kernel noise.
+ * Device-resident ring: everything is enqueued asynchronously (one CUDA graph per step).
+ * Pinned-host ring: indices drawn on the host, rows gathered into pinned staging and
+ * copied on a side stream, overlapped with the previous step. */
+int b200sac_step_sampled(b200sac_t* h, b200sac_replay_t* rb, int32_t n_steps, void* stream);
+
+/* Losses of the most recent `n_last` steps (<= 1024 kept): out[n_last][replicas][4].
+ * Synchronises the stream. */
+int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host, void* stream);
+
+/* Polyak update of the target critics outside a step (Learner.soft_update; tau = 1 is
+ * the hard copy Learner.run() does before training, learner.py:287-288). */
+int b200sac_soft_update(b200sac_t* h, double tau, void* stream);
+
+/* Debug / parity access to per-step intermediates of replica `replica`:
+ * name in {"y","q1","q2","a_next","logp_next","a_cur","logp_cur","qmin","d_action","d_head","r","d"}. */
+int b200sac_debug_read(b200sac_t* h, const char* name, int32_t replica, float* out_host, int64_t cap_floats,
+                       int64_t* n_floats, void* stream);
+
+/* Number of kernels one step launches (for bench.py's gpu_launches accounting). */
+int b200sac_launches_per_step(b200sac_t* h, int32_t* n);
+
+/* ---- replay ring ---------------------------------------------------------------- */
+/* where: 0 = device-resident ring (HBM), 1 = pinned host DRAM ring.
+ * capacity = transitions per replica (per task: capacity / num_tasks when num_tasks > 0). */
+int b200sac_replay_create(b200sac_t* h, int64_t capacity, int32_t where, uint64_t seed, b200sac_replay_t** out);
+int b200sac_replay_destroy(b200sac_replay_t* rb);
+/* Append n transitions (HOST arrays, fp32, same widths as b200sac_step) to one replica's ring.
+ * Thread-safe against one concurrent sampler. */
+int b200sac_replay_push(b200sac_replay_t* rb, int32_t replica, int64_t n, const float* s, const float* a,
+                        const float* r, const float* s2, const float* d);
+/* Fill every replica's ring with `n` synthetic transitions generated on the device
+ * (s,s'~N(0,1), a~U(-1,1), r~N(0,1), d~Bernoulli(0.01), task = i mod T). Benchmark helper. */
+int b200sac_replay_fill_synthetic(b200sac_replay_t* rb, int64_t n, uint64_t seed, void* stream);
+/* min over tasks of the per-task fill, like ReplayBuffer.__len__ in the MT variant. */
+int b200sac_replay_size(b200sac_replay_t* rb, int32_t replica, int64_t* n);
+/* Draw one minibatch the way step_sampled would and return it in HOST arrays
+ * (reference-shaped ReplayBuffer.sample()); idx_out (nullable) gets the ring indices. */
+int b200sac_replay_sample(b200sac_replay_t* rb, int32_t replica, float* s, float* a, float* r, float* s2,
+                          float* d, int64_t* idx_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SAC_H_ */

@@ -65,3 +65,14 @@ def check_state(case, params, m, v, steps, tol=REL, what="state"):
             bad.append((k, "v", e2))
     assert not bad, f"{what} mismatch in {case.name}: {bad[:8]}"
     assert tuple(int(x) for x in steps) == tuple(int(x) for x in case.step_out)
+
+
+def core_config(spec, replicas=1, **kw):
+    from distributed_sac_b200.core import CoreConfig
+    d = dict(state_dim=spec.state_dim, act_dim=spec.act_dim, actor_hidden=list(spec.actor_hidden),
+             critic_hidden=list(spec.critic_hidden), batch=spec.batch, num_tasks=spec.num_tasks,
+             weighted_loss=spec.weighted_loss, replicas=replicas, gamma=spec.gamma, tau=spec.tau,
+             reward_scale=spec.reward_scale, lr_actor=spec.lr_actor, lr_critic=spec.lr_critic,
+             action_scale=spec.action_scale, beta1=spec.beta1, beta2=spec.beta2, adam_eps=spec.adam_eps)
+    d.update(kw)
+    return CoreConfig(**d)
