@@ -214,6 +214,17 @@ class SacCore:
         _lib.check(self.lib.b200sac_read_losses(self._h, n_last, _ptr(out), _stream()))
         return out
 
+    def profile_step(self, replay: "Replay", iters: int = 20):
+        """[(kernel label, mean ms)] per launch of one step (eager run with CUDA events)."""
+        cap = 256
+        out = (C.c_float * cap)()
+        n = C.c_int32(0)
+        names = C.create_string_buffer(8192)
+        _lib.check(self.lib.b200sac_profile_step(self._h, replay._h, int(iters), out, cap, C.byref(n), names, 8192, _stream()))
+        self.steps_done += int(iters)
+        labels = names.value.decode().split(";")
+        return [(labels[i], float(out[i])) for i in range(n.value)]
+
     def debug(self, name: str, replica=0) -> torch.Tensor:
         cap = self.cfg.batch * max(2 * self.cfg.act_dim, 1)
         out = torch.empty(cap)

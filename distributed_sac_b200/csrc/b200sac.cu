@@ -20,6 +20,7 @@
 
 #include "../../include/b200sac.h"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "sac_kernels.cuh"
 
 using namespace bsac;
@@ -74,7 +75,7 @@ static int check_cfg(const b200sac_cfg* c) {
   if (c->num_tasks > 0 && c->batch % c->num_tasks != 0)
     return fail(B200SAC_ERR_INVALID, "batch must be a multiple of num_tasks");
   if (c->replicas < 1 || c->replicas > 4096) return fail(B200SAC_ERR_INVALID, "1 <= replicas <= 4096 required");
-  if (c->precision != 0) return fail(B200SAC_ERR_INVALID, "precision %d not available in this build", c->precision);
+  if (c->precision != 0 && c->precision != 1) return fail(B200SAC_ERR_INVALID, "precision must be 0 (fp32 FFMA) or 1 (3xTF32 tcgen05)");
   return 0;
 }
 
@@ -141,7 +142,7 @@ struct Buf {           // [R][n] fp32 (or int32) slab slice
   long long rs = 0;    // replica stride in floats
 };
 
-enum LaunchKind { L_GEMM_BIG, L_GEMM_SMALL, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
+enum LaunchKind { L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
 
 struct Launch {
   LaunchKind kind;
@@ -149,6 +150,7 @@ struct Launch {
   size_t smem = 0;
   // payloads (only the one matching `kind` is used)
   const GemmProb* probs = nullptr; int G = 0;
+  const TcProb* tprobs = nullptr;
   PolicyHeadArgs pol;
   CriticHeadArgs ch;
   ActorQHeadArgs aq;
@@ -187,6 +189,8 @@ struct b200sac {
   std::vector<Buf> hQ, hT, hP, dhQ;   // per critic hidden layer, [2][B][H]
   GemmProb* d_probs = nullptr;
   std::vector<GemmProb> h_probs;
+  TcProb* d_tprobs = nullptr;
+  std::vector<TcProb> h_tprobs;
   std::vector<Launch> plan;
   IngestOut ing;
   int use_eps_buf_idx = -1;       // index of the policy launch in plan (its use_eps_buf flag varies)
@@ -203,7 +207,8 @@ struct b200sac {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   int stage_slot = 0;
   bool stage_used[2] = {false, false};
-  float* loss_h = nullptr;        // pinned [R][4]
+  float* loss_h = nullptr;        // mapped pinned loss ring [kLossSlots][R][4], written by the tail kernels
+  float* loss_h_dev = nullptr;    // its device-side address
 };
 
 struct b200sac_replay {
@@ -239,7 +244,7 @@ static int destroy_impl(b200sac* h) {
   cudaSetDevice(h->device);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   cudaFree(h->params); cudaFree(h->adam_m); cudaFree(h->adam_v); cudaFree(h->grads);
-  cudaFree(h->cnt); cudaFree(h->losses); cudaFree(h->slab); cudaFree(h->d_probs);
+  cudaFree(h->cnt); cudaFree(h->losses); cudaFree(h->slab); cudaFree(h->d_probs); cudaFree(h->d_tprobs);
   for (int i = 0; i < 2; ++i) {
     if (h->stage_h[i]) cudaFreeHost(h->stage_h[i]);
     cudaFree(h->stage_d[i]);
@@ -255,6 +260,68 @@ static int destroy_impl(b200sac* h) {
   return 0;
 }
 
+// ---- TMA tensor maps (driver entry point resolved at run time: no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [outer][inner] (pitch in floats), box {32 floats = 128 B, box_outer rows}, SWIZZLE_128B, zero OOB fill
+static int make_map(CUtensorMap* tm, const float* ptr, long long inner, long long outer, long long pitch, int box_outer,
+                    bool mn_major = false) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(B200SAC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200SAC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld pitch=%lld", (int)r, inner, outer, pitch);
+  return 0;
+}
+
+static bool tc_eligible(const GemmProb& p) {
+  auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+  if (p.lda % 4 || p.ldb % 4 || !al16(p.A) || !al16(p.B) || (p.rsA % 4) || (p.rsB % 4)) return false;
+  return p.M >= 32 && p.N >= 32 && p.K >= 32;
+}
+
+static int make_tc_prob(const GemmProb& p, int rep, TcProb& t) {
+  memset(&t, 0, sizeof(t));
+  const float* A = p.A + (long long)rep * p.rsA;
+  const float* B = p.B + (long long)rep * p.rsB;
+  t.M = p.M; t.N = p.N; t.K = p.K; t.mode = p.mode; t.relu = p.relu; t.ldc = p.ldc; t.ldmask = p.ldmask;
+  t.bias = p.bias ? p.bias + (long long)rep * p.rsBias : nullptr;
+  t.mask = p.mask ? p.mask + (long long)rep * p.rsMask : nullptr;
+  t.C = p.C + (long long)rep * p.rsC;
+  t.C2 = p.C2 ? p.C2 + (long long)rep * p.rsC2 : nullptr;
+  if (p.mode == GEMM_FWD) {            // A[M][K], B[N][K]: both K-major
+    t.a_mn = 0; t.b_mn = 0;
+    if (int rc = make_map(&t.tmA, A, p.K, p.M, p.lda, TC_BM)) return rc;
+    if (int rc = make_map(&t.tmB, B, p.K, p.N, p.ldb, TC_BN)) return rc;
+  } else if (p.mode == GEMM_DGRAD) {   // A = dY[M][K] K-major, B = W[K][N] MN-major
+    t.a_mn = 0; t.b_mn = 1;
+    if (int rc = make_map(&t.tmA, A, p.K, p.M, p.lda, TC_BM)) return rc;
+    if (int rc = make_map(&t.tmB, B, p.N, p.K, p.ldb, TC_BK, true)) return rc;
+  } else {                             // WGRAD: A = dY[K][M], B = X[K][N]: both MN-major
+    t.a_mn = 1; t.b_mn = 1;
+    if (int rc = make_map(&t.tmA, A, p.M, p.K, p.lda, TC_BK, true)) return rc;
+    if (int rc = make_map(&t.tmB, B, p.N, p.K, p.ldb, TC_BK, true)) return rc;
+  }
+  return 0;
+}
+
 // Build the launch list of one gradient step (everything after the ingest kernel).
 static int build_plan(b200sac* h) {
   const b200sac_cfg& c = h->cfg;
@@ -267,7 +334,34 @@ static int build_plan(b200sac* h) {
   auto W = [&](int64_t off) { return h->params + off; };
   auto Gp = [&](int64_t off) { return h->grads + off; };
 
+  int plan_rc = 0;
   auto gemm_launch = [&](std::vector<GemmProb> ps) {
+    if (c.precision == 1) {
+      std::vector<GemmProb> tc, rest;
+      for (auto& p : ps) (tc_eligible(p) ? tc : rest).push_back(p);
+      if (!tc.empty()) {
+        Launch l;
+        int maxM = 0, maxN = 0;
+        for (auto& p : tc) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; }
+        l.kind = L_GEMM_TC;
+        l.grid = dim3((maxN + TC_BN - 1) / TC_BN, (maxM + TC_BM - 1) / TC_BM, (unsigned)(tc.size() * R));
+        l.block = dim3(TC_THREADS);
+        l.smem = TC_SMEM_BYTES;
+        l.G = (int)tc.size();
+        l.tprobs = (const TcProb*)(uintptr_t)h->h_tprobs.size();
+        l.probs = (const GemmProb*)(uintptr_t)h->h_probs.size();   // keep the SIMT descriptors too (labels)
+        for (int rep = 0; rep < R; ++rep)
+          for (auto& p : tc) {
+            TcProb t;
+            if (int rc = make_tc_prob(p, rep, t)) plan_rc = rc;
+            h->h_tprobs.push_back(t);
+          }
+        for (auto& p : tc) h->h_probs.push_back(p);
+        h->plan.push_back(l);
+      }
+      if (rest.empty()) return;
+      ps = rest;
+    }
     Launch l;
     int maxM = 0, maxN = 0;
     for (auto& p : ps) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; }
@@ -457,7 +551,7 @@ static int build_plan(b200sac* h) {
     P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
     P.log_alpha = h->params + L.off_alpha;
     P.m_alpha = h->adam_m + L.off_alpha; P.v_alpha = h->adam_v + L.off_alpha; P.g_alpha = h->grads + L.off_alpha;
-    P.losses = h->losses; P.R = R;
+    P.losses = h->losses; P.losses_host = h->loss_h_dev; P.R = R;
     int nb = (int)((n + 256 * 4 - 1) / (256 * 4));
     if (nb < 1) nb = 1;
     if (nb > 592) nb = 592;
@@ -521,11 +615,19 @@ static int build_plan(b200sac* h) {
   }
   adam(1);
 
+  if (plan_rc) return plan_rc;
   // upload problem tables and rebase
+  if (!h->h_tprobs.empty()) {
+    CU(cudaMalloc(&h->d_tprobs, h->h_tprobs.size() * sizeof(TcProb)));
+    CU(cudaMemcpy(h->d_tprobs, h->h_tprobs.data(), h->h_tprobs.size() * sizeof(TcProb), cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  }
   CU(cudaMalloc(&h->d_probs, h->h_probs.size() * sizeof(GemmProb)));
   CU(cudaMemcpy(h->d_probs, h->h_probs.data(), h->h_probs.size() * sizeof(GemmProb), cudaMemcpyHostToDevice));
-  for (auto& l : h->plan)
-    if (l.kind == L_GEMM_BIG || l.kind == L_GEMM_SMALL) l.probs = h->d_probs + (size_t)(uintptr_t)l.probs;
+  for (auto& l : h->plan) {
+    if (l.kind == L_GEMM_BIG || l.kind == L_GEMM_SMALL || l.kind == L_GEMM_TC) l.probs = h->d_probs + (size_t)(uintptr_t)l.probs;
+    if (l.kind == L_GEMM_TC) l.tprobs = h->d_tprobs + (size_t)(uintptr_t)l.tprobs;
+  }
   size_t max_smem = 0;
   for (auto& l : h->plan)
     if (l.kind == L_HEADBWD && l.smem > max_smem) max_smem = l.smem;
@@ -534,15 +636,19 @@ static int build_plan(b200sac* h) {
   return 0;
 }
 
-static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf) {
+static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* evs = nullptr) {
   for (size_t i = 0; i < h->plan.size(); ++i) {
     Launch& l = h->plan[i];
+    if (evs) CU(cudaEventRecord(evs[i], st));
     switch (l.kind) {
       case L_GEMM_BIG:
         gemm_simt_kernel<64, 64, 4, 4><<<l.grid, l.block, 0, st>>>(l.probs, l.G);
         break;
       case L_GEMM_SMALL:
         gemm_simt_kernel<32, 32, 2, 2><<<l.grid, l.block, 0, st>>>(l.probs, l.G);
+        break;
+      case L_GEMM_TC:
+        gemm_tc_kernel<<<l.grid, l.block, l.smem, st>>>(l.tprobs);
         break;
       case L_POLICY: {
         PolicyHeadArgs P = l.pol;
@@ -564,6 +670,7 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf) {
         break;
     }
   }
+  if (evs) CU(cudaEventRecord(evs[h->plan.size()], st));
   CU(cudaGetLastError());
   return 0;
 }
@@ -714,7 +821,9 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
     CUH(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
     CUH(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
   }
-  CUH(cudaMallocHost(&h->loss_h, sizeof(float) * R * 4 * kLossSlots));
+  CUH(cudaHostAlloc(&h->loss_h, sizeof(float) * R * 4 * kLossSlots, cudaHostAllocMapped));
+  memset(h->loss_h, 0, sizeof(float) * R * 4 * kLossSlots);
+  CUH(cudaHostGetDevicePointer((void**)&h->loss_h_dev, h->loss_h, 0));
   CUH(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CUH(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
   CUH(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
@@ -818,7 +927,9 @@ struct StreamBridge {
 // ------------------------------------------------------------------------------------------
 // step variants.  variant 0: split device arrays; 1: packed rows (dense, staged); 2: replay gather
 // ------------------------------------------------------------------------------------------
-static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* const* p, b200sac_replay* rb) {
+static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* const* p, b200sac_replay* rb,
+                        cudaEvent_t* evs = nullptr) {
+  if (evs) CU(cudaEventRecord(evs[0], st));
   const int B = h->cfg.batch, R = h->R;
   dim3 grid((B + 7) / 8, R), block(256);
   if (grid.x > 64) grid.x = 64;
@@ -849,7 +960,7 @@ static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* co
     ingest_rows_kernel<<<grid, block, 0, st>>>(h->K, h->ing, rb->rows, rb->rs_rows, h->row_stride, rb->d_idx, B);
   }
   CU(cudaGetLastError());
-  return run_plan(h, st, use_eps);
+  return run_plan(h, st, use_eps, evs ? evs + 1 : nullptr);
 }
 
 static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* const* p, int np, b200sac_replay* rb) {
@@ -937,13 +1048,12 @@ static int fetch_losses(b200sac* h, cudaStream_t st, int n_last, float* out) {
   if (n_last < 1 || n_last > kLossSlots || n_last > h->host_steps)
     return fail(B200SAC_ERR_INVALID, "n_last=%d out of range (steps so far %lld, ring %d)", n_last, h->host_steps, kLossSlots);
   const size_t per = (size_t)h->R * 4;
+  CU(cudaStreamSynchronize(st));       // the tail kernels wrote the mapped host ring directly
   for (int i = 0; i < n_last; ++i) {
     const long long step = h->host_steps - n_last + i;
     const long long slot = step % kLossSlots;
-    CU(cudaMemcpyAsync(h->loss_h + (size_t)i * per, h->losses + (size_t)slot * per, per * sizeof(float), cudaMemcpyDeviceToHost, st));
+    memcpy(out + (size_t)i * per, h->loss_h + (size_t)slot * per, per * sizeof(float));
   }
-  CU(cudaStreamSynchronize(st));
-  memcpy(out, h->loss_h, (size_t)n_last * per * sizeof(float));
   return 0;
 }
 
@@ -968,6 +1078,95 @@ extern "C" int b200sac_step_host(b200sac_t* h, const float* s, const float* a, c
   if (out_losses)
     if (int rc = fetch_losses(h, st, 1, out_losses)) return rc;
   return sb.end();
+}
+
+static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp, const GemmProb* dbase) {
+  switch (l.kind) {
+    case L_GEMM_TC: {
+      const GemmProb& p0 = hp[(size_t)(l.probs - dbase)];
+      const GemmProb& pl = hp[(size_t)(l.probs - dbase) + l.G - 1];
+      if (p0.mode == GEMM_FWD) return "gemm_fwd(tcgen05)";
+      if (p0.mode == GEMM_WGRAD && pl.mode == GEMM_DGRAD) return "gemm_wgrad+dgrad(tcgen05)";
+      if (p0.mode == GEMM_WGRAD) return "gemm_wgrad(tcgen05)";
+      return "gemm_dgrad(tcgen05)";
+    }
+    case L_GEMM_BIG:
+    case L_GEMM_SMALL: {
+      const GemmProb& p0 = hp[(size_t)(l.probs - dbase)];
+      const GemmProb& pl = hp[(size_t)(l.probs - dbase) + l.G - 1];
+      if (p0.mode == GEMM_FWD) return l.kind == L_GEMM_BIG ? "gemm_fwd(64x64)" : "gemm_fwd(32x32)";
+      if (p0.mode == GEMM_WGRAD && pl.mode == GEMM_DGRAD) return l.kind == L_GEMM_BIG ? "gemm_wgrad+dgrad(64x64)" : "gemm_wgrad+dgrad(32x32)";
+      if (p0.mode == GEMM_WGRAD) return l.kind == L_GEMM_BIG ? "gemm_wgrad(64x64)" : "gemm_wgrad(32x32)";
+      return l.kind == L_GEMM_BIG ? "gemm_dgrad(64x64)" : "gemm_dgrad(32x32)";
+    }
+    case L_POLICY: return "policy_head";
+    case L_CHEADS: return "critic_heads";
+    case L_AQHEADS: return "actor_q_heads";
+    case L_HEADBWD: return l.hb.policy_mode ? "head_bwd(policy)" : "head_bwd(q)";
+    case L_ADAM: return l.ad.which == 0 ? "adam_critic+polyak" : "adam_actor+alpha";
+  }
+  return "?";
+}
+
+// Eager (non-graph) run of `iters` sampled steps with a CUDA event between every launch.
+// out_ms[i] = mean device time of launch i (i = 0 is sampling + ingest); names are returned as a
+// ';'-separated list.  This is what bench.py uses for the per-kernel roofline numbers.
+extern "C" int b200sac_profile_step(b200sac_t* h, b200sac_replay_t* rb, int32_t iters, float* out_ms, int32_t cap,
+                                    int32_t* n_out, char* names, int32_t names_cap, void* stream) {
+  if (!h || !rb || rb->h != h || rb->where != 0 || !out_ms || !n_out) return fail(B200SAC_ERR_INVALID, "profile_step needs a device ring");
+  CU(cudaSetDevice(h->device));
+  const int n = (int)h->plan.size() + 1;
+  *n_out = n;
+  if (cap < n) return fail(B200SAC_ERR_INVALID, "need room for %d launches", n);
+  StreamBridge sb(h, stream);
+  if (int rc = sb.begin()) return rc;
+  std::vector<cudaEvent_t> evs((size_t)n + 1);
+  for (auto& e : evs) CU(cudaEventCreate(&e));
+  std::vector<double> acc((size_t)n, 0.0);
+  const void* p[1] = {rb->rows};
+  for (int it = 0; it < iters; ++it) {
+    if (int rc = enqueue_body(h, sb.run, 2, p, rb, evs.data())) return rc;
+    h->host_steps += 1;
+    CU(cudaStreamSynchronize(sb.run));
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (int i = 0; i < n; ++i) out_ms[i] = (float)(acc[i] / iters);
+  for (auto& e : evs) cudaEventDestroy(e);
+  if (names && names_cap > 0) {
+    std::string s = "sample+ingest";
+    for (auto& l : h->plan) { s += ";"; s += launch_name(l, h->h_probs, h->d_probs); }
+    snprintf(names, names_cap, "%s", s.c_str());
+  }
+  return sb.end();
+}
+
+// Stand-alone run of the tcgen05 GEMM kernel on caller-provided DEVICE arrays (parity tests).
+extern "C" int b200sac_tc_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
+                                    const float* B, int32_t ldb, const float* bias, const float* mask, int32_t ldmask,
+                                    float* C, int32_t ldc, float* C2, int32_t relu, void* stream) {
+  if (!A || !B || !C) return fail(B200SAC_ERR_INVALID, "null argument");
+  GemmProb p;
+  memset(&p, 0, sizeof(p));
+  p.A = A; p.B = B; p.bias = bias; p.mask = mask; p.C = C; p.C2 = C2;
+  p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldmask = ldmask; p.mode = mode; p.relu = relu;
+  if (!tc_eligible(p)) return fail(B200SAC_ERR_INVALID, "problem not eligible for the tcgen05 path (need 16-B aligned operands, lda/ldb %% 4 == 0, M,N,K >= 32)");
+  TcProb t;
+  if (int rc = make_tc_prob(p, 0, t)) return rc;
+  TcProb* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(TcProb)));
+  CU(cudaMemcpy(d, &t, sizeof(TcProb), cudaMemcpyHostToDevice));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM, 1);
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(d);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(B200SAC_ERR_CUDA, "gemm_tc_kernel failed: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 extern "C" int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host, void* stream) {

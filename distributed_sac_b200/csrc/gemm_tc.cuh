@@ -1,0 +1,365 @@
+// tcgen05 (5th-gen tensor core) grouped GEMM for the hidden layers of the SAC step, at
+// fp32-class accuracy via the 3xTF32 split:  x = hi + lo (hi = top 19 bits, lo = x - hi),
+// D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi, accumulated in fp32 in TMEM.
+//
+// One CTA = one 128 x 64 output tile of one problem (blockIdx.z = problem x replica):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes (SWIZZLE_128B for K-major operands,
+//               SWIZZLE_128B_ATOM_32B for MN-major ones) of the fp32 operands,
+//               straight from the row-major activation / weight / gradient buffers; out-of-range
+//               rows and columns are zero-filled by the TMA unit (ragged 400-wide layers, tails)
+//   warps 2-5   splitter: rewrite each landed tile in place as hi and emit lo beside it (same
+//               swizzled offsets, so the layout is untouched); later the epilogue warps
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M=128, N=64, K=8),
+//               12 MMAs per 32-wide k chunk; tcgen05.commit releases the smem stage / signals the
+//               epilogue
+//   accumulate  the tensor core adds into the fp32 accumulator with truncation (measured: relative
+//               bias ~ #MMAs x 2^-24), so the tiny cross terms A_hi*B_lo + A_lo*B_hi go to their own
+//               accumulator and the A_hi*B_hi sum is spread over up to six (contiguous K ranges); the
+//               epilogue adds them with round-to-nearest.  Keeps the result within ~1e-6 of fp64.
+//   epilogue    tcgen05.ld 32x32b (thread = accumulator row) -> bias+ReLU | ReLU' mask | plain ->
+//               global; the weight-gradient kind also emits the bias gradient (column sums of dY),
+//               accumulated by the splitter while it walks the A tiles, in a fixed order.
+// The three GEMM kinds only differ in operand majors (instruction-descriptor bits 15/16 and the
+// smem-descriptor LBO/SBO), exactly as in gemm_simt.cuh:
+//   FWD   A = X  [M][K] K-major,  B = W [N][K] K-major
+//   DGRAD A = dY [M][K] K-major,  B = W [K][N] MN-major
+//   WGRAD A = dY [K][M] MN-major, B = X [K][N] MN-major
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace bsac {
+
+constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 32, TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                  // 16 KiB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;                  //  8 KiB
+constexpr int TC_STAGE_BYTES = 2 * (TC_A_BYTES + TC_B_BYTES);  // hi + lo of both operands = 48 KiB
+constexpr int TC_THREADS = 192;
+constexpr int TC_SPLIT_THREADS = 128;
+constexpr int TC_NMAIN = 6;         // A_hi*B_hi is spread over up to 6 accumulators (contiguous K ranges)
+constexpr int TC_TMEM_COLS = 512;   // 6 main + 1 cross-term accumulator x 64 fp32 columns = 448 -> 512 (power of two)
+constexpr int TC_BSUM_BYTES = 16 * TC_BM * 4;                  // [16 partials][128 m] fp32
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_BSUM_BYTES + 256 + 1024;   // + barriers + align slack
+
+struct alignas(128) TcProb {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  const float* bias;
+  const float* mask;
+  float* C;
+  float* C2;
+  int M, N, K;
+  int ldc, ldmask;
+  int mode, relu;
+  int a_mn, b_mn;
+  int pad[3];
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+B200_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+B200_D void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+B200_D void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+B200_D void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+B200_D bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must become a trapped launch, never a hung GPU.
+B200_D void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+B200_D void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+B200_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+B200_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+B200_D void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+B200_D void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+B200_D void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// smem matrix descriptor, Blackwell version field = 1 (cute::UMMA::SmemDescriptor).
+// layout_type 2 = SWIZZLE_128B (16-B atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-B atoms;
+// the only layout tcgen05 accepts for MN-major tf32 operands).
+B200_D uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
+B200_D uint32_t tc_instr_desc(int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __restrict__ probs) {
+  extern __shared__ uint8_t smem_raw[];
+  const TcProb* P = probs + blockIdx.z;
+  const int M = P->M, N = P->N, K = P->K;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  if (m0 >= M || n0 >= N) return;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-B alignment
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bsum_s = base + TC_STAGES * TC_STAGE_BYTES;
+  float* bsum_g = reinterpret_cast<float*>(gbase + TC_STAGES * TC_STAGE_BYTES);
+  const uint32_t bars = bsum_s + TC_BSUM_BYTES;
+  uint8_t* bars_g = gbase + TC_STAGES * TC_STAGE_BYTES + TC_BSUM_BYTES;
+  // barrier slots (8 B each): full[4] ready[4] empty[4] accum[1]; then the TMEM base address word
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto ready_bar = [&](int s) { return bars + 8u * (TC_STAGES + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };
+  const uint32_t accum_bar = bars + 8u * (3 * TC_STAGES);
+  const uint32_t tmem_slot = bars + 8u * (3 * TC_STAGES + 1);
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(bars_g + 8 * (3 * TC_STAGES + 1));
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int nk = (K + TC_BK - 1) / TC_BK;
+  const int a_mn = P->a_mn, b_mn = P->b_mn;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(ready_bar(s), TC_SPLIT_THREADS);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t st = base + (uint32_t)s * TC_STAGE_BYTES;
+        const uint32_t dA = st, dB = st + 2 * TC_A_BYTES;
+        mbar_expect_tx(full_bar(s), TC_A_BYTES + TC_B_BYTES);
+        const int k0 = kc * TC_BK;
+        if (!a_mn) {
+          tma_load_2d(dA, &P->tmA, k0, m0, full_bar(s));
+        } else {
+          for (int g = 0; g < TC_BM / 32; ++g) tma_load_2d(dA + g * 4096, &P->tmA, m0 + 32 * g, k0, full_bar(s));
+        }
+        if (!b_mn) {
+          tma_load_2d(dB, &P->tmB, k0, n0, full_bar(s));
+        } else {
+          for (int g = 0; g < TC_BN / 32; ++g) tma_load_2d(dB + g * 4096, &P->tmB, n0 + 32 * g, k0, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc = tc_instr_desc(a_mn, b_mn);
+      const int nmain = nk < TC_NMAIN ? nk : TC_NMAIN;   // chunk kc accumulates into main[(kc * nmain) / nk]
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
+        mbar_wait(ready_bar(s), ph);
+        tc_fence_after();
+        const uint32_t st = base + (uint32_t)s * TC_STAGE_BYTES;
+        const uint32_t aH = st, aL = st + TC_A_BYTES, bH = st + 2 * TC_A_BYTES, bL = bH + TC_B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          // K-major: 8 tf32 = 32 B further along the swizzled 128-B row; MN-major: next 8-row k group
+          const uint32_t offA = a_mn ? ks * 1024u : ks * 32u;
+          const uint32_t offB = b_mn ? ks * 1024u : ks * 32u;
+          // K-major  (SW128):        8-row groups 1024 B apart (SBO), LBO unused
+          // MN-major (SW128_BASE32B): 32-wide MN groups 4096 B apart (LBO), 4-row k groups 512 B apart (SBO)
+          const uint32_t lboA = a_mn ? 4096u : 16u, lboB = b_mn ? 4096u : 16u;
+          const uint32_t sboA = a_mn ? 512u : 1024u, sboB = b_mn ? 512u : 1024u;
+          const uint32_t ltA = a_mn ? 1u : 2u, ltB = b_mn ? 1u : 2u;
+          const uint64_t dAh = tc_smem_desc(aH + offA, lboA, sboA, ltA), dAl = tc_smem_desc(aL + offA, lboA, sboA, ltA);
+          const uint64_t dBh = tc_smem_desc(bH + offB, lboB, sboB, ltB), dBl = tc_smem_desc(bL + offB, lboB, sboB, ltB);
+          const int mi = (kc * nmain) / nk;
+          const uint32_t d_main = tmem_base + 64u * (uint32_t)mi, d_cross = tmem_base + 64u * TC_NMAIN;
+          const bool first_main = (ks == 0) && (kc == 0 || ((kc - 1) * nmain) / nk != mi);
+          tc_mma_tf32(d_cross, dAh, dBl, idesc, (kc | ks) != 0 ? 1u : 0u);
+          tc_mma_tf32(d_cross, dAl, dBh, idesc, 1u);
+          tc_mma_tf32(d_main, dAh, dBh, idesc, first_main ? 0u : 1u);
+        }
+        tc_commit(empty_bar(s));          // smem stage reusable once these MMAs have read it
+      }
+      tc_commit(accum_bar);               // accumulator complete
+    }
+  } else {
+    // =============================== splitter, then epilogue ===============================
+    const int t = threadIdx.x - 64;       // 0..127
+    const bool want_bsum = (P->mode == GEMM_WGRAD) && (P->C2 != nullptr) && (blockIdx.x == 0);
+    float bs[4][4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bs[g][q] = 0.f;
+
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % TC_STAGES;
+      const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      uint8_t* st = gbase + (size_t)s * TC_STAGE_BYTES;
+      float4* aH = reinterpret_cast<float4*>(st);
+      float4* aL = reinterpret_cast<float4*>(st + TC_A_BYTES);
+      float4* bH = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES);
+      float4* bL = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES + TC_B_BYTES);
+      auto split = [](float4 v, float4& hi, float4& lo) {
+        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+      };
+#pragma unroll
+      for (int i = 0; i < TC_A_BYTES / 16 / TC_SPLIT_THREADS; ++i) {     // 8 x 16-B vectors of A
+        const int idx = t + i * TC_SPLIT_THREADS;
+        const float4 v = aH[idx];
+        float4 hi, lo;
+        split(v, hi, lo);
+        aH[idx] = hi;
+        aL[idx] = lo;
+        if (want_bsum) {   // MN-major A tile: [g = idx/256][k = (idx%256)/8][slot = idx%8], 32-B chunk (slot/2) ^= (k&3)
+          bs[i >> 1][0] += v.x; bs[i >> 1][1] += v.y; bs[i >> 1][2] += v.z; bs[i >> 1][3] += v.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TC_B_BYTES / 16 / TC_SPLIT_THREADS; ++i) {     // 4 x 16-B vectors of B
+        const int idx = t + i * TC_SPLIT_THREADS;
+        const float4 v = bH[idx];
+        float4 hi, lo;
+        split(v, hi, lo);
+        bH[idx] = hi;
+        bL[idx] = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+      mbar_arrive(ready_bar(s));
+    }
+
+    if (want_bsum) {
+      // thread t saw, for every g, physical 16-B slot t%8 of rows k = t/8 and 16 + t/8; SW128_BASE32B
+      // XORs the 32-B chunk index (slot/2) with k&3, so its logical 4-float m-vector is:
+      const int j = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1), r = t >> 3;   // r = 0..15: 16 partials per column
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bsum_g[r * TC_BM + g * 32 + j * 4 + q] = bs[g][q];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int m = m0 + t;
+      if (m < M) {
+        float ssum = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) ssum += bsum_g[rr * TC_BM + t];
+        P->C2[m] = ssum;
+      }
+    }
+
+    // ---- epilogue: TMEM -> registers -> global ----
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
+    const int m = m0 + q * 32 + lane;
+    const int mode = P->mode, relu = P->relu, ldc = P->ldc;
+    const float* bias = P->bias;
+    const float* mask = P->mask;
+#pragma unroll
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      uint32_t v[32], w[32];
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      const int nmain = nk < TC_NMAIN ? nk : TC_NMAIN;
+      tc_ld32(lane_addr, v);                                  // main[0]
+      for (int mi = 1; mi < nmain; ++mi) {
+        tc_ld32(lane_addr + 64u * (uint32_t)mi, w);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
+      }
+      tc_ld32(lane_addr + 64u * TC_NMAIN, w);                 // cross terms
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
+      if (m < M) {
+        float* crow = P->C + (long long)m * ldc;
+        const float* mrow = mask ? mask + (long long)m * P->ldmask : nullptr;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int n = n0 + c * 32 + jj;
+          if (n < N) {
+            float x = __uint_as_float(v[jj]);
+            if (mode == GEMM_FWD) {
+              if (bias) x += __ldg(bias + n);
+              if (relu) x = fmaxf(x, 0.f);
+            } else if (mode == GEMM_DGRAD) {
+              if (mrow && !(mrow[n] > 0.f)) x = 0.f;
+            }
+            crow[n] = x;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace bsac

@@ -555,7 +555,8 @@ struct AdamArgs {
   const float* lq; const float* la; const float* logp_cur; const float* logstd_sum; const int* tid;
   long long rsY, rsLogp, rsR;
   float* log_alpha; float* m_alpha; float* v_alpha; float* g_alpha;   // arena pointers
-  float* losses;                                     // [kLossSlots][R][4]
+  float* losses;                                     // [kLossSlots][R][4] device ring
+  float* losses_host;                                // same ring in mapped pinned host memory (zero-copy D2H)
   int R;
 };
 
@@ -620,11 +621,12 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
   };
   const long long slot = (P.cnt[rep].v[3] - 1) % kLossSlots;
   float* L = P.losses + ((long long)slot * P.R + rep) * 4;
+  float* LH = P.losses_host + ((long long)slot * P.R + rep) * 4;
   if (P.tail == TAIL_CRITIC_LOSS) {
     float s = 0.f;
     for (int i = tid; i < B; i += 256) s += (P.lq + rep * P.rsY)[i];
     s = block_sum(s);
-    if (tid == 0) L[0] = s * K.c_loss;
+    if (tid == 0) { L[0] = s * K.c_loss; LH[0] = L[0]; }
     return;
   }
   // TAIL_ALPHA_AND_LOSSES: actor loss, entropy, temperature gradient + its Adam step
@@ -639,6 +641,7 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
     if (tid == 0) {
       L[1] = s * K.c_loss;
       L[3] = 0.5f * K.act * (1.0f + 1.8378770664093453f) + e * K.inv_B;   // 0.5 A (1+log 2pi) + mean(sum log_std)
+      LH[1] = L[1]; LH[3] = L[3];
     }
     const int Teff = K.T > 0 ? K.T : 1;
     float* la = P.log_alpha + rep * P.rsP;
@@ -661,7 +664,7 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
         la[t] = pi; (P.m_alpha + rep * P.rsM)[t] = mi; (P.v_alpha + rep * P.rsM)[t] = vi;
       }
     }
-    if (tid == 0) L[2] = aloss;
+    if (tid == 0) { L[2] = aloss; LH[2] = aloss; __threadfence_system(); }
   }
 }
 

@@ -143,6 +143,19 @@ int b200sac_soft_update(b200sac_t* h, double tau, void* stream);
 int b200sac_debug_read(b200sac_t* h, const char* name, int32_t replica, float* out_host, int64_t cap_floats,
                        int64_t* n_floats, void* stream);
 
+/* Eager (no graph) run of `iters` sampled steps from a DEVICE ring with a CUDA event between all
+ * launches: out_ms[i] = mean device time of launch i of the step (0 = sampling + ingest).
+ * names (nullable): ';'-separated kernel labels.  Measurement helper for bench.py's roofline. */
+int b200sac_profile_step(b200sac_t* h, b200sac_replay_t* rb, int32_t iters, float* out_ms, int32_t cap,
+                         int32_t* n_out, char* names, int32_t names_cap, void* stream);
+
+/* Stand-alone run of the tcgen05 3xTF32 GEMM kernel on DEVICE arrays (parity tests of the tensor-core
+ * path): mode 0 FWD C[M][N] = act(A[M][K] B[N][K]^T + bias), 1 DGRAD C[M][N] = (A[M][K] B[K][N]) * [mask > 0],
+ * 2 WGRAD C[M][N] = A[K][M]^T B[K][N], C2[M] = column sums of A.  Synchronises. */
+int b200sac_tc_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,
+                         int32_t ldb, const float* bias, const float* mask, int32_t ldmask, float* C, int32_t ldc,
+                         float* C2, int32_t relu, void* stream);
+
 /* Number of kernels one step launches (for bench.py's gpu_launches accounting). */
 int b200sac_launches_per_step(b200sac_t* h, int32_t* n);
 
