@@ -225,6 +225,15 @@ class SacCore:
         labels = names.value.decode().split(";")
         return [(labels[i], float(out[i])) for i in range(n.value)]
 
+    def graph_timeline(self, replay: "Replay", iters: int = 200):
+        """Mean in-graph start-to-start time (us) of every launch of one step: [sample, ingest, plan...]."""
+        cap = 256
+        out = (C.c_float * cap)()
+        n = C.c_int32(0)
+        _lib.check(self.lib.b200sac_graph_timeline(self._h, replay._h, int(iters), out, cap, C.byref(n), _stream()))
+        self.steps_done += int(iters) + 6
+        return [float(out[i]) for i in range(n.value)]
+
     def debug(self, name: str, replica=0) -> torch.Tensor:
         cap = self.cfg.batch * max(2 * self.cfg.act_dim, 1)
         out = torch.empty(cap)

@@ -150,6 +150,7 @@ struct Launch {
   size_t smem = 0;
   // payloads (only the one matching `kind` is used)
   const GemmProb* probs = nullptr; int G = 0;
+  GemmGroup grp;
   const TcProb* tprobs = nullptr;
   PolicyHeadArgs pol;
   CriticHeadArgs ch;
@@ -365,13 +366,14 @@ static int build_plan(b200sac* h) {
     Launch l;
     int maxM = 0, maxN = 0;
     for (auto& p : ps) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; }
-    bool big = ((long long)maxM * maxN) >= (long long)512 * 256;
-    if (const char* e = getenv("B200SAC_TILE")) big = (e[0] == 'b');
-    const int bm = big ? 64 : 32, bn = big ? 64 : 32;
-    l.kind = big ? L_GEMM_BIG : L_GEMM_SMALL;
-    l.grid = dim3((maxN + bn - 1) / bn, (maxM + bm - 1) / bm, (unsigned)(ps.size() * R));
-    l.block = dim3(256);
+    l.kind = L_GEMM_SMALL;
+    l.grid = dim3((maxN + GS_T - 1) / GS_T, (maxM + GS_T - 1) / GS_T, (unsigned)(ps.size() * R));
+    l.block = dim3(GS_THREADS);
     l.G = (int)ps.size();
+    if (ps.size() > GS_MAXG) plan_rc = fail(B200SAC_ERR_INVALID, "internal: more than %d problems in one GEMM group", GS_MAXG);
+    memset(&l.grp, 0, sizeof(l.grp));
+    l.grp.G = l.G;
+    for (size_t i = 0; i < ps.size() && i < GS_MAXG; ++i) l.grp.p[i] = ps[i];
     l.probs = (const GemmProb*)(uintptr_t)h->h_probs.size();   // index for now; rebased later
     for (auto& p : ps) h->h_probs.push_back(p);
     h->plan.push_back(l);
@@ -509,7 +511,7 @@ static int build_plan(b200sac* h) {
       P.log_alpha = W(L.off_alpha);
       P.dout_dbg = h->dout_dbg.p; P.dact_dbg = h->dact_dbg.p; P.rsDbg = h->dout_dbg.rs;
     }
-    l.grid = dim3((P.Kdim + 31) / 32, P.nets, R);
+    l.grid = dim3((P.Kdim + kHbCols - 1) / kHbCols, P.nets, R);
     l.block = dim3(256);
     l.smem = ((size_t)B * P.NO + 256 * (size_t)P.NO) * sizeof(float);
     h->plan.push_back(l);
@@ -636,37 +638,51 @@ static int build_plan(b200sac* h) {
   return 0;
 }
 
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor
+// drains; every kernel begins with griddepcontrol.wait (common.cuh::kstamp), so data dependencies hold.
+static bool g_use_pdl = true;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* evs = nullptr) {
   for (size_t i = 0; i < h->plan.size(); ++i) {
     Launch& l = h->plan[i];
     if (evs) CU(cudaEventRecord(evs[i], st));
     switch (l.kind) {
       case L_GEMM_BIG:
-        gemm_simt_kernel<64, 64, 4, 4><<<l.grid, l.block, 0, st>>>(l.probs, l.G);
-        break;
       case L_GEMM_SMALL:
-        gemm_simt_kernel<32, 32, 2, 2><<<l.grid, l.block, 0, st>>>(l.probs, l.G);
+        launch_k(gemm_simt_kernel, l.grid, l.block, 0, st, l.grp);
         break;
       case L_GEMM_TC:
-        gemm_tc_kernel<<<l.grid, l.block, l.smem, st>>>(l.tprobs);
+        launch_k(gemm_tc_kernel, l.grid, l.block, l.smem, st, l.tprobs);
         break;
       case L_POLICY: {
         PolicyHeadArgs P = l.pol;
         P.use_eps_buf = use_eps_buf ? 1 : 0;
-        policy_head_kernel<<<l.grid, l.block, 0, st>>>(h->K, P);
+        launch_k(policy_head_kernel, l.grid, l.block, 0, st, h->K, P);
         break;
       }
       case L_CHEADS:
-        critic_heads_kernel<<<l.grid, l.block, 0, st>>>(h->K, l.ch);
+        launch_k(critic_heads_kernel, l.grid, l.block, 0, st, h->K, l.ch);
         break;
       case L_AQHEADS:
-        actor_q_heads_kernel<<<l.grid, l.block, 0, st>>>(h->K, l.aq);
+        launch_k(actor_q_heads_kernel, l.grid, l.block, 0, st, h->K, l.aq);
         break;
       case L_HEADBWD:
-        head_bwd_kernel<<<l.grid, l.block, l.smem, st>>>(h->K, l.hb);
+        launch_k(head_bwd_kernel, l.grid, l.block, l.smem, st, h->K, l.hb);
         break;
       case L_ADAM:
-        adam_kernel<<<l.grid, l.block, 0, st>>>(h->K, l.ad);
+        launch_k(adam_kernel, l.grid, l.block, 0, st, h->K, l.ad);
         break;
     }
   }
@@ -694,6 +710,10 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   h->cfg = *cfg;
   h->device = device;
   h->R = cfg->replicas;
+  // measured on B200 (LL, one learner): PDL shortens the tcgen05 step (211 -> 201 us) but lengthens the
+  // FFMA one (158 -> 171 us: early-launched CTAs take slots from the draining predecessor)
+  g_use_pdl = (cfg->precision == 1);
+  if (const char* e = getenv("B200SAC_PDL")) g_use_pdl = (e[0] != '0');
   build_layout(cfg, h->L);
   const Layout& L = h->L;
   const int B = cfg->batch, R = h->R, A = cfg->act_dim, obs = cfg->state_dim + cfg->num_tasks, xw = obs + A;
@@ -732,7 +752,11 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   CUH(cudaMemset(h->adam_m, 0, sizeof(float) * L.trainable * R));
   CUH(cudaMemset(h->adam_v, 0, sizeof(float) * L.trainable * R));
   CUH(cudaMemset(h->grads, 0, sizeof(float) * L.trainable * R));
-  CUH(cudaMemset(h->cnt, 0, sizeof(Counters) * R));
+  {
+    std::vector<Counters> c0((size_t)R);
+    for (auto& c : c0) { memset(&c, 0, sizeof(c)); for (int i = 0; i < 3; ++i) c.b1p[i] = c.b2p[i] = 1.0; }
+    CUH(cudaMemcpy(h->cnt, c0.data(), sizeof(Counters) * R, cudaMemcpyHostToDevice));
+  }
   CUH(cudaMemset(h->losses, 0, sizeof(float) * kLossSlots * R * 4));
 
   // work slab
@@ -893,7 +917,11 @@ extern "C" int b200sac_set_steps(b200sac_t* h, int32_t replica, const int64_t st
   CU(cudaSetDevice(h->device));
   Counters c;
   CU(cudaMemcpy(&c, h->cnt + replica, sizeof(c), cudaMemcpyDeviceToHost));
-  c.v[0] = steps[0]; c.v[1] = steps[1]; c.v[2] = steps[2];
+  for (int i = 0; i < 3; ++i) {
+    c.v[i] = steps[i];
+    c.b1p[i] = pow(h->cfg.beta1, (double)steps[i]);
+    c.b2p[i] = pow(h->cfg.beta2, (double)steps[i]);
+  }
   CU(cudaMemcpy(h->cnt + replica, &c, sizeof(c), cudaMemcpyHostToDevice));
   return 0;
 }
@@ -936,8 +964,8 @@ static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* co
   bool use_eps = false;
   if (variant == 0) {
     use_eps = p[5] != nullptr;
-    ingest_split_kernel<<<grid, block, 0, st>>>(h->K, h->ing, (const float*)p[0], (const float*)p[1], (const float*)p[2],
-                                                (const float*)p[3], (const float*)p[4], (const float*)p[5], (const float*)p[6]);
+    launch_k(ingest_split_kernel, grid, block, 0, st, h->K, h->ing, (const float*)p[0], (const float*)p[1], (const float*)p[2],
+             (const float*)p[3], (const float*)p[4], (const float*)p[5], (const float*)p[6]);
   } else if (variant == 1) {
     const float* rows = (const float*)p[0];
     const float* e = (const float*)p[1];
@@ -946,7 +974,8 @@ static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* co
       // eps staged as [R][B][A] next, then [R][B][A] cur: reuse the split ingest just for the noise
       // (rows carry the transition itself)
     }
-    ingest_rows_kernel<<<grid, block, 0, st>>>(h->K, h->ing, rows, (long long)B * h->row_stride, h->row_stride, nullptr, 0);
+    launch_k(ingest_rows_kernel, grid, block, 0, st, h->K, h->ing, rows, (long long)B * h->row_stride, h->row_stride,
+             (const int*)nullptr, (long long)0);
     if (use_eps) {
       const size_t n = (size_t)B * h->cfg.act_dim * sizeof(float);
       for (int rep = 0; rep < R; ++rep) {
@@ -956,8 +985,10 @@ static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* co
       }
     }
   } else {
-    sample_indices_kernel<<<R, 256, 0, st>>>(h->K, h->cnt, rb->d_fill, rb->cap_per_task, rb->d_idx, B, rb->seed);
-    ingest_rows_kernel<<<grid, block, 0, st>>>(h->K, h->ing, rb->rows, rb->rs_rows, h->row_stride, rb->d_idx, B);
+    launch_k(sample_indices_kernel, dim3(R), dim3(256), 0, st, h->K, (const Counters*)h->cnt, (const long long*)rb->d_fill,
+             rb->cap_per_task, rb->d_idx, (long long)B, rb->seed);
+    launch_k(ingest_rows_kernel, grid, block, 0, st, h->K, h->ing, (const float*)rb->rows, rb->rs_rows, h->row_stride,
+             (const int*)rb->d_idx, (long long)B);
   }
   CU(cudaGetLastError());
   return run_plan(h, st, use_eps, evs ? evs + 1 : nullptr);
@@ -1094,10 +1125,10 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
     case L_GEMM_SMALL: {
       const GemmProb& p0 = hp[(size_t)(l.probs - dbase)];
       const GemmProb& pl = hp[(size_t)(l.probs - dbase) + l.G - 1];
-      if (p0.mode == GEMM_FWD) return l.kind == L_GEMM_BIG ? "gemm_fwd(64x64)" : "gemm_fwd(32x32)";
-      if (p0.mode == GEMM_WGRAD && pl.mode == GEMM_DGRAD) return l.kind == L_GEMM_BIG ? "gemm_wgrad+dgrad(64x64)" : "gemm_wgrad+dgrad(32x32)";
-      if (p0.mode == GEMM_WGRAD) return l.kind == L_GEMM_BIG ? "gemm_wgrad(64x64)" : "gemm_wgrad(32x32)";
-      return l.kind == L_GEMM_BIG ? "gemm_dgrad(64x64)" : "gemm_dgrad(32x32)";
+      if (p0.mode == GEMM_FWD) return "gemm_fwd(ffma)";
+      if (p0.mode == GEMM_WGRAD && pl.mode == GEMM_DGRAD) return "gemm_wgrad+dgrad(ffma)";
+      if (p0.mode == GEMM_WGRAD) return "gemm_wgrad(ffma)";
+      return "gemm_dgrad(ffma)";
     }
     case L_POLICY: return "policy_head";
     case L_CHEADS: return "critic_heads";
@@ -1166,6 +1197,67 @@ extern "C" int b200sac_tc_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t 
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(d);
   if (e != cudaSuccess) return fail(B200SAC_ERR_CUDA, "gemm_tc_kernel failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// clock64() timeline of CTA (0,0) of one warm tcgen05 GEMM launch (see TC_STAMP indices in gemm_tc.cuh).
+extern "C" int b200sac_tc_gemm_timeline(int32_t mode, int32_t M, int32_t N, int32_t K, long long* out96) {
+  float *A = nullptr, *B = nullptr, *C = nullptr;
+  long long* dbg = nullptr;
+  const size_t na = (size_t)(mode == GEMM_WGRAD ? K * M : M * K), nb = (size_t)(mode == GEMM_FWD ? N * K : K * N);
+  CU(cudaMalloc(&A, na * 4)); CU(cudaMalloc(&B, nb * 4)); CU(cudaMalloc(&C, (size_t)M * N * 4)); CU(cudaMalloc(&dbg, 96 * 8));
+  CU(cudaMemset(A, 0, na * 4)); CU(cudaMemset(B, 0, nb * 4)); CU(cudaMemset(dbg, 0, 96 * 8));
+  GemmProb p;
+  memset(&p, 0, sizeof(p));
+  p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.mode = mode;
+  p.lda = mode == GEMM_WGRAD ? M : K; p.ldb = mode == GEMM_FWD ? K : N; p.ldc = N;
+  TcProb t;
+  if (int rc = make_tc_prob(p, 0, t)) return rc;
+  t.dbg = dbg;
+  TcProb* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(TcProb)));
+  CU(cudaMemcpy(d, &t, sizeof(TcProb), cudaMemcpyHostToDevice));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM, 1);
+  for (int it = 0; it < 3; ++it) gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES>>>(d);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out96, dbg, 96 * 8, cudaMemcpyDeviceToHost));
+  cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(dbg); cudaFree(d);
+  return 0;
+}
+
+// In-graph timeline: run `iters` sampled steps (graph launches) with kernel-start stamping enabled and
+// return the mean start-to-start time (us) of each launch of the step: out_us[0] = sampling kernel, ...,
+// out_us[n-1] = last kernel (measured to the next step's first kernel).
+extern "C" int b200sac_graph_timeline(b200sac_t* h, b200sac_replay_t* rb, int32_t iters, float* out_us, int32_t cap,
+                                      int32_t* n_out, void* stream) {
+  if (!h || !rb || rb->h != h || rb->where != 0 || !out_us || !n_out) return fail(B200SAC_ERR_INVALID, "graph_timeline needs a device ring");
+  CU(cudaSetDevice(h->device));
+  const int n = (int)h->plan.size() + 2;       // sample + ingest + plan
+  *n_out = n;
+  if (cap < n) return fail(B200SAC_ERR_INVALID, "need room for %d launches", n);
+  const int total = n * (iters + 1);
+  unsigned long long* dt = nullptr;
+  int* di = nullptr;
+  CU(cudaMalloc(&dt, sizeof(unsigned long long) * total));
+  CU(cudaMalloc(&di, sizeof(int)));
+  CU(cudaMemset(di, 0, sizeof(int)));
+  StampBuf sb_on = {dt, di, total}, sb_off = {nullptr, nullptr, 0};
+  if (int rc = b200sac_step_sampled(h, rb, 5, stream)) return rc;     // warm (graph instantiated)
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyToSymbol(g_stamp, &sb_on, sizeof(StampBuf)));
+  int rc = b200sac_step_sampled(h, rb, iters + 1, stream);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyToSymbol(g_stamp, &sb_off, sizeof(StampBuf)));
+  if (rc) return rc;
+  std::vector<unsigned long long> t((size_t)total);
+  CU(cudaMemcpy(t.data(), dt, sizeof(unsigned long long) * total, cudaMemcpyDeviceToHost));
+  cudaFree(dt); cudaFree(di);
+  for (int i = 0; i < n; ++i) {
+    double acc = 0;
+    for (int it = 0; it < iters; ++it) acc += (double)(t[(size_t)it * n + i + 1] - t[(size_t)it * n + i]);
+    out_us[i] = (float)(acc / iters * 1e-3);
+  }
   return 0;
 }
 

@@ -55,6 +55,26 @@ B200_D void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
   z1 = r * s;
 }
 
+// In-graph timeline: when enabled, the first thread of every kernel appends %globaltimer (ns) to a
+// device buffer.  Kernels of a step run back to back on one stream, so consecutive differences are the
+// true per-kernel times inside the CUDA graph (launch gaps included) -- unlike ncu's cold, serialised ones.
+struct StampBuf { unsigned long long* t; int* idx; int cap; };
+__device__ StampBuf g_stamp = {nullptr, nullptr, 0};
+// Every step kernel starts with kstamp(): (1) programmatic dependent launch -- wait until the
+// predecessor grid has completed and flushed (no-op when launched without the PDL attribute), then let
+// the successor start launching right away (it blocks at its own wait), so launch latency overlaps
+// execution; (2) the optional timeline stamp.
+B200_D void kstamp() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (g_stamp.t != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    const int i = atomicAdd(g_stamp.idx, 1);
+    if (i < g_stamp.cap) g_stamp.t[i] = ns;
+  }
+}
+
 B200_D float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -7,8 +7,9 @@
 //               SWIZZLE_128B_ATOM_32B for MN-major ones) of the fp32 operands,
 //               straight from the row-major activation / weight / gradient buffers; out-of-range
 //               rows and columns are zero-filled by the TMA unit (ragged 400-wide layers, tails)
-//   warps 2-5   splitter: rewrite each landed tile in place as hi and emit lo beside it (same
-//               swizzled offsets, so the layout is untouched); later the epilogue warps
+//   warps 2-5   splitter: emit lo = x - trunc19(x) beside each landed tile (same swizzled offsets, so the
+//               layout is untouched); the raw fp32 tile itself serves as hi because the tensor core reads
+//               only the top 19 bits of a tf32 operand word (measured); later the epilogue warps
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M=128, N=64, K=8),
 //               12 MMAs per 32-wide k chunk; tcgen05.commit releases the smem stage / signals the
 //               epilogue
@@ -54,8 +55,11 @@ struct alignas(128) TcProb {
   int ldc, ldmask;
   int mode, relu;
   int a_mn, b_mn;
-  int pad[3];
+  int pad[1];
+  long long* dbg;      // optional clock64() timeline of CTA (0,0) (b200sac_tc_gemm_timeline)
 };
+
+#define TC_STAMP(i) do { if (dbg) dbg[(i)] = clock64(); } while (0)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 B200_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,6 +125,13 @@ B200_D void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+B200_D void stg_f32(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+B200_D float ldg_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 // smem matrix descriptor, Blackwell version field = 1 (cute::UMMA::SmemDescriptor).
 // layout_type 2 = SWIZZLE_128B (16-B atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-B atoms;
 // the only layout tcgen05 accepts for MN-major tf32 operands).
@@ -134,6 +145,12 @@ B200_D uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_by
   return d;
 }
 
+// number of main accumulators for nk k-chunks: ~2 chunks (8 MMAs) each, at most TC_NMAIN
+B200_D int tc_nmain(int nk) {
+  int n = nk / 2;
+  return n < 1 ? 1 : (n > TC_NMAIN ? TC_NMAIN : n);
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
 B200_D uint32_t tc_instr_desc(int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
@@ -141,6 +158,7 @@ B200_D uint32_t tc_instr_desc(int a_mn, int b_mn) {
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __restrict__ probs) {
+  kstamp();
   extern __shared__ uint8_t smem_raw[];
   const TcProb* P = probs + blockIdx.z;
   const int M = P->M, N = P->N, K = P->K;
@@ -164,6 +182,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int nk = (K + TC_BK - 1) / TC_BK;
+  long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x % 32) == 0) ? P->dbg : nullptr;
+  if (threadIdx.x == 0) TC_STAMP(0);
   const int a_mn = P->a_mn, b_mn = P->b_mn;
 
   if (warp == 0 && lane == 0) {
@@ -183,6 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -191,6 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         const int s = kc % TC_STAGES;
         const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
+        if (kc < 16) TC_STAMP(2 + kc);
         const uint32_t st = base + (uint32_t)s * TC_STAGE_BYTES;
         const uint32_t dA = st, dB = st + 2 * TC_A_BYTES;
         mbar_expect_tx(full_bar(s), TC_A_BYTES + TC_B_BYTES);
@@ -211,34 +233,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       const uint32_t idesc = tc_instr_desc(a_mn, b_mn);
-      const int nmain = nk < TC_NMAIN ? nk : TC_NMAIN;   // chunk kc accumulates into main[(kc * nmain) / nk]
+      const int nmain = tc_nmain(nk);                    // chunk kc accumulates into main[(kc * nmain) / nk]
       for (int kc = 0; kc < nk; ++kc) {
         const int s = kc % TC_STAGES;
         const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
         mbar_wait(ready_bar(s), ph);
+        if (kc < 16) TC_STAMP(50 + 2 * kc);
         tc_fence_after();
         const uint32_t st = base + (uint32_t)s * TC_STAGE_BYTES;
-        const uint32_t aH = st, aL = st + TC_A_BYTES, bH = st + 2 * TC_A_BYTES, bL = bH + TC_B_BYTES;
+        // One descriptor per operand per chunk; everything else is an add on the 14-bit address field
+        // (units of 16 B): +A_BYTES -> lo copy, +2*A_BYTES -> B tile, k step = 32 B (K-major) / 1024 B (MN-major).
+        const uint64_t dA0 = tc_smem_desc(st, a_mn ? 4096u : 16u, a_mn ? 512u : 1024u, a_mn ? 1u : 2u);
+        const uint64_t dB0 = tc_smem_desc(st + 2 * TC_A_BYTES, b_mn ? 4096u : 16u, b_mn ? 512u : 1024u, b_mn ? 1u : 2u);
+        const uint64_t stepA = a_mn ? (1024u >> 4) : (32u >> 4), stepB = b_mn ? (1024u >> 4) : (32u >> 4);
+        const int mi = (kc * nmain) / nk;
+        const uint32_t d_main = tmem_base + 64u * (uint32_t)mi, d_cross = tmem_base + 64u * TC_NMAIN;
+        const bool new_main = (kc == 0) || (((kc - 1) * nmain) / nk != mi);
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
-          // K-major: 8 tf32 = 32 B further along the swizzled 128-B row; MN-major: next 8-row k group
-          const uint32_t offA = a_mn ? ks * 1024u : ks * 32u;
-          const uint32_t offB = b_mn ? ks * 1024u : ks * 32u;
-          // K-major  (SW128):        8-row groups 1024 B apart (SBO), LBO unused
-          // MN-major (SW128_BASE32B): 32-wide MN groups 4096 B apart (LBO), 4-row k groups 512 B apart (SBO)
-          const uint32_t lboA = a_mn ? 4096u : 16u, lboB = b_mn ? 4096u : 16u;
-          const uint32_t sboA = a_mn ? 512u : 1024u, sboB = b_mn ? 512u : 1024u;
-          const uint32_t ltA = a_mn ? 1u : 2u, ltB = b_mn ? 1u : 2u;
-          const uint64_t dAh = tc_smem_desc(aH + offA, lboA, sboA, ltA), dAl = tc_smem_desc(aL + offA, lboA, sboA, ltA);
-          const uint64_t dBh = tc_smem_desc(bH + offB, lboB, sboB, ltB), dBl = tc_smem_desc(bL + offB, lboB, sboB, ltB);
-          const int mi = (kc * nmain) / nk;
-          const uint32_t d_main = tmem_base + 64u * (uint32_t)mi, d_cross = tmem_base + 64u * TC_NMAIN;
-          const bool first_main = (ks == 0) && (kc == 0 || ((kc - 1) * nmain) / nk != mi);
+          const uint64_t dAh = dA0 + stepA * ks, dAl = dAh + (TC_A_BYTES >> 4);
+          const uint64_t dBh = dB0 + stepB * ks, dBl = dBh + (TC_B_BYTES >> 4);
           tc_mma_tf32(d_cross, dAh, dBl, idesc, (kc | ks) != 0 ? 1u : 0u);
           tc_mma_tf32(d_cross, dAl, dBh, idesc, 1u);
-          tc_mma_tf32(d_main, dAh, dBh, idesc, first_main ? 0u : 1u);
+          tc_mma_tf32(d_main, dAh, dBh, idesc, (new_main && ks == 0) ? 0u : 1u);
         }
         tc_commit(empty_bar(s));          // smem stage reusable once these MMAs have read it
+        if (kc < 16) TC_STAMP(51 + 2 * kc);
       }
       tc_commit(accum_bar);               // accumulator complete
     }
@@ -256,41 +276,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
       const int s = kc % TC_STAGES;
       const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
       mbar_wait(full_bar(s), ph);
+      if (t == 0 && kc < 16) TC_STAMP(18 + 2 * kc);
       uint8_t* st = gbase + (size_t)s * TC_STAGE_BYTES;
       float4* aH = reinterpret_cast<float4*>(st);
       float4* aL = reinterpret_cast<float4*>(st + TC_A_BYTES);
       float4* bH = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES);
       float4* bL = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES + TC_B_BYTES);
-      auto split = [](float4 v, float4& hi, float4& lo) {
-        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+      // tcgen05 kind::tf32 reads only the top 19 bits of each fp32 operand word (measured: using the raw
+      // tile as "hi" is bit-identical to masking it first; a round-to-nearest model is off by 9e-4), so the
+      // raw tile stays in place as the hi operand and only lo = x - trunc19(x) is written.
+      auto split = [](float4 v, float4& lo) {
+        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
       };
+      constexpr int NA = TC_A_BYTES / 16 / TC_SPLIT_THREADS, NB = TC_B_BYTES / 16 / TC_SPLIT_THREADS;   // 8, 4
+      float4 va[NA], vb[NB];
 #pragma unroll
-      for (int i = 0; i < TC_A_BYTES / 16 / TC_SPLIT_THREADS; ++i) {     // 8 x 16-B vectors of A
-        const int idx = t + i * TC_SPLIT_THREADS;
-        const float4 v = aH[idx];
-        float4 hi, lo;
-        split(v, hi, lo);
-        aH[idx] = hi;
-        aL[idx] = lo;
+      for (int i = 0; i < NA; ++i) va[i] = aH[t + i * TC_SPLIT_THREADS];   // all loads first
+#pragma unroll
+      for (int i = 0; i < NB; ++i) vb[i] = bH[t + i * TC_SPLIT_THREADS];
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        float4 lo;
+        split(va[i], lo);
+        aL[t + i * TC_SPLIT_THREADS] = lo;
         if (want_bsum) {   // MN-major A tile: [g = idx/256][k = (idx%256)/8][slot = idx%8], 32-B chunk (slot/2) ^= (k&3)
-          bs[i >> 1][0] += v.x; bs[i >> 1][1] += v.y; bs[i >> 1][2] += v.z; bs[i >> 1][3] += v.w;
+          bs[i >> 1][0] += va[i].x; bs[i >> 1][1] += va[i].y; bs[i >> 1][2] += va[i].z; bs[i >> 1][3] += va[i].w;
         }
       }
 #pragma unroll
-      for (int i = 0; i < TC_B_BYTES / 16 / TC_SPLIT_THREADS; ++i) {     // 4 x 16-B vectors of B
-        const int idx = t + i * TC_SPLIT_THREADS;
-        const float4 v = bH[idx];
-        float4 hi, lo;
-        split(v, hi, lo);
-        bH[idx] = hi;
-        bL[idx] = lo;
+      for (int i = 0; i < NB; ++i) {
+        float4 lo;
+        split(vb[i], lo);
+        bL[t + i * TC_SPLIT_THREADS] = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
       mbar_arrive(ready_bar(s));
+      if (t == 0 && kc < 16) TC_STAMP(19 + 2 * kc);
     }
 
     if (want_bsum) {
@@ -313,49 +337,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
 
     // ---- epilogue: TMEM -> registers -> global ----
     mbar_wait(accum_bar, 0);
+    if (t == 0) TC_STAMP(82);
     tc_fence_after();
     const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
-    const int m = m0 + q * 32 + lane;
     const int mode = P->mode, relu = P->relu, ldc = P->ldc;
-    const float* bias = P->bias;
-    const float* mask = P->mask;
+    const float* __restrict__ bias = P->bias;
+    const float* __restrict__ mask = P->mask;
+    float* __restrict__ Cout = P->C;
+    const int ldmask = P->ldmask;
+    const int nmain = tc_nmain(nk);
+    // All MMAs have completed (accum barrier), so the pipeline stages are free: each warp transposes its
+    // 32x32 block through a padded smem scratch so that global stores / mask loads are row-contiguous.
+    float* scratch = reinterpret_cast<float*>(gbase) + (warp - 2) * (32 * 33);
 #pragma unroll
     for (int c = 0; c < TC_BN / 32; ++c) {
       uint32_t v[32], w[32];
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-      const int nmain = nk < TC_NMAIN ? nk : TC_NMAIN;
       tc_ld32(lane_addr, v);                                  // main[0]
+      if (t == 0 && c == 0) TC_STAMP(85);
       for (int mi = 1; mi < nmain; ++mi) {
         tc_ld32(lane_addr + 64u * (uint32_t)mi, w);
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
       }
       tc_ld32(lane_addr + 64u * TC_NMAIN, w);                 // cross terms
+      if (t == 0 && c == 0) TC_STAMP(86);
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
-      if (m < M) {
-        float* crow = P->C + (long long)m * ldc;
-        const float* mrow = mask ? mask + (long long)m * P->ldmask : nullptr;
+      for (int jj = 0; jj < 32; ++jj) scratch[lane * 33 + jj] = __uint_as_float(v[jj]) + __uint_as_float(w[jj]);
+      __syncwarp();
+      if (t == 0 && c == 0) TC_STAMP(87);
+      const int n = n0 + c * 32 + lane;                       // this lane's output column
+      const bool nin = n < N;
+      const float bv = (mode == GEMM_FWD && bias && nin) ? __ldg(bias + n) : 0.f;
+      const int mrow0 = m0 + q * 32;
+      float* __restrict__ cptr = Cout + (long long)mrow0 * ldc + n;
+      const float* __restrict__ mptr = mask ? mask + (long long)mrow0 * ldmask + n : nullptr;
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int n = n0 + c * 32 + jj;
-          if (n < N) {
-            float x = __uint_as_float(v[jj]);
-            if (mode == GEMM_FWD) {
-              if (bias) x += __ldg(bias + n);
-              if (relu) x = fmaxf(x, 0.f);
-            } else if (mode == GEMM_DGRAD) {
-              if (mrow && !(mrow[n] > 0.f)) x = 0.f;
-            }
-            crow[n] = x;
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float x[8], mk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = scratch[(r0 + u) * 33 + lane];
+        if (mode == GEMM_DGRAD && mptr) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) mk[u] = (nin && mrow0 + r0 + u < M) ? ldg_f32(mptr + (long long)(r0 + u) * ldmask) : 1.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) x[u] = mk[u] > 0.f ? x[u] : 0.f;
+        } else if (mode == GEMM_FWD) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            x[u] += bv;
+            if (relu) x[u] = fmaxf(x[u], 0.f);
           }
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (nin && mrow0 + r0 + u < M) stg_f32(cptr + (long long)(r0 + u) * ldc, x[u]);
       }
+      __syncwarp();
+      if (t == 0 && c == 0) TC_STAMP(88);
     }
   }
 
+  if (threadIdx.x == 64) TC_STAMP(83);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(84);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");

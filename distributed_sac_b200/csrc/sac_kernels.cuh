@@ -29,8 +29,9 @@ struct StepConst {
   unsigned long long seed;
 };
 
-// Mutable per-replica counters in device memory: [0..2] Adam steps critic/actor/alpha, [3] step index.
-struct Counters { long long v[4]; };
+// Mutable per-replica counters in device memory: v[0..2] Adam steps critic/actor/alpha, v[3] step index;
+// b1p/b2p[i] = beta^v[i], kept as running products so no kernel needs a double-precision pow().
+struct Counters { long long v[4]; double b1p[3]; double b2p[3]; };
 
 // ------------------------------------------------------------------------------------------
 // Ingest: scatter one minibatch into the four pre-concatenated layer-0 inputs
@@ -80,9 +81,11 @@ B200_D void ingest_row(const StepConst& K, const IngestOut& O, int rep, int i, c
   }
 }
 
-B200_D void bump_counters(Counters* cnt, int rep) {
+B200_D void bump_counters(Counters* cnt, int rep, double beta1, double beta2) {
   Counters* c = cnt + rep;
   c->v[0] += 1; c->v[1] += 1; c->v[2] += 1; c->v[3] += 1;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { c->b1p[i] *= beta1; c->b2p[i] *= beta2; }
 }
 
 // minibatch given as five separate arrays [R][B][w]
@@ -90,10 +93,11 @@ __global__ void ingest_split_kernel(StepConst K, IngestOut O, const float* __res
                                     const float* __restrict__ a, const float* __restrict__ r,
                                     const float* __restrict__ s2, const float* __restrict__ d,
                                     const float* __restrict__ eps_next, const float* __restrict__ eps_cur) {
+  kstamp();
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
   const int B = K.B;
-  if (blockIdx.x == 0 && threadIdx.x == 0) bump_counters(O.cnt, rep);
+  if (blockIdx.x == 0 && threadIdx.x == 0) bump_counters(O.cnt, rep, K.beta1, K.beta2);
   for (int i = blockIdx.x * wpb + warp; i < B; i += gridDim.x * wpb) {
     const long long ri = (long long)rep * B + i;
     ingest_row(K, O, rep, i, s + ri * K.obs, a + ri * K.act, r[ri], s2 + ri * K.obs, d[ri], lane, 32);
@@ -111,10 +115,11 @@ __global__ void ingest_split_kernel(StepConst K, IngestOut O, const float* __res
 // (device replay ring) or dense (pinned-host staging after the H2D copy).
 __global__ void ingest_rows_kernel(StepConst K, IngestOut O, const float* __restrict__ rows, long long rs_rows,
                                    int row_stride, const int* __restrict__ idx, long long rs_idx) {
+  kstamp();
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
   const int B = K.B;
-  if (blockIdx.x == 0 && threadIdx.x == 0) bump_counters(O.cnt, rep);
+  if (blockIdx.x == 0 && threadIdx.x == 0) bump_counters(O.cnt, rep, K.beta1, K.beta2);
   for (int i = blockIdx.x * wpb + warp; i < B; i += gridDim.x * wpb) {
     const long long src = idx ? (long long)idx[rep * rs_idx + i] : (long long)i;
     const float* row = rows + rep * rs_rows + src * row_stride;
@@ -134,6 +139,7 @@ constexpr int kHashSlots = 4096;   // >= 2 * max batch (batch <= 2048)
 __global__ void sample_indices_kernel(StepConst K, const Counters* __restrict__ cnt, const long long* __restrict__ fill,
                                       long long cap_per_task, int* __restrict__ idx_out, long long rs_idx,
                                       unsigned long long seed) {
+  kstamp();
   __shared__ int keys[kHashSlots];
   __shared__ int owner[kHashSlots];
   __shared__ int unresolved;
@@ -248,6 +254,7 @@ B200_D PolicyPoint policy_point(float mu, float raw, float eps, float k) {
 }
 
 __global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
+  kstamp();
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int row = blockIdx.x * (blockDim.x / 32) + warp;
@@ -339,6 +346,7 @@ B200_D float warp_dot(const float* __restrict__ x, const float* __restrict__ w, 
 }
 
 __global__ void critic_heads_kernel(StepConst K, CriticHeadArgs P) {
+  kstamp();
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int row = blockIdx.x * (blockDim.x / 32) + warp;
@@ -387,6 +395,7 @@ struct ActorQHeadArgs {
 };
 
 __global__ void actor_q_heads_kernel(StepConst K, ActorQHeadArgs P) {
+  kstamp();
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int row = blockIdx.x * (blockDim.x / 32) + warp;
@@ -436,22 +445,26 @@ struct HeadBwdArgs {
   float* dact_dbg;
 };
 
+constexpr int kHbCols = 8;     // hidden columns per CTA
+constexpr int kHbRows = 32;    // row groups per CTA (256 threads = 8 cols x 32 row groups)
+
 __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs P) {
+  kstamp();
   extern __shared__ float sm[];
   const int net = blockIdx.y, rep = blockIdx.z;
   const int M = P.M, NO = P.NO, KD = P.Kdim;
   float* sd = sm;                       // [M][NO]
-  float* red = sm + (size_t)M * NO;     // [8][32][NO] / scratch
-  const int tid = threadIdx.x, tx = tid % 32, ty = tid / 32;
+  float* red = sm + (size_t)M * NO;     // [32][8][NO] partial dW / scratch (>= 256 floats)
+  const int tid = threadIdx.x, tx = tid % kHbCols, ty = tid / kHbCols;
 
   if (P.policy_mode) {
     const int A = K.act;
     const float k = K.action_scale;
     for (int e = tid; e < M * A; e += 256) {
       const int m = e / A, j = e % A;
-      const float* sv = P.psave + rep * P.rsSave + ((long long)m * A + j) * kSaveW;
+      const float* __restrict__ sv = P.psave + rep * P.rsSave + ((long long)m * A + j) * kSaveW;
       const float std = sv[0], diff = sv[1], t = sv[2], act = sv[3], jac = sv[4], eps = sv[5], mask = sv[6];
-      const float* dx0 = P.dx + rep * P.rsDxRep + (long long)m * P.lddx + K.obs + j;
+      const float* __restrict__ dx0 = P.dx + rep * P.rsDxRep + (long long)m * P.lddx + K.obs + j;
       const float da = dx0[0] + dx0[P.rsDxNet];
       const int tk = (P.tid + rep * P.rsR)[m];
       const float alpha = (float)exp((double)(P.log_alpha + rep * P.rsP)[tk]);
@@ -472,54 +485,63 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
       }
     }
   } else {
-    const float* src = P.dout + rep * P.rsDoutRep + net * P.rsDoutNet;
+    const float* __restrict__ src = P.dout + rep * P.rsDoutRep + net * P.rsDoutNet;
     for (int e = tid; e < M * NO; e += 256) sd[e] = src[e];
   }
   __syncthreads();
 
-  const int kcol = blockIdx.x * 32 + tx;
+  const int kcol = blockIdx.x * kHbCols + tx;
   const bool kin = kcol < KD;
-  const float* W = P.W[net] + rep * P.rsP;
+  const float* __restrict__ W = P.W[net] + rep * P.rsP;
   float w[kMaxHeadOut], gw[kMaxHeadOut];
 #pragma unroll
   for (int j = 0; j < kMaxHeadOut; ++j) {
     w[j] = (j < NO && kin) ? W[(long long)j * KD + kcol] : 0.f;
     gw[j] = 0.f;
   }
-  const float* h = P.h + rep * P.rsHrep + net * P.rsHnet;
-  float* dh = P.dh + rep * P.rsDhRep + net * P.rsDhNet;
-  for (int m = ty; m < M; m += 8) {
-    const float hv = kin ? h[(long long)m * P.ldh + kcol] : 0.f;
-    float ds = 0.f;
+  const float* __restrict__ h = P.h + rep * P.rsHrep + net * P.rsHnet;
+  float* __restrict__ dh = P.dh + rep * P.rsDhRep + net * P.rsDhNet;
+  constexpr int U = 8;                                   // rows in flight per thread
+  for (int mb = ty; mb < M; mb += kHbRows * U) {
+    float hv[U];
 #pragma unroll
-    for (int j = 0; j < kMaxHeadOut; ++j) {
-      if (j < NO) {
-        const float dv = sd[m * NO + j];
-        ds = fmaf(dv, w[j], ds);
-        gw[j] = fmaf(dv, hv, gw[j]);
+    for (int u = 0; u < U; ++u) {
+      const int m = mb + u * kHbRows;
+      hv[u] = (kin && m < M) ? h[(long long)m * P.ldh + kcol] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int m = mb + u * kHbRows;
+      if (m < M) {
+        float ds = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxHeadOut; ++j) {
+          if (j < NO) {
+            const float dv = sd[m * NO + j];
+            ds = fmaf(dv, w[j], ds);
+            gw[j] = fmaf(dv, hv[u], gw[j]);
+          }
+        }
+        if (kin) dh[(long long)m * P.lddh + kcol] = hv[u] > 0.f ? ds : 0.f;
       }
     }
-    if (kin) dh[(long long)m * P.lddh + kcol] = hv > 0.f ? ds : 0.f;
   }
   if (P.dW[net] != nullptr) {
 #pragma unroll
     for (int j = 0; j < kMaxHeadOut; ++j)
-      if (j < NO) red[(ty * 32 + tx) * NO + j] = gw[j];
+      if (j < NO) red[(ty * kHbCols + tx) * NO + j] = gw[j];
     __syncthreads();
-    if (ty == 0 && kin) {
-      float* dW = P.dW[net] + rep * P.rsG;
-      for (int j = 0; j < NO; ++j) {
-        float s = 0.f;
-        for (int q = 0; q < 8; ++q) s += red[(q * 32 + tx) * NO + j];
-        dW[(long long)j * KD + kcol] = s;
-      }
+    if (ty < NO && kin) {                 // thread (ty = output j, tx = column): fixed-order sum over row groups
+      float ssum = 0.f;
+      for (int q = 0; q < kHbRows; ++q) ssum += red[(q * kHbCols + tx) * NO + ty];
+      (P.dW[net] + rep * P.rsG)[(long long)ty * KD + kcol] = ssum;
     }
     if (blockIdx.x == 0) {             // bias gradient: fixed-order tree over rows
       __syncthreads();
       for (int j = 0; j < NO; ++j) {
-        float s = 0.f;
-        for (int m = tid; m < M; m += 256) s += sd[m * NO + j];
-        red[tid] = s;
+        float ssum = 0.f;
+        for (int m = tid; m < M; m += 256) ssum += sd[m * NO + j];
+        red[tid] = ssum;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) {
           if (tid < o) red[tid] += red[tid + o];
@@ -560,9 +582,9 @@ struct AdamArgs {
   int R;
 };
 
-B200_D void adam_scalars(double lr, double b1, double b2, long long step, float& step_size, float& bc2_sqrt) {
-  const double bc1 = 1.0 - pow(b1, (double)step);
-  const double bc2 = 1.0 - pow(b2, (double)step);
+B200_D void adam_scalars(double lr, double b1_pow_t, double b2_pow_t, float& step_size, float& bc2_sqrt) {
+  const double bc1 = 1.0 - b1_pow_t;        // bias_correction1 = 1 - beta1 ** step
+  const double bc2 = 1.0 - b2_pow_t;
   step_size = (float)(lr / bc1);
   bc2_sqrt = (float)sqrt(bc2);
 }
@@ -576,6 +598,7 @@ B200_D void adam_one(float& p, float& m, float& v, float g, float w1, float b2, 
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
+  kstamp();
   const int rep = blockIdx.y;
   __shared__ float red[256];
   __shared__ float s_ss, s_bc;
@@ -583,7 +606,7 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
   if (!is_tail) {
     if (threadIdx.x == 0) {
       float a, b;
-      adam_scalars(P.lr, K.beta1, K.beta2, P.cnt[rep].v[P.which], a, b);
+      adam_scalars(P.lr, P.cnt[rep].b1p[P.which], P.cnt[rep].b2p[P.which], a, b);
       s_ss = a; s_bc = b;
     }
     __syncthreads();
@@ -657,7 +680,7 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
         aloss += la[t] * grad;                       // loss value = sum_t log_alpha[t] * grad[t]
         (P.g_alpha + rep * P.rsM)[t] = grad;
         float ss, bc;
-        adam_scalars(K.lr_alpha, K.beta1, K.beta2, P.cnt[rep].v[2], ss, bc);
+        adam_scalars(K.lr_alpha, P.cnt[rep].b1p[2], P.cnt[rep].b2p[2], ss, bc);
         float pi = la[t], mi = (P.m_alpha + rep * P.rsM)[t], vi = (P.v_alpha + rep * P.rsM)[t];
         adam_one(pi, mi, vi, grad, (float)(1.0 - K.beta1), (float)K.beta2, (float)(1.0 - K.beta2), ss, bc,
                  (float)K.adam_eps);

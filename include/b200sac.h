@@ -149,6 +149,12 @@ int b200sac_debug_read(b200sac_t* h, const char* name, int32_t replica, float* o
 int b200sac_profile_step(b200sac_t* h, b200sac_replay_t* rb, int32_t iters, float* out_ms, int32_t cap,
                          int32_t* n_out, char* names, int32_t names_cap, void* stream);
 
+/* In-graph timeline: `iters` sampled steps from a DEVICE ring as normal graph launches, with every
+ * kernel stamping %globaltimer at entry; out_us[i] = mean start-to-start time of launch i
+ * (0 = index sampling, 1 = ingest, then the step's launches in order, as b200sac_profile_step names them). */
+int b200sac_graph_timeline(b200sac_t* h, b200sac_replay_t* rb, int32_t iters, float* out_us, int32_t cap,
+                           int32_t* n_out, void* stream);
+
 /* Stand-alone run of the tcgen05 3xTF32 GEMM kernel on DEVICE arrays (parity tests of the tensor-core
  * path): mode 0 FWD C[M][N] = act(A[M][K] B[N][K]^T + bias), 1 DGRAD C[M][N] = (A[M][K] B[K][N]) * [mask > 0],
  * 2 WGRAD C[M][N] = A[K][M]^T B[K][N], C2[M] = column sums of A.  Synchronises. */
