@@ -120,10 +120,30 @@ def cpu_learner(workload, n_buffer=20000, seed=0):
     return spec, lrn, rb
 
 
+def best_cpu_threads(workload):
+    """Eager PyTorch on many cores is often slower than on a few for these tiny ops: probe a few thread
+    counts briefly and use the fastest, so the CPU arm is the reference path at its best on this host."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({1, 4, 8, 16, min(32, ncpu), ncpu} & set(range(1, ncpu + 1)))
+    best, best_v = 1, 0.0
+    spec, lrn, rb = cpu_learner(workload)
+    for t in cands:
+        torch.set_num_threads(t)
+        for _ in range(2):
+            lrn.update_SAC(*rb.sample())
+        t0 = time.perf_counter()
+        n = 6
+        for _ in range(n):
+            lrn.update_SAC(*rb.sample())
+        v = n / (time.perf_counter() - t0)
+        if v > best_v:
+            best, best_v = t, v
+    return best
+
+
 def time_cpu(workload, steps, warmup, threads=None):
     """steps/s of sample() + update_SAC() on the host cores."""
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or best_cpu_threads(workload))
     spec, lrn, rb = cpu_learner(workload)
     for _ in range(warmup):
         lrn.update_SAC(*rb.sample())
@@ -151,10 +171,11 @@ def run_reference(args, rank, world):
         return
     steps, warmup = args.steps, max(args.warmup, 3)
     # bounded sample: keep the whole run within ~2 minutes of CPU time whatever K the driver passes
-    probe_v, _, _ = time_cpu(args.workload, 10, 3)
+    threads = best_cpu_threads(args.workload)
+    probe_v, _, _ = time_cpu(args.workload, 10, 3, threads)
     steps = max(10, min(steps, int(120 * probe_v)))
     warmup = min(warmup, max(3, int(10 * probe_v)))
-    v, dt, cores = time_cpu(args.workload, steps, warmup)
+    v, dt, cores = time_cpu(args.workload, steps, warmup, threads)
     line = {
         "impl": "reference", "metric": "SAC gradient steps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
@@ -234,7 +255,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed update() calls for the e2e leg (default: min(steps, 2000))")
     ap.add_argument("--cpu-steps", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--precision", type=int, default=1, help="0 = fp32 FFMA GEMMs, 1 = 3xTF32 tcgen05 GEMMs (fp32-class accuracy)")
+    ap.add_argument("--precision", type=int, default=-1,
+                    help="0 = fp32 FFMA GEMMs, 1 = 3xTF32 tcgen05 GEMMs (fp32-class accuracy), -1 = time both, headline = faster")
     ap.add_argument("--sweep", default="", help="comma list of extra replicas-per-GPU values to report (device-resident)")
     args = ap.parse_args()
 
@@ -285,17 +307,24 @@ def main():
         return ms
 
     # ---- device-resident leg (value) -------------------------------------------------------------
+    from distributed_sac_b200.replicas import broadcast_initial_params
+    row_bytes = None
+    by_precision = {}
+    cands = [0, 1] if args.precision < 0 else [args.precision]
+    probe = {}
+    if len(cands) > 1:            # short probe of both GEMM back-ends; the full timed run uses the faster one
+        for pr in cands:
+            c0 = SacCore(core_config(args.workload, R, pr), local, seed=1234 + rank)
+            r0 = Replay(c0, 1 << 16, where="device", seed=99 + rank)
+            r0.fill_synthetic(1 << 16, seed=1234 + rank)
+            probe[pr] = timed_resident(c0, r0, 300, 50)
+            by_precision["fp32_ffma" if pr == 0 else "tc3xtf32"] = world * R * 300 / (probe[pr] * 1e-3)
+            r0.close(); c0.close()
+        args.precision = min(probe, key=probe.get)
     core = SacCore(core_config(args.workload, R, args.precision), local, seed=1234 + rank)
     if dist is not None:
         # independent replicas: ONE collective, the broadcast of the initial parameter arena
-        ptr, n = core.arena_view(_lib.PARAMS)
-        flat = torch.empty(n * R, dtype=torch.float32, device="cuda")
-        for r in range(R):
-            core.lib.b200sac_export(core._h, _lib.PARAMS, r, flat[r * n:(r + 1) * n].data_ptr(), n, None)
-        dist.broadcast(flat, src=0)
-        for r in range(R):
-            core.lib.b200sac_import(core._h, _lib.PARAMS, r, flat[r * n:(r + 1) * n].data_ptr(), n, None)
-        torch.cuda.synchronize()
+        broadcast_initial_params(core, src=0)
     ring = Replay(core, args.ring, where="device", seed=99 + rank)
     ring.fill_synthetic(args.ring, seed=1234 + rank)
     row_bytes = 4 * ((2 * core.cfg.obs_dim + core.cfg.act_dim + 2 + 31) // 32 * 32)
@@ -308,15 +337,22 @@ def main():
     value = world * R * K / (ms * 1e-3)
     losses = core.read_losses(min(K, 64))
     assert torch.isfinite(losses).all(), "non-finite losses in the timed region"
+    by_precision["fp32_ffma" if args.precision == 0 else "tc3xtf32"] = value
 
     # per-launch profile of one step (eager, CUDA events) for the roofline block
     with torch.cuda.stream(stream):
         prof = core.profile_step(ring, iters=30)
     torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        tl = core.graph_timeline(ring, iters=200)          # true in-graph start-to-start times (us)
+    torch.cuda.synchronize()
+    names = ["sample_indices", "ingest"] + [n for n, _ in prof][1:]
+    prof = list(zip(names, [t * 1e-3 for t in tl]))      # ms, like the eager numbers it replaces
     tot = sum(t for _, t in prof)
     by_kernel = {}
     for name, t in prof:
-        fam = name.split("(")[0]
+        fam = name.split("(")[0] if "tcgen05" not in name else "gemm_tc"
+        fam = "gemm_ffma" if fam.startswith("gemm_") and fam != "gemm_tc" else fam
         by_kernel[fam] = by_kernel.get(fam, 0.0) + t
     top = max(by_kernel.items(), key=lambda kv: kv[1])
     work = WORK[args.workload]
@@ -330,19 +366,24 @@ def main():
         "algorithmic_bytes_per_step": work["mbytes"] * 1e6 * R, "algorithmic_flop_per_step": work["gflop"] * 1e9 * R,
         "tensor": {"achieved": ach_tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf"],
                    "note": "3xTF32 issues 3 tensor-core MACs per algorithmic MAC; denominator = measured dense bf16 cuBLAS"},
-        "dominant_kernel": {"name": top[0], "share_of_step": top[1] / tot, "ms_per_step_eager": top[1]},
-        "per_launch_ms_eager": [[n, round(t, 5)] for n, t in prof],
+        "dominant_kernel": {"name": top[0], "share_of_step": top[1] / tot, "us_per_step_in_graph": top[1] * 1e3,
+                            "launches_per_step": sum(1 for n, _ in prof if (("tcgen05" in n) if top[0] == "gemm_tc" else
+                                                     (n.startswith("gemm_") and "tcgen05" not in n) if top[0] == "gemm_ffma" else n.split("(")[0] == top[0]))},
+        "per_launch_us_in_graph": [[n, round(t * 1e3, 2)] for n, t in prof],
         "note": "latency-bound: ~%d dependent launches per step; params+Adam state stay L2-resident between steps" % (core.launches_per_step + 1),
     }
 
     sweep = {}
     for r_extra in [int(x) for x in args.sweep.split(",") if x]:
-        c2 = SacCore(core_config(args.workload, r_extra, args.precision), local, seed=77 + rank)
-        ring2 = Replay(c2, max(1 << 16, args.ring // max(1, r_extra // 2)), where="device", seed=5)
-        ring2.fill_synthetic(max(1 << 16, args.ring // max(1, r_extra // 2)), seed=6)
-        ms2 = timed_resident(c2, ring2, max(200, K // 4), W)
-        sweep[str(r_extra)] = world * r_extra * max(200, K // 4) / (ms2 * 1e-3)
-        ring2.close(); c2.close()
+        sweep[str(r_extra)] = {}
+        n_ring = max(1 << 16, args.ring // max(1, r_extra // 2))
+        for pr in (0, 1):
+            c2 = SacCore(core_config(args.workload, r_extra, pr), local, seed=77 + rank)
+            ring2 = Replay(c2, n_ring, where="device", seed=5)
+            ring2.fill_synthetic(n_ring, seed=6)
+            ms2 = timed_resident(c2, ring2, max(200, K // 4), W)
+            sweep[str(r_extra)]["fp32_ffma" if pr == 0 else "tc3xtf32"] = world * r_extra * max(200, K // 4) / (ms2 * 1e-3)
+            ring2.close(); c2.close()
     ring.close()
     core.close()
 
@@ -414,6 +455,8 @@ def main():
             "clocks": clk, "e2e": e2e, "gpu_launches": K * (core.launches_per_step + 1),
             "roofline": roofline, "cpu_baseline": cpu,
         }
+        line["by_precision"] = by_precision
+        line["config"]["gemm_backend"] = "fp32 FFMA" if args.precision == 0 else "tcgen05 3xTF32"
         if sweep:
             line["replicas_per_gpu_sweep"] = sweep
         print(json.dumps(line), flush=True)

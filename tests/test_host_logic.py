@@ -1,0 +1,75 @@
+"""CPU: host-side logic that needs no GPU -- the C-ABI library loads and exports every symbol the
+header declares, the parameter layout, cfg decoding, reference key maps."""
+import ctypes as C
+import json
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from distributed_sac_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from distributed_sac_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "b200sac.h")).read()
+    declared = set(re.findall(r"\b(b200sac_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200sac.h but not exported"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    assert b"b200sac" in lib.b200sac_version()
+
+
+def test_layout_matches_reference_parameter_counts(lib):
+    from distributed_sac_b200.core import CoreConfig, layout
+    t, arena, train = layout(CoreConfig())                     # LunarLander: SURVEY 8(a) a11/a12
+    n = lambda pre: sum(r * c for k, (o, r, c, tr, opt) in t.items() if k.startswith(pre))
+    assert n("actor.") == 69124 and n("q1.") == 68865 and n("q1_target.") == 68865
+    assert n("actor.") + n("q1.") + n("q2.") + 1 == 206855
+    assert t["actor.2.weight"][1:3] == (4, 256) and t["q1.0.weight"][1:3] == (256, 10)
+    assert all(off % 4 == 0 for off, *_ in t.values())          # 16-byte aligned tensors (TMA / float4)
+    assert train < arena and t["log_alpha"][3] == 1 and t["q2_target.2.bias"][3] == 0
+    t, arena, train = layout(CoreConfig(state_dim=39, act_dim=4, actor_hidden=[400] * 3, critic_hidden=[400] * 3,
+                                        batch=1280, num_tasks=10))
+    assert n("actor.") == 344008 and n("q1.") == 342801 and t["log_alpha"][1] == 10
+
+
+def test_layout_rejects_bad_configs(lib):
+    from distributed_sac_b200.core import CoreConfig, layout
+    for bad in (dict(act_dim=0), dict(act_dim=9), dict(batch=0), dict(batch=4096), dict(num_tasks=3, batch=256),
+                dict(actor_hidden=[]), dict(replicas=0), dict(precision=7)):
+        with pytest.raises(RuntimeError, match="b200sac error"):
+            layout(CoreConfig(**bad))
+
+
+def test_cfg_decoder_and_key_maps(tmp_path):
+    from distributed_sac_b200 import names
+    from distributed_sac_b200.learner import cfg_read
+    p = tmp_path / "c.json"
+    p.write_text(json.dumps({"batch_size": "256", "device": "cuda", "nested": {"x": ["7", "a"]}, "lr": 3e-4}))
+    c = cfg_read(str(p))
+    assert c["batch_size"] == 256 and c["nested"]["x"] == [7, "a"] and c["device"] == "cuda" and c["lr"] == 3e-4
+    assert names.actor_key_map("LL", 3) == {
+        "layer_intermediate.0.weight": "actor.0.weight", "layer_intermediate.0.bias": "actor.0.bias",
+        "layer_intermediate.1.weight": "actor.1.weight", "layer_intermediate.1.bias": "actor.1.bias",
+        "mu_log_std_layer.weight": "actor.2.weight", "mu_log_std_layer.bias": "actor.2.bias"}
+    assert names.critic_key_map("MS", 4, 2, True)["Q_function_2.6.bias"] == "q2_target.3.bias"
+    assert names.critic_key_map("VS", 4, 1)["layer_module.2.weight"] == "q1.3.weight"
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from distributed_sac_b200.core import CoreConfig, SacCore
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SacCore(CoreConfig())
