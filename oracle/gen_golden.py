@@ -172,6 +172,101 @@ def make_case(name, family, n_steps, cfg_overrides=None, seed=0, checkpoint=None
     print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  losses[0]={losses[0]}  losses[-1]={losses[-1]}")
 
 
+def _care_named(lrn):
+    """canonical name -> live reference Parameter for the CARE(M) learner (oracle/care_port.py names)."""
+    out = {}
+    def mlp(seq, net):
+        lin = [m for m in seq if hasattr(m, "out_features")]
+        for i, m in enumerate(lin):
+            out[f"{net}.{i}.weight"], out[f"{net}.{i}.bias"] = m.weight, m.bias
+    mlp(lrn.actor.mu_log_std_layer, "actor")
+    mlp(lrn.local_critic.Q_function_1, "q1"); mlp(lrn.local_critic.Q_function_2, "q2")
+    mlp(lrn.target_critic.Q_function_1, "q1_target"); mlp(lrn.target_critic.Q_function_2, "q2_target")
+    for pre, se in (("cse", lrn.local_critic.state_encoder), ("tse", lrn.target_critic.state_encoder)):
+        mixl = [m for m in se.mixture_encoders.mixtureEncoders if hasattr(m, "W")]
+        for l, m in enumerate(mixl):
+            out[f"{pre}.mix.{l}.W"], out[f"{pre}.mix.{l}.b"] = m.W, m.b
+        for name, seq in (("trunk", se.trunk), ("ctx", se.mlp_context)):
+            for j, m in enumerate([m for m in seq if hasattr(m, "out_features")]):
+                out[f"{pre}.{name}.{j}.weight"], out[f"{pre}.{name}.{j}.bias"] = m.weight, m.bias
+    out["embedding"] = lrn.context_encoder.embedding[0].weight
+    out["log_alpha"] = lrn.log_alpha
+    return out
+
+
+def make_care_case(name, n_steps, cfg_overrides, seed=0, data_seed=4321):
+    import care_port as cp
+    lrn, _ = rh.make_learner("C10", cfg_overrides, seed=seed)
+    enc = lrn.encoder_cfg
+    lin = lambda seq: [m.out_features for m in seq if hasattr(m, "out_features")]
+    spec = cp.CareSpec(state_dim=lrn.actor.state_dim, act_dim=lrn.actor.action_dim, num_tasks=lrn.num_tasks,
+                       actor_hidden=lin(lrn.actor.mu_log_std_layer)[:-1], critic_hidden=lin(lrn.local_critic.Q_function_1)[:-1],
+                       batch=lrn.batch_size, num_encoders=int(enc["num_encoders"]), mix_hidden=list(enc["hidden_dims_mixtureEnc"]),
+                       mix_out=int(enc["output_dim_mixtureEnc"]), ctx_in=int(enc["RoBERTa_embedding_dim"]),
+                       ctx_hidden=list(enc["hidden_dims_contextEnc"]), ctx_out=int(enc["output_dim_contextEnc"]),
+                       tau_se=float(enc["state_encoder_tau"]), weighted_loss=bool(lrn.use_modified_care), gamma=lrn.gamma,
+                       tau=lrn.tau, reward_scale=float(lrn.reward_scale), lr_actor=lrn.lr_actor, lr_critic=lrn.lr_critic)
+    assert lrn.use_modified_care, "only CARE(M) is restated"
+    named = _care_named(lrn)
+    d = {"spec": json.dumps(spec.to_json()), "family": "C10", "n_steps": n_steps}
+    for k, p in named.items():
+        d["p_in/" + k] = p.detach().clone().numpy()
+    trainable = [k for k in named if not (k.startswith("tse.") or "_target" in k or k == "embedding")]
+    for k in trainable:
+        d["m_in/" + k] = np.zeros_like(d["p_in/" + k]); d["v_in/" + k] = np.zeros_like(d["p_in/" + k])
+    d["step_in"] = np.zeros(3, np.int64)
+    g = torch.Generator().manual_seed(data_seed + 17)
+    batches, eps_n, eps_c, losses = [], [], [], []
+    for i in range(n_steps):
+        batches.append(cp.synthetic_batch(spec, seed=data_seed + i))
+        eps_n.append(torch.randn(spec.batch, spec.act_dim, generator=g))
+        eps_c.append(torch.randn(spec.batch, spec.act_dim, generator=g))
+    s, a, r, s2, dn = batches[0]
+    with torch.no_grad(), rh.injected_eps([eps_n[0], eps_c[0]]):
+        alpha = lrn.get_log_alpha(s).exp()
+        z = lrn.context_encoder.forward(s)
+        a2, lp2, _ = lrn.actor.get_action_log_prob_log_std(mtobss=s2, z_context=z)
+        qt = torch.min(*lrn.target_critic.forward(mtobss=s2, z_context=z, action=a2))
+        q1, q2 = lrn.local_critic.forward(mtobss=s, z_context=z, action=a)
+        ac, lpc, _ = lrn.actor.get_action_log_prob_log_std(mtobss=s, z_context=z)
+        y = lrn.reward_scale * r + lrn.gamma * (1 - dn) * (qt - alpha * lp2)
+    for k, t in dict(y=y, q1=q1, q2=q2, a_next=a2, logp_next=lp2, a_cur=ac, logp_cur=lpc).items():
+        d["i0/" + k] = t.numpy()
+    for i in range(n_steps):
+        lrn.memory.sample = (lambda b: (lambda: tuple(t.clone() for t in b)))(batches[i])
+        with rh.injected_eps([eps_n[i], eps_c[i]]) as q:
+            res = lrn.update()
+            assert not q
+        losses.append(list(res))
+    d["losses"] = np.array(losses, np.float64)
+    for j, key in enumerate(("s", "a", "r", "s2", "d")):
+        d["batch/" + key] = np.stack([b[j].numpy() for b in batches])
+    d["eps_next"] = np.stack([e.numpy() for e in eps_n]); d["eps_cur"] = np.stack([e.numpy() for e in eps_c])
+    for k, p in named.items():
+        d["p_out/" + k] = p.detach().clone().numpy()
+    opts = {"critic": lrn.critic_optimizer, "actor": lrn.actor_optimizer, "alpha": lrn.log_alpha_optimizer}
+    steps = {"critic": 0, "actor": 0, "alpha": 0}
+    for k in trainable:
+        tag = "alpha" if k == "log_alpha" else ("actor" if k.startswith("actor.") else "critic")
+        st = opts[tag].state[named[k]]
+        d["m_out/" + k], d["v_out/" + k] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+        steps[tag] = int(st["step"])
+    d["step_out"] = np.array([steps["critic"], steps["actor"], steps["alpha"]], np.int64)
+    # the actor's tied encoder must equal the critic's after update() (learner.py:402)
+    ase = dict(lrn.actor.state_encoder.named_parameters()); cse = dict(lrn.local_critic.state_encoder.named_parameters())
+    assert all(torch.equal(ase[k], cse[k]) for k in ase)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  losses[0]={losses[0]}  losses[-1]={losses[-1]}")
+
+
+CARE_CASES = {
+    "care_small_s4": dict(n_steps=4, seed=7, cfg_overrides=dict(
+        batch_size=120, actor=dict(actor_hidden_dim=[64, 48, 32]), critic=dict(critic_hidden_dim=[40, 72, 56]),
+        encoder=dict(hidden_dims_contextEnc=[24, 20], output_dim_contextEnc=16, embedding_dim_contextEnc=16,
+                     hidden_dims_mixtureEnc=[28], output_dim_mixtureEnc=12, num_encoders=4))),
+}
+
 CASES = {
     # full-size LunarLander learner, seeded Xavier init, distinct target nets, fresh Adam
     "ll_xavier_s2": dict(family="LL", n_steps=2, seed=0),
@@ -192,6 +287,9 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    todo = sys.argv[1:] or list(CASES)
+    todo = sys.argv[1:] or (list(CASES) + list(CARE_CASES))
     for c in todo:
-        make_case(c, **CASES[c])
+        if c in CARE_CASES:
+            make_care_case(c, **CARE_CASES[c])
+        else:
+            make_case(c, **CASES[c])

@@ -76,3 +76,22 @@ def core_config(spec, replicas=1, **kw):
              action_scale=spec.action_scale, beta1=spec.beta1, beta2=spec.beta2, adam_eps=spec.adam_eps)
     d.update(kw)
     return CoreConfig(**d)
+
+
+class CareCase:
+    """Fixture of the CARE(M) learner (oracle/care_port.py names)."""
+
+    def __init__(self, name="care_small_s4"):
+        import care_port as cp
+        z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+        self.name = name
+        self.spec = cp.CareSpec(**json.loads(str(z["spec"])))
+        self.n_steps = int(z["n_steps"])
+        grab = lambda pre: {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
+        self.p_in, self.m_in, self.v_in = grab("p_in/"), grab("m_in/"), grab("v_in/")
+        self.p_out, self.m_out, self.v_out = grab("p_out/"), grab("m_out/"), grab("v_out/")
+        self.i0, self.batch = grab("i0/"), grab("batch/")
+        self.eps_next, self.eps_cur = torch.from_numpy(z["eps_next"]), torch.from_numpy(z["eps_cur"])
+        self.step_in, self.step_out, self.losses = z["step_in"], z["step_out"], z["losses"]
+
+    step_batch = Case.step_batch
