@@ -16,12 +16,16 @@ class Cfg(C.Structure):
         ("n_actor_hidden", C.c_int32), ("n_critic_hidden", C.c_int32),
         ("actor_hidden", C.c_int32 * MAX_HIDDEN), ("critic_hidden", C.c_int32 * MAX_HIDDEN),
         ("batch", C.c_int32), ("weighted_loss", C.c_int32), ("replicas", C.c_int32),
-        ("precision", C.c_int32), ("reserved0", C.c_int32),
+        ("precision", C.c_int32), ("care", C.c_int32),
         ("gamma", C.c_double), ("tau", C.c_double), ("reward_scale", C.c_double),
         ("lr_actor", C.c_double), ("lr_critic", C.c_double), ("lr_alpha", C.c_double),
         ("action_scale", C.c_double),
         ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double),
         ("log_alpha_init", C.c_double),
+        ("num_encoders", C.c_int32), ("n_mix_hidden", C.c_int32), ("mix_hidden", C.c_int32 * MAX_HIDDEN),
+        ("mix_out", C.c_int32), ("ctx_in", C.c_int32), ("n_ctx_hidden", C.c_int32),
+        ("ctx_hidden", C.c_int32 * MAX_HIDDEN), ("ctx_out", C.c_int32), ("reserved1", C.c_int32),
+        ("tau_se", C.c_double),
     ]
 
 

@@ -36,6 +36,15 @@ class CoreConfig:
     beta2: float = 0.999
     adam_eps: float = 1e-8
     log_alpha_init: float = 0.0
+    # CARE(M) state encoders (cfg "encoder" block of MT10_Distributed_CARE_cfg.json)
+    care: bool = False
+    num_encoders: int = 6
+    mix_hidden: List[int] = field(default_factory=lambda: [50])
+    mix_out: int = 50
+    ctx_in: int = 768
+    ctx_hidden: List[int] = field(default_factory=lambda: [50, 50])
+    ctx_out: int = 50
+    tau_se: float = 0.05
 
     @property
     def obs_dim(self):
@@ -58,6 +67,15 @@ class CoreConfig:
         c.action_scale = self.action_scale
         c.beta1, c.beta2, c.adam_eps = self.beta1, self.beta2, self.adam_eps
         c.log_alpha_init = self.log_alpha_init
+        c.care = int(self.care)
+        if self.care:
+            c.num_encoders, c.mix_out, c.ctx_in, c.ctx_out = self.num_encoders, self.mix_out, self.ctx_in, self.ctx_out
+            c.n_mix_hidden, c.n_ctx_hidden = len(self.mix_hidden), len(self.ctx_hidden)
+            for i, v in enumerate(self.mix_hidden):
+                c.mix_hidden[i] = int(v)
+            for i, v in enumerate(self.ctx_hidden):
+                c.ctx_hidden[i] = int(v)
+            c.tau_se = self.tau_se
         return c
 
 
@@ -137,7 +155,12 @@ class SacCore:
             if which != _lib.PARAMS and not trainable:
                 continue
             t = flat[off:off + rows * cols]
-            is_mat = name.endswith(".weight")
+            if ".mix." in name:        # stored as [K][out][in] | [K][out]; the reference holds (K,in,out) | (K,1,out)
+                K = self.cfg.num_encoders
+                out[name] = (t.reshape(K, rows // K, cols).permute(0, 2, 1).contiguous() if name.endswith(".W")
+                             else t.reshape(K, 1, rows // K).clone())
+                continue
+            is_mat = name.endswith(".weight") or name == "embedding"
             out[name] = t.reshape(rows, cols).clone() if is_mat else t.clone()
         return out
 
@@ -152,7 +175,10 @@ class SacCore:
             off, rows, cols, trainable, _ = self.table[name]
             if which != _lib.PARAMS and not trainable:
                 continue
-            t = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+            t = torch.as_tensor(t, dtype=torch.float32)
+            if ".mix." in name and name.endswith(".W"):
+                t = t.permute(0, 2, 1).contiguous()          # (K,in,out) -> [K][out][in]
+            t = t.reshape(-1)
             if t.numel() != rows * cols:
                 raise ValueError(f"{name}: expected {rows * cols} elements, got {t.numel()}")
             flat[off:off + rows * cols] = t

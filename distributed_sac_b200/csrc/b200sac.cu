@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <new>
@@ -22,6 +23,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "sac_kernels.cuh"
+#include "care_kernels.cuh"
 
 using namespace bsac;
 
@@ -53,6 +55,10 @@ struct LayerOff { int64_t w, b; int in, out; };
 struct Layout {
   std::vector<b200sac_tensor_desc> descs;
   std::vector<LayerOff> actor, q[2], qt[2];
+  // CARE: the critic's state encoder (the target's sits at + target_delta with the same relative layout)
+  std::vector<LayerOff> mix, trunk, ctx;      // mix: w = [K][out][in], b = [K][out]
+  int64_t cse_begin = 0, off_emb = 0;
+  int in_w = 0;                               // width of the state part of the MLP inputs
   int64_t off_alpha = 0, arena = 0, trainable = 0;
   int64_t actor_begin = 0, actor_n = 0, critic_begin = 0, critic_n = 0, target_delta = 0;
 };
@@ -76,48 +82,88 @@ static int check_cfg(const b200sac_cfg* c) {
     return fail(B200SAC_ERR_INVALID, "batch must be a multiple of num_tasks");
   if (c->replicas < 1 || c->replicas > 4096) return fail(B200SAC_ERR_INVALID, "1 <= replicas <= 4096 required");
   if (c->precision != 0 && c->precision != 1) return fail(B200SAC_ERR_INVALID, "precision must be 0 (fp32 FFMA) or 1 (3xTF32 tcgen05)");
+  if (c->care) {
+    if (c->num_tasks < 1) return fail(B200SAC_ERR_INVALID, "CARE needs num_tasks >= 1 (one-hot task id in the observation)");
+    if (c->num_encoders < 1 || c->num_encoders > 32) return fail(B200SAC_ERR_INVALID, "1 <= num_encoders <= 32 required");
+    if (c->n_mix_hidden < 1 || c->n_mix_hidden > B200SAC_MAX_HIDDEN || c->n_ctx_hidden < 0 || c->n_ctx_hidden > B200SAC_MAX_HIDDEN)
+      return fail(B200SAC_ERR_INVALID, "bad number of encoder hidden layers");
+    if (c->mix_out < 1 || c->mix_out > 512 || c->ctx_out < 1 || c->ctx_out > 512 || c->ctx_in < 1 || c->ctx_in > 2048)
+      return fail(B200SAC_ERR_INVALID, "encoder widths out of range (mix_out, ctx_out <= 512, ctx_in <= 2048)");
+    for (int i = 0; i < c->n_mix_hidden; ++i)
+      if (c->mix_hidden[i] < 1 || c->mix_hidden[i] > 512) return fail(B200SAC_ERR_INVALID, "mix_hidden[%d] out of range", i);
+    for (int i = 0; i < c->n_ctx_hidden; ++i)
+      if (c->ctx_hidden[i] < 1 || c->ctx_hidden[i] > 512) return fail(B200SAC_ERR_INVALID, "ctx_hidden[%d] out of range", i);
+    if (c->num_encoders + c->ctx_out > 64 * 8) return fail(B200SAC_ERR_INVALID, "num_encoders + ctx_out too large");
+  }
   return 0;
 }
 
 static void build_layout(const b200sac_cfg* c, Layout& L) {
   const int obs = c->state_dim + c->num_tasks;
+  L.in_w = c->care ? (c->ctx_out + c->mix_out) : obs;
   int64_t off = 0;
-  auto add = [&](const char* net, int i, const char* kind, int rows, int cols, int trainable, int opt) {
+  auto add = [&](const char* name, int rows, int cols, int trainable, int opt) {
     b200sac_tensor_desc d;
     memset(&d, 0, sizeof(d));
-    if (i >= 0) snprintf(d.name, sizeof(d.name), "%s.%d.%s", net, i, kind);
-    else snprintf(d.name, sizeof(d.name), "%s", net);
+    snprintf(d.name, sizeof(d.name), "%s", name);
     d.offset = off; d.rows = rows; d.cols = cols; d.trainable = trainable; d.opt = opt;
     L.descs.push_back(d);
     int64_t o = off;
     off = pad4(off + (int64_t)rows * cols);
     return o;
   };
-  auto add_net = [&](const char* net, std::vector<LayerOff>& v, int in0, const int* hid, int nh, int out, int tr, int opt) {
+  char nm[48];
+  auto add_net = [&](const char* net, std::vector<LayerOff>* v, int in0, const int* hid, int nh, int out, int tr, int opt) {
     int in = in0;
     for (int i = 0; i <= nh; ++i) {
       int o = (i < nh) ? hid[i] : out;
       LayerOff lo;
       lo.in = in; lo.out = o;
-      lo.w = add(net, i, "weight", o, in, tr, opt);
-      lo.b = add(net, i, "bias", o, 1, tr, opt);
-      v.push_back(lo);
+      snprintf(nm, sizeof(nm), "%s.%d.weight", net, i);
+      lo.w = add(nm, o, in, tr, opt);
+      snprintf(nm, sizeof(nm), "%s.%d.bias", net, i);
+      lo.b = add(nm, o, 1, tr, opt);
+      if (v) v->push_back(lo);
       in = o;
     }
   };
+  // state encoder block: mixture layers ([K][out][in] | [K][out]), attention trunk, context MLP
+  auto add_encoder = [&](const char* pre, bool record, int tr, int opt) {
+    int in = c->state_dim;
+    for (int l = 0; l <= c->n_mix_hidden; ++l) {
+      int o = (l < c->n_mix_hidden) ? c->mix_hidden[l] : c->mix_out;
+      LayerOff lo;
+      lo.in = in; lo.out = o;
+      snprintf(nm, sizeof(nm), "%s.mix.%d.W", pre, l);
+      lo.w = add(nm, c->num_encoders * o, in, tr, opt);
+      snprintf(nm, sizeof(nm), "%s.mix.%d.b", pre, l);
+      lo.b = add(nm, c->num_encoders * o, 1, tr, opt);
+      if (record) L.mix.push_back(lo);
+      in = o;
+    }
+    char pfx[24];
+    snprintf(pfx, sizeof(pfx), "%s.trunk", pre);
+    add_net(pfx, record ? &L.trunk : nullptr, c->ctx_in, c->mix_hidden, c->n_mix_hidden, c->num_encoders, tr, opt);
+    snprintf(pfx, sizeof(pfx), "%s.ctx", pre);
+    add_net(pfx, record ? &L.ctx : nullptr, c->ctx_in, c->ctx_hidden, c->n_ctx_hidden, c->ctx_out, tr, opt);
+  };
   L.actor_begin = off;
-  add_net("actor", L.actor, obs, c->actor_hidden, c->n_actor_hidden, 2 * c->act_dim, 1, 1);
+  add_net("actor", &L.actor, L.in_w, c->actor_hidden, c->n_actor_hidden, 2 * c->act_dim, 1, 1);
   L.actor_n = off - L.actor_begin;
   L.critic_begin = off;
-  add_net("q1", L.q[0], obs + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0);
-  add_net("q2", L.q[1], obs + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0);
+  add_net("q1", &L.q[0], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0);
+  add_net("q2", &L.q[1], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0);
+  L.cse_begin = off;
+  if (c->care) add_encoder("cse", true, 1, 0);
   L.critic_n = off - L.critic_begin;
-  L.off_alpha = add("log_alpha", -1, "", c->num_tasks > 0 ? c->num_tasks : 1, 1, 1, 2);
+  L.off_alpha = add("log_alpha", c->num_tasks > 0 ? c->num_tasks : 1, 1, 1, 2);
   L.trainable = off;
   int64_t tb = off;
-  add_net("q1_target", L.qt[0], obs + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1);
-  add_net("q2_target", L.qt[1], obs + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1);
+  add_net("q1_target", &L.qt[0], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1);
+  add_net("q2_target", &L.qt[1], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1);
+  if (c->care) add_encoder("tse", false, 0, -1);
   L.target_delta = tb - L.critic_begin;
+  if (c->care) L.off_emb = add("embedding", c->num_tasks, c->ctx_in, 0, -1);
   L.arena = off;
 }
 
@@ -142,7 +188,7 @@ struct Buf {           // [R][n] fp32 (or int32) slab slice
   long long rs = 0;    // replica stride in floats
 };
 
-enum LaunchKind { L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
+enum LaunchKind { L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
 
 struct Launch {
   LaunchKind kind;
@@ -152,6 +198,11 @@ struct Launch {
   const GemmProb* probs = nullptr; int G = 0;
   GemmGroup grp;
   const TcProb* tprobs = nullptr;
+  CareTabArgs ctab;
+  CareMixArgs cmix;
+  CareMixBwdArgs cmixb;
+  CareTabReduceArgs ctred;
+  CareTabWgradArgs ctwg;
   PolicyHeadArgs pol;
   CriticHeadArgs ch;
   ActorQHeadArgs aq;
@@ -186,6 +237,11 @@ struct b200sac {
   size_t slab_floats = 0;
   Buf XA, XQ, XT, XP, r, d, tid, eps, pout, psave, act_out, logp, logstd, y, q, dq, lq, dqa, la, qmin, dxP,
       dout_dbg, dact_dbg;
+  // CARE
+  Buf XS, careTab[3], careDtab, careDatt, mixZ[3], mixDZ;     // instances: 0 = critic's (old) on [s';s], 1 = target's on s', 2 = critic's (new) on s
+  std::vector<Buf> mixH[3], mixDH;                             // per mixture hidden layer: [K][rows][pitch]
+  CareNet care_trunk, care_ctx;
+  int care_row_w = 0, care_off_att = 0, care_off_ctx = 0;
   std::vector<Buf> hA, dhA;       // per actor hidden layer
   std::vector<Buf> hQ, hT, hP, dhQ;   // per critic hidden layer, [2][B][H]
   GemmProb* d_probs = nullptr;
@@ -336,6 +392,7 @@ static int build_plan(b200sac* h) {
   auto Gp = [&](int64_t off) { return h->grads + off; };
 
   int plan_rc = 0;
+  std::function<void(std::vector<GemmProb>)> gemm_launch_ref;
   auto gemm_launch = [&](std::vector<GemmProb> ps) {
     if (c.precision == 1) {
       std::vector<GemmProb> tc, rest;
@@ -363,6 +420,12 @@ static int build_plan(b200sac* h) {
       if (rest.empty()) return;
       ps = rest;
     }
+    if (ps.size() > GS_MAXG) {            // more problems than one parameter block holds: several launches
+      std::vector<GemmProb> head(ps.begin(), ps.begin() + GS_MAXG), tail(ps.begin() + GS_MAXG, ps.end());
+      gemm_launch_ref(head);
+      gemm_launch_ref(tail);
+      return;
+    }
     Launch l;
     int maxM = 0, maxN = 0;
     for (auto& p : ps) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; }
@@ -378,6 +441,83 @@ static int build_plan(b200sac* h) {
     for (auto& p : ps) h->h_probs.push_back(p);
     h->plan.push_back(l);
   };
+  gemm_launch_ref = gemm_launch;
+
+  // ---- CARE helpers ------------------------------------------------------------------------
+  const int Kenc = c.num_encoders, nmix = c.care ? (int)L.mix.size() : 0;
+  auto pitch = [](int w) { return (w + 3) & ~3; };
+  // mixture-of-encoders forward of encoder instance `inst` (0: critic's on XS rows [row0, row0+rows) into the
+  // instance-0 buffers at the same rows; 1: target's; 2: critic's after its Adam step)
+  auto care_tables = [&](std::vector<int> insts) {
+    Launch l;
+    l.kind = L_CARE_TAB;
+    CareTabArgs& P = l.ctab;
+    memset(&P, 0, sizeof(P));
+    P.params = h->params; P.rsP = rsP; P.emb_off = L.off_emb;
+    P.trunk = h->care_trunk; P.ctx = h->care_ctx;
+    P.T = c.num_tasks; P.K = Kenc; P.row_w = h->care_row_w; P.off_att = h->care_off_att;
+    for (size_t i = 0; i < insts.size(); ++i) {
+      P.inst_delta[i] = insts[i] == 1 ? L.target_delta : 0;
+      P.tab[i] = h->careTab[insts[i]].p;
+    }
+    P.rsTab = h->careTab[0].rs;
+    l.grid = dim3(c.num_tasks, (unsigned)insts.size(), R);
+    l.block = dim3(128);
+    h->plan.push_back(l);
+  };
+  auto care_mixture_fwd = [&](std::vector<std::tuple<int, int, int>> jobs /* (inst, xs_row0, rows) */) {
+    for (int l = 0; l < nmix; ++l) {
+      std::vector<GemmProb> ps;
+      for (auto& jb : jobs) {
+        const int inst = std::get<0>(jb), row0 = std::get<1>(jb), rows = std::get<2>(jb);
+        const int rows_buf = inst == 0 ? 2 * B : B;             // rows held by the instance's buffers
+        const int out_row0 = inst == 0 ? row0 : 0;
+        const LayerOff& lo = L.mix[l];
+        const long long delta = inst == 1 ? L.target_delta : 0;
+        const bool last = (l == nmix - 1);
+        const Buf& ob = last ? h->mixZ[inst] : h->mixH[inst][l];
+        for (int k = 0; k < Kenc; ++k) {
+          GemmProb p;
+          memset(&p, 0, sizeof(p));
+          if (l == 0) { p.A = h->XS.p + (long long)row0 * h->K.obs; p.rsA = h->XS.rs; p.lda = h->K.obs; }
+          else {
+            const Buf& ib = h->mixH[inst][l - 1];
+            p.A = ib.p + ((long long)k * rows_buf + out_row0) * pitch(lo.in); p.rsA = ib.rs; p.lda = pitch(lo.in);
+          }
+          p.B = W(delta + lo.w + (long long)k * lo.out * lo.in); p.rsB = rsP; p.ldb = lo.in;
+          p.bias = W(delta + lo.b + (long long)k * lo.out); p.rsBias = rsP;
+          p.C = ob.p + ((long long)k * rows_buf + out_row0) * pitch(lo.out); p.rsC = ob.rs; p.ldc = pitch(lo.out);
+          p.M = rows; p.N = lo.out; p.K = lo.in; p.mode = GEMM_FWD; p.relu = last ? 0 : 1;
+          ps.push_back(p);
+        }
+      }
+      gemm_launch(ps);
+    }
+  };
+  auto care_mix = [&](int inst, int rows, float* d1, long long rs1, int ld1, float* d2, long long rs2, int ld2, int off2) {
+    Launch l;
+    l.kind = L_CARE_MIX;
+    CareMixArgs& P = l.cmix;
+    memset(&P, 0, sizeof(P));
+    const int rows_buf = inst == 0 ? 2 * B : B;
+    P.Z = h->mixZ[inst].p; P.rsZ = h->mixZ[inst].rs; P.kstride = (long long)rows_buf * pitch(c.mix_out); P.ldz = pitch(c.mix_out);
+    P.tab = h->careTab[inst].p; P.rsTab = h->careTab[inst].rs; P.row_w = h->care_row_w; P.off_att = h->care_off_att;
+    P.off_ctx = h->care_off_ctx;
+    P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
+    P.rows = rows; P.B = B; P.K = Kenc; P.mo = c.mix_out; P.co = c.ctx_out;
+    P.dst1 = d1; P.rsD1 = rs1; P.ld1 = ld1; P.dst2 = d2; P.rsD2 = rs2; P.ld2 = ld2; P.row_off2 = off2;
+    l.grid = dim3((rows + 7) / 8, R);
+    l.block = dim3(256);
+    h->plan.push_back(l);
+  };
+  if (c.care) {
+    // encoded states of [s'; s] with the critic's (== actor's, tied) encoder and of s' with the target's
+    care_tables({0, 1});
+    care_mixture_fwd({std::make_tuple(0, 0, 2 * B), std::make_tuple(1, 0, B)});
+    care_mix(0, 2 * B, h->XA.p, h->XA.rs, L.in_w, h->XQ.p, h->XQ.rs, h->K.xw, B);
+    care_mix(1, B, h->XT.p, h->XT.rs, h->K.xw, nullptr, 0, 0, 0);
+  }
+
   auto fwd = [&](const float* Ain, long long rsA, int M, const LayerOff& lo, bool target_or_local_params, float* out,
                  long long rsOut) {
     (void)target_or_local_params;
@@ -532,7 +672,96 @@ static int build_plan(b200sac* h) {
         ps.push_back(dgrad(netp(h->dhQ[l], net, lo.out), h->dhQ[l].rs, lo, netp(h->hQ[l - 1], net, lo.in), h->hQ[l - 1].rs,
                            netp(h->dhQ[l - 1], net, lo.in), h->dhQ[l - 1].rs));
       }
+    else if (c.care)     // the critic loss also trains the critic's state encoder: need d(loss)/d(encoded state)
+      for (int net = 0; net < 2; ++net) {
+        const LayerOff& lo = L.q[net][0];
+        ps.push_back(dgrad(netp(h->dhQ[0], net, lo.out), h->dhQ[0].rs, lo, nullptr, 0,
+                           h->dxP.p + (long long)net * B * h->K.xw, h->dxP.rs));
+      }
     gemm_launch(ps);
+  }
+  if (c.care) {
+    {  // backward of the attention mix: dZk, d(att)
+      Launch l;
+      l.kind = L_CARE_MIXBWD;
+      CareMixBwdArgs& P = l.cmixb;
+      memset(&P, 0, sizeof(P));
+      P.dx = h->dxP.p; P.rsDxNet = (long long)B * h->K.xw; P.rsDxRep = h->dxP.rs; P.lddx = h->K.xw;
+      P.Z = h->mixZ[0].p; P.rsZ = h->mixZ[0].rs; P.kstride = (long long)2 * B * pitch(c.mix_out); P.ldz = pitch(c.mix_out);
+      P.z_row_off = B;
+      P.tab = h->careTab[0].p; P.rsTab = h->careTab[0].rs; P.row_w = h->care_row_w; P.off_att = h->care_off_att;
+      P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
+      P.dZ = h->mixDZ.p; P.rsDZ = h->mixDZ.rs; P.dkstride = (long long)B * pitch(c.mix_out); P.lddz = pitch(c.mix_out);
+      P.datt = h->careDatt.p; P.rsDatt = h->careDatt.rs;
+      P.B = B; P.K = Kenc; P.mo = c.mix_out; P.co = c.ctx_out;
+      l.grid = dim3((B + 7) / 8, R);
+      l.block = dim3(256);
+      h->plan.push_back(l);
+    }
+    for (int l = nmix - 1; l >= 0; --l) {          // mixture-of-encoders backward, K problems per kind
+      std::vector<GemmProb> ps;
+      const LayerOff& lo = L.mix[l];
+      const Buf& dzb = (l == nmix - 1) ? h->mixDZ : h->mixDH[l];
+      for (int k = 0; k < Kenc; ++k) {
+        GemmProb p;
+        memset(&p, 0, sizeof(p));
+        p.A = dzb.p + (long long)k * B * pitch(lo.out); p.rsA = dzb.rs; p.lda = pitch(lo.out);
+        if (l == 0) { p.B = h->XS.p + (long long)B * h->K.obs; p.rsB = h->XS.rs; p.ldb = h->K.obs; }
+        else {
+          const Buf& ib = h->mixH[0][l - 1];
+          p.B = ib.p + ((long long)k * 2 * B + B) * pitch(lo.in); p.rsB = ib.rs; p.ldb = pitch(lo.in);
+        }
+        p.C = Gp(lo.w + (long long)k * lo.out * lo.in); p.rsC = rsG; p.ldc = lo.in;
+        p.C2 = Gp(lo.b + (long long)k * lo.out); p.rsC2 = rsG;
+        p.M = lo.out; p.N = lo.in; p.K = B; p.mode = GEMM_WGRAD;
+        ps.push_back(p);
+      }
+      if (l > 0)
+        for (int k = 0; k < Kenc; ++k) {
+          const Buf& ib = h->mixH[0][l - 1];
+          GemmProb p;
+          memset(&p, 0, sizeof(p));
+          p.A = dzb.p + (long long)k * B * pitch(lo.out); p.rsA = dzb.rs; p.lda = pitch(lo.out);
+          p.B = W(lo.w + (long long)k * lo.out * lo.in); p.rsB = rsP; p.ldb = lo.in;
+          p.mask = ib.p + ((long long)k * 2 * B + B) * pitch(lo.in); p.rsMask = ib.rs; p.ldmask = pitch(lo.in);
+          p.C = h->mixDH[l - 1].p + (long long)k * B * pitch(lo.in); p.rsC = h->mixDH[l - 1].rs; p.ldc = pitch(lo.in);
+          p.M = B; p.N = lo.in; p.K = lo.out; p.mode = GEMM_DGRAD;
+          ps.push_back(p);
+        }
+      gemm_launch(ps);
+    }
+    {  // per-task reduction + softmax backward, then the trunk / context-MLP weight gradients
+      Launch l;
+      l.kind = L_CARE_TABRED;
+      CareTabReduceArgs& P = l.ctred;
+      memset(&P, 0, sizeof(P));
+      P.datt = h->careDatt.p; P.rsDatt = h->careDatt.rs;
+      P.dx = h->dxP.p; P.rsDxNet = (long long)B * h->K.xw; P.rsDxRep = h->dxP.rs; P.lddx = h->K.xw;
+      P.tab = h->careTab[0].p; P.rsTab = h->careTab[0].rs; P.row_w = h->care_row_w; P.off_att = h->care_off_att;
+      P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
+      P.dtab = h->careDtab.p; P.rsDtab = h->careDtab.rs;
+      P.B = B; P.K = Kenc; P.co = c.ctx_out;
+      l.grid = dim3(c.num_tasks, R);
+      l.block = dim3(256);
+      h->plan.push_back(l);
+      Launch l2;
+      l2.kind = L_CARE_TABWG;
+      CareTabWgradArgs& Q = l2.ctwg;
+      memset(&Q, 0, sizeof(Q));
+      Q.params = h->params; Q.rsP = rsP; Q.emb_off = L.off_emb;
+      Q.tab = h->careTab[0].p; Q.rsTab = h->careTab[0].rs; Q.row_w = h->care_row_w;
+      Q.dtab = h->careDtab.p; Q.rsDtab = h->careDtab.rs;
+      Q.grads = h->grads; Q.rsG = rsG;
+      Q.trunk = h->care_trunk; Q.ctx = h->care_ctx;
+      Q.T = c.num_tasks; Q.K = Kenc; Q.co = c.ctx_out;
+      size_t fl = 0;
+      for (int j = 0; j < Q.trunk.n; ++j) fl += (size_t)c.num_tasks * Q.trunk.dims[j + 1];
+      for (int j = 0; j < Q.ctx.n; ++j) fl += (size_t)c.num_tasks * Q.ctx.dims[j + 1];
+      l2.smem = fl * sizeof(float);
+      l2.grid = dim3(64, R);
+      l2.block = dim3(256);
+      h->plan.push_back(l2);
+    }
   }
   auto adam = [&](int which) {
     Launch l;
@@ -544,6 +773,8 @@ static int build_plan(b200sac* h) {
     P.p = h->params + beg; P.m = h->adam_m + beg; P.v = h->adam_v + beg; P.g = h->grads + beg;
     P.rsP = rsP; P.rsM = rsG; P.n = n;
     P.target_delta = which == 0 ? L.target_delta : 0;
+    P.tau2_begin = (which == 0 && c.care) ? (L.cse_begin - L.critic_begin) : (long long)1 << 60;
+    P.tau2 = (float)c.tau_se; P.one_minus_tau2 = (float)(1.0 - c.tau_se);
     P.which = which;
     P.lr = which == 0 ? c.lr_critic : c.lr_actor;
     P.cnt = h->cnt;
@@ -562,6 +793,11 @@ static int build_plan(b200sac* h) {
     h->plan.push_back(l);
   };
   adam(0);
+  if (c.care) {          // encoded states of s with the UPDATED critic encoder for the actor pass (learner.py:336-341)
+    care_tables({2});
+    care_mixture_fwd({std::make_tuple(2, B, B)});
+    care_mix(2, B, h->XP.p, h->XP.rs, h->K.xw, nullptr, 0, 0, 0);
+  }
   // ---- Phase D: actor pass through the updated critics ---------------------------------------
   for (int l = 0; l < Lc; ++l) {
     std::vector<GemmProb> ps;
@@ -659,6 +895,21 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
     Launch& l = h->plan[i];
     if (evs) CU(cudaEventRecord(evs[i], st));
     switch (l.kind) {
+      case L_CARE_TAB:
+        launch_k(care_tables_kernel, l.grid, l.block, 0, st, l.ctab);
+        break;
+      case L_CARE_MIX:
+        launch_k(care_mix_kernel, l.grid, l.block, 0, st, l.cmix);
+        break;
+      case L_CARE_MIXBWD:
+        launch_k(care_mix_bwd_kernel, l.grid, l.block, 0, st, l.cmixb);
+        break;
+      case L_CARE_TABRED:
+        launch_k(care_tab_reduce_kernel, l.grid, l.block, 0, st, l.ctred);
+        break;
+      case L_CARE_TABWG:
+        launch_k(care_tab_wgrad_kernel, l.grid, l.block, l.smem, st, l.ctwg);
+        break;
       case L_GEMM_BIG:
       case L_GEMM_SMALL:
         launch_k(gemm_simt_kernel, l.grid, l.block, 0, st, l.grp);
@@ -716,10 +967,11 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   if (const char* e = getenv("B200SAC_PDL")) g_use_pdl = (e[0] != '0');
   build_layout(cfg, h->L);
   const Layout& L = h->L;
-  const int B = cfg->batch, R = h->R, A = cfg->act_dim, obs = cfg->state_dim + cfg->num_tasks, xw = obs + A;
+  const int B = cfg->batch, R = h->R, A = cfg->act_dim, obs = cfg->state_dim + cfg->num_tasks, xw = L.in_w + A;
+  const int in_w = L.in_w;
   StepConst& K = h->K;
   memset(&K, 0, sizeof(K));
-  K.B = B; K.obs = obs; K.act = A; K.T = cfg->num_tasks; K.xw = xw;
+  K.B = B; K.obs = obs; K.act = A; K.T = cfg->num_tasks; K.xw = xw; K.in_w = in_w; K.care = cfg->care ? 1 : 0;
   K.Ha = cfg->actor_hidden[cfg->n_actor_hidden - 1];
   K.Hc = cfg->critic_hidden[cfg->n_critic_hidden - 1];
   K.gamma = (float)cfg->gamma; K.reward_scale = (float)cfg->reward_scale; K.action_scale = (float)cfg->action_scale;
@@ -762,7 +1014,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   // work slab
   size_t cur = 0;
   const int La = cfg->n_actor_hidden, Lc = cfg->n_critic_hidden;
-  h->XA = carve(cur, (size_t)2 * B * obs, R);
+  h->XA = carve(cur, (size_t)2 * B * in_w, R);
   h->XQ = carve(cur, (size_t)B * xw, R);
   h->XT = carve(cur, (size_t)B * xw, R);
   h->XP = carve(cur, (size_t)B * xw, R);
@@ -798,6 +1050,33 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
     h->hP.push_back(carve(cur, (size_t)2 * B * cfg->critic_hidden[l], R));
     h->dhQ.push_back(carve(cur, (size_t)2 * B * cfg->critic_hidden[l], R));
   }
+  if (cfg->care) {
+    const int Kenc = cfg->num_encoders, T = cfg->num_tasks;
+    auto pitch = [](int w) { return (w + 3) & ~3; };
+    h->XS = carve(cur, (size_t)2 * B * obs, R);
+    // per-task table row: trunk activations per layer, attention, context-MLP activations per layer
+    int off = 0;
+    CareNet& tr = h->care_trunk;
+    CareNet& cx = h->care_ctx;
+    memset(&tr, 0, sizeof(tr)); memset(&cx, 0, sizeof(cx));
+    tr.n = (int)L.trunk.size(); cx.n = (int)L.ctx.size();
+    tr.dims[0] = cx.dims[0] = cfg->ctx_in;
+    for (int j = 0; j < tr.n; ++j) { tr.dims[j + 1] = L.trunk[j].out; tr.w[j] = L.trunk[j].w; tr.b[j] = L.trunk[j].b; tr.act_off[j] = off; off += L.trunk[j].out; }
+    h->care_off_att = off; off += Kenc;
+    for (int j = 0; j < cx.n; ++j) { cx.dims[j + 1] = L.ctx[j].out; cx.w[j] = L.ctx[j].w; cx.b[j] = L.ctx[j].b; cx.act_off[j] = off; off += L.ctx[j].out; }
+    h->care_off_ctx = cx.act_off[cx.n - 1];
+    h->care_row_w = off;
+    for (int i = 0; i < 3; ++i) h->careTab[i] = carve(cur, (size_t)T * off, R);
+    h->careDtab = carve(cur, (size_t)T * (Kenc + cfg->ctx_out), R);
+    h->careDatt = carve(cur, (size_t)B * Kenc, R);
+    const int rows_of[3] = {2 * B, B, B};
+    for (int i = 0; i < 3; ++i) {
+      for (int l = 0; l < cfg->n_mix_hidden; ++l) h->mixH[i].push_back(carve(cur, (size_t)Kenc * rows_of[i] * pitch(cfg->mix_hidden[l]), R));
+      h->mixZ[i] = carve(cur, (size_t)Kenc * rows_of[i] * pitch(cfg->mix_out), R);
+    }
+    for (int l = 0; l < cfg->n_mix_hidden; ++l) h->mixDH.push_back(carve(cur, (size_t)Kenc * B * pitch(cfg->mix_hidden[l]), R));
+    h->mixDZ = carve(cur, (size_t)Kenc * B * pitch(cfg->mix_out), R);
+  }
   h->slab_floats = cur;
   CUH(cudaMalloc(&h->slab, cur * sizeof(float)));
   CUH(cudaMemset(h->slab, 0, cur * sizeof(float)));
@@ -806,6 +1085,13 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
     rebase(*b, h->slab);
   for (auto* v : {&h->hA, &h->dhA, &h->hQ, &h->hT, &h->hP, &h->dhQ})
     for (auto& b : *v) rebase(b, h->slab);
+  if (cfg->care) {
+    for (Buf* b : {&h->XS, &h->careTab[0], &h->careTab[1], &h->careTab[2], &h->careDtab, &h->careDatt, &h->mixZ[0], &h->mixZ[1],
+                   &h->mixZ[2], &h->mixDZ})
+      rebase(*b, h->slab);
+    for (auto* v : {&h->mixH[0], &h->mixH[1], &h->mixH[2], &h->mixDH})
+      for (auto& b : *v) rebase(b, h->slab);
+  }
   if (h->q.rs != 2 * h->y.rs || h->dq.rs != 2 * h->y.rs || h->dqa.rs != 2 * h->y.rs) {
     destroy_impl(h);
     return fail(B200SAC_ERR_INVALID, "internal: q stride");
@@ -815,6 +1101,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   O.XA = h->XA.p; O.XQ = h->XQ.p; O.XT = h->XT.p; O.XP = h->XP.p; O.r = h->r.p; O.d = h->d.p; O.eps = h->eps.p;
   O.tid = (int*)h->tid.p; O.cnt = h->cnt;
   O.rsXA = h->XA.rs; O.rsXQ = h->XQ.rs; O.rsR = h->r.rs; O.rsEps = h->eps.rs;
+  O.XS = cfg->care ? h->XS.p : nullptr; O.rsXS = cfg->care ? h->XS.rs : 0;
   if (h->d.rs != h->r.rs || h->tid.rs != h->r.rs || h->lq.rs != h->y.rs || h->la.rs != h->y.rs || h->qmin.rs != h->y.rs ||
       h->logstd.rs != h->logp.rs) {
     destroy_impl(h);
@@ -828,6 +1115,15 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
       for (const auto& lo : *net) {
         xavier_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, lo.out, lo.in, seed, tag++);
       }
+    if (cfg->care) {     // mixture weights ~ N(0,1) (state_encoder.py:146-153); trunk / context MLP Xavier; embedding random
+      for (const auto& lo : L.mix) {
+        randn_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, (long long)cfg->num_encoders * lo.out * lo.in, seed, tag++);
+        randn_kernel<<<dim3(8, R), 256>>>(h->params + lo.b, L.arena, (long long)cfg->num_encoders * lo.out, seed, tag++);
+      }
+      for (const auto* net : {&L.trunk, &L.ctx})
+        for (const auto& lo : *net) xavier_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, lo.out, lo.in, seed, tag++);
+      randn_kernel<<<dim3(64, R), 256>>>(h->params + L.off_emb, L.arena, (long long)cfg->num_tasks * cfg->ctx_in, seed ^ 0x5EEDull, tag++);
+    }
     std::vector<float> la((size_t)(cfg->num_tasks > 0 ? cfg->num_tasks : 1), (float)cfg->log_alpha_init);
     for (int rep = 0; rep < R; ++rep)
       CUH(cudaMemcpy(h->params + (size_t)rep * L.arena + L.off_alpha, la.data(), la.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1130,6 +1426,11 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
       if (p0.mode == GEMM_WGRAD) return "gemm_wgrad(ffma)";
       return "gemm_dgrad(ffma)";
     }
+    case L_CARE_TAB: return "care_tables";
+    case L_CARE_MIX: return "care_mix";
+    case L_CARE_MIXBWD: return "care_mix_bwd";
+    case L_CARE_TABRED: return "care_tab_reduce";
+    case L_CARE_TABWG: return "care_tab_wgrad";
     case L_POLICY: return "policy_head";
     case L_CHEADS: return "critic_heads";
     case L_AQHEADS: return "actor_q_heads";
@@ -1270,8 +1571,13 @@ extern "C" int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host
 extern "C" int b200sac_soft_update(b200sac_t* h, double tau, void* stream) {
   if (!h) return fail(B200SAC_ERR_INVALID, "null handle");
   CU(cudaSetDevice(h->device));
-  polyak_kernel<<<dim3(128, h->R), 256, 0, (cudaStream_t)stream>>>(h->params + h->L.critic_begin, h->L.arena, h->L.critic_n,
-                                                                   h->L.target_delta, (float)tau, (float)(1.0 - tau));
+  // CARE: Learner.soft_update is called per module with its own tau; this entry point applies `tau` to the Q
+  // functions and, unless tau == 1 (hard copy of everything), state_encoder_tau to the state encoder.
+  const bool hard = (tau == 1.0);
+  polyak_kernel<<<dim3(128, h->R), 256, 0, (cudaStream_t)stream>>>(
+      h->params + h->L.critic_begin, h->L.arena, h->L.critic_n, h->L.target_delta, (float)tau, (float)(1.0 - tau),
+      (h->cfg.care && !hard) ? (long long)(h->L.cse_begin - h->L.critic_begin) : -1LL, (float)h->cfg.tau_se,
+      (float)(1.0 - h->cfg.tau_se));
   CU(cudaGetLastError());
   return 0;
 }

@@ -18,7 +18,9 @@ constexpr int kLossSlots = 1024;
 
 // Per-learner constant block (device copy lives in the handle).
 struct StepConst {
-  int B, obs, act, T, xw;         // xw = obs + act
+  int B, obs, act, T, xw;         // obs = raw observation width (state + one-hot); xw = in_w + act
+  int in_w;                       // width of the state part of the MLP inputs: obs, or ctx_out + mix_out with CARE
+  int care;
   int Ha, Hc;                     // last hidden widths (actor / critic)
   float gamma, reward_scale, action_scale;
   float c_loss;                   // 1/B or 1/B^2 (weighted_loss)
@@ -45,27 +47,37 @@ struct Counters { long long v[4]; double b1p[3]; double b2p[3]; };
 // ------------------------------------------------------------------------------------------
 struct IngestOut {
   float *XA, *XQ, *XT, *XP, *r, *d, *eps;   // replica 0 bases
+  float* XS;                                 // CARE: raw [s' ; s] rows
   int* tid;
   Counters* cnt;
-  long long rsXA, rsXQ, rsR, rsEps;          // per-replica strides
+  long long rsXA, rsXQ, rsR, rsEps, rsXS;    // per-replica strides
 };
 
 B200_D void ingest_row(const StepConst& K, const IngestOut& O, int rep, int i, const float* s, const float* a,
                        float r, const float* s2, float d, int lane, int nl) {
   const int obs = K.obs, act = K.act, xw = K.xw, B = K.B;
-  float* XA = O.XA + rep * O.rsXA;
   float* XQ = O.XQ + rep * O.rsXQ;
-  float* XT = O.XT + rep * O.rsXQ;
-  float* XP = O.XP + rep * O.rsXQ;
-  for (int j = lane; j < obs; j += nl) {
-    float v = s[j], v2 = s2[j];
-    XA[(long long)i * obs + j] = v2;
-    XA[(long long)(B + i) * obs + j] = v;
-    XQ[(long long)i * xw + j] = v;
-    XP[(long long)i * xw + j] = v;
-    XT[(long long)i * xw + j] = v2;
+  if (K.care) {
+    // CARE: the MLP inputs are encoded states produced later by care_mix_kernel; keep the raw rows [s' ; s]
+    float* XS = O.XS + rep * O.rsXS;
+    for (int j = lane; j < obs; j += nl) {
+      XS[(long long)i * obs + j] = s2[j];
+      XS[(long long)(B + i) * obs + j] = s[j];
+    }
+  } else {
+    float* XA = O.XA + rep * O.rsXA;
+    float* XT = O.XT + rep * O.rsXQ;
+    float* XP = O.XP + rep * O.rsXQ;
+    for (int j = lane; j < obs; j += nl) {
+      float v = s[j], v2 = s2[j];
+      XA[(long long)i * obs + j] = v2;
+      XA[(long long)(B + i) * obs + j] = v;
+      XQ[(long long)i * xw + j] = v;
+      XP[(long long)i * xw + j] = v;
+      XT[(long long)i * xw + j] = v2;
+    }
   }
-  for (int j = lane; j < act; j += nl) XQ[(long long)i * xw + obs + j] = a[j];
+  for (int j = lane; j < act; j += nl) XQ[(long long)i * xw + K.in_w + j] = a[j];
   if (lane == 0) {
     (O.r + rep * O.rsR)[i] = r;
     (O.d + rep * O.rsR)[i] = d;
@@ -309,8 +321,8 @@ __global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
     float* pout = P.pout + rep * P.rsPout + (long long)row * NO;
     pout[lane] = mu;
     pout[A + lane] = raw;
-    if (row < B) (P.XT + rep * P.rsX)[(long long)row * K.xw + K.obs + lane] = p.act;
-    else (P.XP + rep * P.rsX)[(long long)(row - B) * K.xw + K.obs + lane] = p.act;
+    if (row < B) (P.XT + rep * P.rsX)[(long long)row * K.xw + K.in_w + lane] = p.act;
+    else (P.XP + rep * P.rsX)[(long long)(row - B) * K.xw + K.in_w + lane] = p.act;
   }
   // sum over actions in index order (lane 0 accumulates j = 0..A-1)
   float tot = 0.f, tls = 0.f;
@@ -464,7 +476,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
       const int m = e / A, j = e % A;
       const float* __restrict__ sv = P.psave + rep * P.rsSave + ((long long)m * A + j) * kSaveW;
       const float std = sv[0], diff = sv[1], t = sv[2], act = sv[3], jac = sv[4], eps = sv[5], mask = sv[6];
-      const float* __restrict__ dx0 = P.dx + rep * P.rsDxRep + (long long)m * P.lddx + K.obs + j;
+      const float* __restrict__ dx0 = P.dx + rep * P.rsDxRep + (long long)m * P.lddx + K.in_w + j;
       const float da = dx0[0] + dx0[P.rsDxNet];
       const int tk = (P.tid + rep * P.rsR)[m];
       const float alpha = (float)exp((double)(P.log_alpha + rep * P.rsP)[tk]);
@@ -569,6 +581,8 @@ struct AdamArgs {
   long long rsP, rsM;                                // replica strides: param arena / trainable arena
   long long n;
   long long target_delta;                            // p[i + target_delta] is the Polyak target (0 = none)
+  long long tau2_begin;                              // elements i >= tau2_begin use (tau2, 1 - tau2): CARE state encoder
+  float tau2, one_minus_tau2;
   int which;                                         // counter index (0 critic, 1 actor)
   double lr;
   const Counters* cnt;
@@ -624,7 +638,7 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
       p[i] = pi; m[i] = mi; v[i] = vi;
       if (P.target_delta != 0) {
         const float t = p[i + P.target_delta];
-        p[i + P.target_delta] = K.tau * pi + K.one_minus_tau * t;
+        p[i + P.target_delta] = i >= P.tau2_begin ? P.tau2 * pi + P.one_minus_tau2 * t : K.tau * pi + K.one_minus_tau * t;
       }
     }
     return;
@@ -693,10 +707,25 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
 
 // Stand-alone Polyak (Learner.soft_update outside a step; tau = 1 -> hard copy).
 __global__ void polyak_kernel(float* p, long long rsP, long long n, long long target_delta, float tau,
-                              float one_minus_tau) {
+                              float one_minus_tau, long long n_tau1 = -1, float tau2 = 0.f, float one_minus_tau2 = 0.f) {
   float* q = p + blockIdx.y * rsP;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    q[i + target_delta] = tau * q[i] + one_minus_tau * q[i + target_delta];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const bool second = n_tau1 >= 0 && i >= n_tau1;
+    q[i + target_delta] = second ? tau2 * q[i] + one_minus_tau2 * q[i + target_delta] : tau * q[i] + one_minus_tau * q[i + target_delta];
+  }
+}
+
+// randn init of the mixture-of-encoders weights (state_encoder.py:146-153)
+__global__ void randn_kernel(float* w, long long rsP, long long n, unsigned long long seed, int tag) {
+  const int rep = blockIdx.y;
+  Philox ph(seed + (unsigned long long)rep);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t rnd[4];
+    ph((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)tag, 0x9A11u, rnd);
+    float z0, z1;
+    box_muller(rnd[0], rnd[1], z0, z1);
+    (w + rep * rsP)[i] = z0;
+  }
 }
 
 // Synthetic replay fill (bench helper): rows [s | a | r | s2 | d | pad], SURVEY 8(d) distributions.

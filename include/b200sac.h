@@ -61,12 +61,24 @@ typedef struct b200sac_cfg {
   int32_t weighted_loss;             /* MTSAC use_weighted_loss (== extra 1/batch) */
   int32_t replicas;                  /* independent learners in this handle (>= 1) */
   int32_t precision;                 /* 0 = fp32 FFMA; 1 = 3xTF32 on tcgen05 for hidden layers */
-  int32_t reserved0;
+  int32_t care;                      /* 1 = CARE(M): context embedding + mixture-of-encoders state encoders
+                                        (MT10_Distributed_CARE/src/{context,state}_encoder.py, use_modified_care) */
   double gamma, tau, reward_scale;
   double lr_actor, lr_critic, lr_alpha;
   double action_scale;               /* k = (hi - lo) / 2 */
   double beta1, beta2, adam_eps;
   double log_alpha_init;
+  /* CARE only (cfg "encoder" block): */
+  int32_t num_encoders;              /* K (num_encoders) */
+  int32_t n_mix_hidden;              /* hidden_dims_mixtureEnc (also the attention trunk's hidden dims) */
+  int32_t mix_hidden[B200SAC_MAX_HIDDEN];
+  int32_t mix_out;                   /* output_dim_mixtureEnc */
+  int32_t ctx_in;                    /* RoBERTa_embedding_dim (768) */
+  int32_t n_ctx_hidden;              /* hidden_dims_contextEnc */
+  int32_t ctx_hidden[B200SAC_MAX_HIDDEN];
+  int32_t ctx_out;                   /* output_dim_contextEnc */
+  int32_t reserved1;
+  double tau_se;                     /* state_encoder_tau */
 } b200sac_cfg;
 
 typedef struct b200sac_tensor_desc {

@@ -95,3 +95,16 @@ class CareCase:
         self.step_in, self.step_out, self.losses = z["step_in"], z["step_out"], z["losses"]
 
     step_batch = Case.step_batch
+
+
+def care_core_config(spec, replicas=1, **kw):
+    from distributed_sac_b200.core import CoreConfig
+    d = dict(state_dim=spec.state_dim, act_dim=spec.act_dim, actor_hidden=list(spec.actor_hidden),
+             critic_hidden=list(spec.critic_hidden), batch=spec.batch, num_tasks=spec.num_tasks,
+             weighted_loss=spec.weighted_loss, replicas=replicas, gamma=spec.gamma, tau=spec.tau,
+             reward_scale=spec.reward_scale, lr_actor=spec.lr_actor, lr_critic=spec.lr_critic,
+             action_scale=spec.action_scale, beta1=spec.beta1, beta2=spec.beta2, adam_eps=spec.adam_eps,
+             care=True, num_encoders=spec.num_encoders, mix_hidden=list(spec.mix_hidden), mix_out=spec.mix_out,
+             ctx_in=spec.ctx_in, ctx_hidden=list(spec.ctx_hidden), ctx_out=spec.ctx_out, tau_se=spec.tau_se)
+    d.update(kw)
+    return CoreConfig(**d)
