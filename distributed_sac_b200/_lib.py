@@ -31,7 +31,7 @@ class Cfg(C.Structure):
 
 class TensorDesc(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32),
-                ("trainable", C.c_int32), ("opt", C.c_int32)]
+                ("trainable", C.c_int32), ("opt", C.c_int32), ("pitch", C.c_int32), ("reserved", C.c_int32)]
 
 
 _F = C.POINTER(C.c_float)

@@ -88,7 +88,7 @@ def layout(cfg: CoreConfig):
     _lib.check(lib.b200sac_layout(C.byref(c), None, 0, C.byref(n), C.byref(arena), C.byref(train)))
     descs = (_lib.TensorDesc * n.value)()
     _lib.check(lib.b200sac_layout(C.byref(c), descs, n.value, C.byref(n), C.byref(arena), C.byref(train)))
-    table = {d.name.decode(): (d.offset, d.rows, d.cols, d.trainable, d.opt) for d in descs}
+    table = {d.name.decode(): (d.offset, d.rows, d.cols, d.trainable, d.opt, d.pitch) for d in descs}
     return table, arena.value, train.value
 
 
@@ -151,10 +151,10 @@ class SacCore:
     def get_named(self, which=_lib.PARAMS, replica=0) -> Dict[str, torch.Tensor]:
         flat = self.export_arena(which, replica)
         out = {}
-        for name, (off, rows, cols, trainable, _opt) in self.table.items():
+        for name, (off, rows, cols, trainable, _opt, pitch) in self.table.items():
             if which != _lib.PARAMS and not trainable:
                 continue
-            t = flat[off:off + rows * cols]
+            t = flat[off:off + rows * pitch].reshape(rows, pitch)[:, :cols].reshape(-1)
             if ".mix." in name:        # stored as [K][out][in] | [K][out]; the reference holds (K,in,out) | (K,1,out)
                 K = self.cfg.num_encoders
                 out[name] = (t.reshape(K, rows // K, cols).permute(0, 2, 1).contiguous() if name.endswith(".W")
@@ -172,7 +172,7 @@ class SacCore:
                 if strict:
                     raise KeyError(name)
                 continue
-            off, rows, cols, trainable, _ = self.table[name]
+            off, rows, cols, trainable, _, pitch = self.table[name]
             if which != _lib.PARAMS and not trainable:
                 continue
             t = torch.as_tensor(t, dtype=torch.float32)
@@ -181,7 +181,7 @@ class SacCore:
             t = t.reshape(-1)
             if t.numel() != rows * cols:
                 raise ValueError(f"{name}: expected {rows * cols} elements, got {t.numel()}")
-            flat[off:off + rows * cols] = t
+            flat[off:off + rows * pitch].reshape(rows, pitch)[:, :cols] = t.reshape(rows, cols)
             seen.add(name)
         if strict:
             need = {n for n, d in self.table.items() if which == _lib.PARAMS or d[3]}

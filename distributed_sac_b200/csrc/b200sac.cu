@@ -51,7 +51,7 @@ extern "C" const char* b200sac_version(void) { return "b200sac 0.1 (sm_100a)"; }
 // ------------------------------------------------------------------------------------------
 // layout
 // ------------------------------------------------------------------------------------------
-struct LayerOff { int64_t w, b; int in, out; };
+struct LayerOff { int64_t w, b; int in, out; int ld; };   // ld = row pitch of the weight matrix (>= in)
 struct Layout {
   std::vector<b200sac_tensor_desc> descs;
   std::vector<LayerOff> actor, q[2], qt[2];
@@ -102,25 +102,28 @@ static void build_layout(const b200sac_cfg* c, Layout& L) {
   const int obs = c->state_dim + c->num_tasks;
   L.in_w = c->care ? (c->ctx_out + c->mix_out) : obs;
   int64_t off = 0;
-  auto add = [&](const char* name, int rows, int cols, int trainable, int opt) {
+  auto add = [&](const char* name, int rows, int cols, int trainable, int opt, int pitch = 0) {
     b200sac_tensor_desc d;
     memset(&d, 0, sizeof(d));
     snprintf(d.name, sizeof(d.name), "%s", name);
-    d.offset = off; d.rows = rows; d.cols = cols; d.trainable = trainable; d.opt = opt;
+    if (pitch < cols) pitch = cols;
+    d.offset = off; d.rows = rows; d.cols = cols; d.trainable = trainable; d.opt = opt; d.pitch = pitch;
     L.descs.push_back(d);
     int64_t o = off;
-    off = pad4(off + (int64_t)rows * cols);
+    off = pad4(off + (int64_t)rows * pitch);
     return o;
   };
   char nm[48];
-  auto add_net = [&](const char* net, std::vector<LayerOff>* v, int in0, const int* hid, int nh, int out, int tr, int opt) {
+  auto add_net = [&](const char* net, std::vector<LayerOff>* v, int in0, const int* hid, int nh, int out, int tr, int opt,
+                     bool pad_first = false) {
     int in = in0;
     for (int i = 0; i <= nh; ++i) {
       int o = (i < nh) ? hid[i] : out;
       LayerOff lo;
       lo.in = in; lo.out = o;
+      lo.ld = (i == 0 && pad_first) ? (int)pad4(in) : in;     // first layer: TMA-addressable rows (16-B pitch)
       snprintf(nm, sizeof(nm), "%s.%d.weight", net, i);
-      lo.w = add(nm, o, in, tr, opt);
+      lo.w = add(nm, o, in, tr, opt, lo.ld);
       snprintf(nm, sizeof(nm), "%s.%d.bias", net, i);
       lo.b = add(nm, o, 1, tr, opt);
       if (v) v->push_back(lo);
@@ -133,7 +136,7 @@ static void build_layout(const b200sac_cfg* c, Layout& L) {
     for (int l = 0; l <= c->n_mix_hidden; ++l) {
       int o = (l < c->n_mix_hidden) ? c->mix_hidden[l] : c->mix_out;
       LayerOff lo;
-      lo.in = in; lo.out = o;
+      lo.in = in; lo.out = o; lo.ld = in;
       snprintf(nm, sizeof(nm), "%s.mix.%d.W", pre, l);
       lo.w = add(nm, c->num_encoders * o, in, tr, opt);
       snprintf(nm, sizeof(nm), "%s.mix.%d.b", pre, l);
@@ -148,19 +151,19 @@ static void build_layout(const b200sac_cfg* c, Layout& L) {
     add_net(pfx, record ? &L.ctx : nullptr, c->ctx_in, c->ctx_hidden, c->n_ctx_hidden, c->ctx_out, tr, opt);
   };
   L.actor_begin = off;
-  add_net("actor", &L.actor, L.in_w, c->actor_hidden, c->n_actor_hidden, 2 * c->act_dim, 1, 1);
+  add_net("actor", &L.actor, L.in_w, c->actor_hidden, c->n_actor_hidden, 2 * c->act_dim, 1, 1, true);
   L.actor_n = off - L.actor_begin;
   L.critic_begin = off;
-  add_net("q1", &L.q[0], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0);
-  add_net("q2", &L.q[1], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0);
+  add_net("q1", &L.q[0], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0, true);
+  add_net("q2", &L.q[1], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 1, 0, true);
   L.cse_begin = off;
   if (c->care) add_encoder("cse", true, 1, 0);
   L.critic_n = off - L.critic_begin;
   L.off_alpha = add("log_alpha", c->num_tasks > 0 ? c->num_tasks : 1, 1, 1, 2);
   L.trainable = off;
   int64_t tb = off;
-  add_net("q1_target", &L.qt[0], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1);
-  add_net("q2_target", &L.qt[1], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1);
+  add_net("q1_target", &L.qt[0], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1, true);
+  add_net("q2_target", &L.qt[1], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1, true);
   if (c->care) add_encoder("tse", false, 0, -1);
   L.target_delta = tb - L.critic_begin;
   if (c->care) L.off_emb = add("embedding", c->num_tasks, c->ctx_in, 0, -1);
@@ -462,7 +465,7 @@ static int build_plan(b200sac* h) {
     }
     P.rsTab = h->careTab[0].rs;
     l.grid = dim3(c.num_tasks, (unsigned)insts.size(), R);
-    l.block = dim3(128);
+    l.block = dim3(512);
     h->plan.push_back(l);
   };
   auto care_mixture_fwd = [&](std::vector<std::tuple<int, int, int>> jobs /* (inst, xs_row0, rows) */) {
@@ -514,8 +517,8 @@ static int build_plan(b200sac* h) {
     // encoded states of [s'; s] with the critic's (== actor's, tied) encoder and of s' with the target's
     care_tables({0, 1});
     care_mixture_fwd({std::make_tuple(0, 0, 2 * B), std::make_tuple(1, 0, B)});
-    care_mix(0, 2 * B, h->XA.p, h->XA.rs, L.in_w, h->XQ.p, h->XQ.rs, h->K.xw, B);
-    care_mix(1, B, h->XT.p, h->XT.rs, h->K.xw, nullptr, 0, 0, 0);
+    care_mix(0, 2 * B, h->XA.p, h->XA.rs, h->K.ldxa, h->XQ.p, h->XQ.rs, h->K.ldx, B);
+    care_mix(1, B, h->XT.p, h->XT.rs, h->K.ldx, nullptr, 0, 0, 0);
   }
 
   auto fwd = [&](const float* Ain, long long rsA, int M, const LayerOff& lo, bool target_or_local_params, float* out,
@@ -523,8 +526,8 @@ static int build_plan(b200sac* h) {
     (void)target_or_local_params;
     GemmProb p;
     memset(&p, 0, sizeof(p));
-    p.A = Ain; p.rsA = rsA; p.lda = lo.in;
-    p.B = W(lo.w); p.rsB = rsP; p.ldb = lo.in;
+    p.A = Ain; p.rsA = rsA; p.lda = lo.ld;
+    p.B = W(lo.w); p.rsB = rsP; p.ldb = lo.ld;
     p.bias = W(lo.b); p.rsBias = rsP;
     p.C = out; p.rsC = rsOut; p.ldc = lo.out;
     p.M = M; p.N = lo.out; p.K = lo.in; p.mode = GEMM_FWD; p.relu = 1;
@@ -534,8 +537,8 @@ static int build_plan(b200sac* h) {
     GemmProb p;
     memset(&p, 0, sizeof(p));
     p.A = dZ; p.rsA = rsdZ; p.lda = lo.out;
-    p.B = X; p.rsB = rsX; p.ldb = lo.in;
-    p.C = Gp(lo.w); p.rsC = rsG; p.ldc = lo.in;
+    p.B = X; p.rsB = rsX; p.ldb = lo.ld;
+    p.C = Gp(lo.w); p.rsC = rsG; p.ldc = lo.ld;
     p.C2 = Gp(lo.b); p.rsC2 = rsG;
     p.M = lo.out; p.N = lo.in; p.K = B; p.mode = GEMM_WGRAD;
     return p;
@@ -545,9 +548,9 @@ static int build_plan(b200sac* h) {
     GemmProb p;
     memset(&p, 0, sizeof(p));
     p.A = dZ; p.rsA = rsdZ; p.lda = lo.out;
-    p.B = W(lo.w); p.rsB = rsP; p.ldb = lo.in;
-    p.mask = mask; p.rsMask = rsMask; p.ldmask = lo.in;
-    p.C = out; p.rsC = rsOut; p.ldc = lo.in;
+    p.B = W(lo.w); p.rsB = rsP; p.ldb = lo.ld;
+    p.mask = mask; p.rsMask = rsMask; p.ldmask = lo.ld;
+    p.C = out; p.rsC = rsOut; p.ldc = lo.ld;
     p.M = B; p.N = lo.in; p.K = lo.out; p.mode = GEMM_DGRAD;
     return p;
   };
@@ -645,7 +648,7 @@ static int build_plan(b200sac* h) {
       P.W[0] = W(lo.w); P.dW[0] = Gp(lo.w); P.db[0] = Gp(lo.b);
       P.h = h->hA[La - 1].p + (long long)B * Ha; P.rsHrep = h->hA[La - 1].rs; P.ldh = Ha;   // rows B..2B-1 (= s half)
       P.dh = h->dhA[La - 1].p; P.rsDhRep = h->dhA[La - 1].rs; P.lddh = Ha;
-      P.dx = h->dxP.p; P.rsDxNet = (long long)B * h->K.xw; P.rsDxRep = h->dxP.rs; P.lddx = h->K.xw;
+      P.dx = h->dxP.p; P.rsDxNet = (long long)B * h->K.ldx; P.rsDxRep = h->dxP.rs; P.lddx = h->K.ldx;
       P.psave = h->psave.p + (long long)B * A * kSaveW; P.rsSave = h->psave.rs;
       P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
       P.log_alpha = W(L.off_alpha);
@@ -676,7 +679,7 @@ static int build_plan(b200sac* h) {
       for (int net = 0; net < 2; ++net) {
         const LayerOff& lo = L.q[net][0];
         ps.push_back(dgrad(netp(h->dhQ[0], net, lo.out), h->dhQ[0].rs, lo, nullptr, 0,
-                           h->dxP.p + (long long)net * B * h->K.xw, h->dxP.rs));
+                           h->dxP.p + (long long)net * B * h->K.ldx, h->dxP.rs));
       }
     gemm_launch(ps);
   }
@@ -686,7 +689,7 @@ static int build_plan(b200sac* h) {
       l.kind = L_CARE_MIXBWD;
       CareMixBwdArgs& P = l.cmixb;
       memset(&P, 0, sizeof(P));
-      P.dx = h->dxP.p; P.rsDxNet = (long long)B * h->K.xw; P.rsDxRep = h->dxP.rs; P.lddx = h->K.xw;
+      P.dx = h->dxP.p; P.rsDxNet = (long long)B * h->K.ldx; P.rsDxRep = h->dxP.rs; P.lddx = h->K.ldx;
       P.Z = h->mixZ[0].p; P.rsZ = h->mixZ[0].rs; P.kstride = (long long)2 * B * pitch(c.mix_out); P.ldz = pitch(c.mix_out);
       P.z_row_off = B;
       P.tab = h->careTab[0].p; P.rsTab = h->careTab[0].rs; P.row_w = h->care_row_w; P.off_att = h->care_off_att;
@@ -736,13 +739,13 @@ static int build_plan(b200sac* h) {
       CareTabReduceArgs& P = l.ctred;
       memset(&P, 0, sizeof(P));
       P.datt = h->careDatt.p; P.rsDatt = h->careDatt.rs;
-      P.dx = h->dxP.p; P.rsDxNet = (long long)B * h->K.xw; P.rsDxRep = h->dxP.rs; P.lddx = h->K.xw;
+      P.dx = h->dxP.p; P.rsDxNet = (long long)B * h->K.ldx; P.rsDxRep = h->dxP.rs; P.lddx = h->K.ldx;
       P.tab = h->careTab[0].p; P.rsTab = h->careTab[0].rs; P.row_w = h->care_row_w; P.off_att = h->care_off_att;
       P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
       P.dtab = h->careDtab.p; P.rsDtab = h->careDtab.rs;
       P.B = B; P.K = Kenc; P.co = c.ctx_out;
       l.grid = dim3(c.num_tasks, R);
-      l.block = dim3(256);
+      l.block = dim3(1024);
       h->plan.push_back(l);
       Launch l2;
       l2.kind = L_CARE_TABWG;
@@ -758,7 +761,7 @@ static int build_plan(b200sac* h) {
       for (int j = 0; j < Q.trunk.n; ++j) fl += (size_t)c.num_tasks * Q.trunk.dims[j + 1];
       for (int j = 0; j < Q.ctx.n; ++j) fl += (size_t)c.num_tasks * Q.ctx.dims[j + 1];
       l2.smem = fl * sizeof(float);
-      l2.grid = dim3(64, R);
+      l2.grid = dim3(148, R);
       l2.block = dim3(256);
       h->plan.push_back(l2);
     }
@@ -796,7 +799,7 @@ static int build_plan(b200sac* h) {
   if (c.care) {          // encoded states of s with the UPDATED critic encoder for the actor pass (learner.py:336-341)
     care_tables({2});
     care_mixture_fwd({std::make_tuple(2, B, B)});
-    care_mix(2, B, h->XP.p, h->XP.rs, h->K.xw, nullptr, 0, 0, 0);
+    care_mix(2, B, h->XP.p, h->XP.rs, h->K.ldx, nullptr, 0, 0, 0);
   }
   // ---- Phase D: actor pass through the updated critics ---------------------------------------
   for (int l = 0; l < Lc; ++l) {
@@ -834,7 +837,7 @@ static int build_plan(b200sac* h) {
                            netp(h->dhQ[l - 1], net, lo.in), h->dhQ[l - 1].rs));
       else
         ps.push_back(dgrad(netp(h->dhQ[0], net, lo.out), h->dhQ[0].rs, lo, nullptr, 0,
-                           h->dxP.p + (long long)net * B * h->K.xw, h->dxP.rs));
+                           h->dxP.p + (long long)net * B * h->K.ldx, h->dxP.rs));
     }
     gemm_launch(ps);
   }
@@ -843,11 +846,11 @@ static int build_plan(b200sac* h) {
   for (int l = La - 1; l >= 0; --l) {
     std::vector<GemmProb> ps;
     const LayerOff& lo = L.actor[l];
-    const float* X = l == 0 ? h->XA.p + (long long)B * lo.in : h->hA[l - 1].p + (long long)B * lo.in;
+    const float* X = l == 0 ? h->XA.p + (long long)B * lo.ld : h->hA[l - 1].p + (long long)B * lo.ld;
     const long long rsX = l == 0 ? h->XA.rs : h->hA[l - 1].rs;
     ps.push_back(wgrad(h->dhA[l].p, h->dhA[l].rs, X, rsX, lo));
     if (l > 0)
-      ps.push_back(dgrad(h->dhA[l].p, h->dhA[l].rs, lo, h->hA[l - 1].p + (long long)B * lo.in, h->hA[l - 1].rs,
+      ps.push_back(dgrad(h->dhA[l].p, h->dhA[l].rs, lo, h->hA[l - 1].p + (long long)B * lo.ld, h->hA[l - 1].rs,
                          h->dhA[l - 1].p, h->dhA[l - 1].rs));
     gemm_launch(ps);
   }
@@ -972,6 +975,8 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   StepConst& K = h->K;
   memset(&K, 0, sizeof(K));
   K.B = B; K.obs = obs; K.act = A; K.T = cfg->num_tasks; K.xw = xw; K.in_w = in_w; K.care = cfg->care ? 1 : 0;
+  K.ldxa = (int)pad4(in_w); K.ldx = (int)pad4(xw);
+  const int ldxa = K.ldxa, ldx = K.ldx;
   K.Ha = cfg->actor_hidden[cfg->n_actor_hidden - 1];
   K.Hc = cfg->critic_hidden[cfg->n_critic_hidden - 1];
   K.gamma = (float)cfg->gamma; K.reward_scale = (float)cfg->reward_scale; K.action_scale = (float)cfg->action_scale;
@@ -1014,10 +1019,10 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   // work slab
   size_t cur = 0;
   const int La = cfg->n_actor_hidden, Lc = cfg->n_critic_hidden;
-  h->XA = carve(cur, (size_t)2 * B * in_w, R);
-  h->XQ = carve(cur, (size_t)B * xw, R);
-  h->XT = carve(cur, (size_t)B * xw, R);
-  h->XP = carve(cur, (size_t)B * xw, R);
+  h->XA = carve(cur, (size_t)2 * B * ldxa, R);
+  h->XQ = carve(cur, (size_t)B * ldx, R);
+  h->XT = carve(cur, (size_t)B * ldx, R);
+  h->XP = carve(cur, (size_t)B * ldx, R);
   h->XT.rs = h->XP.rs = h->XQ.rs;
   h->r = carve(cur, B, R);
   h->d = carve(cur, B, R);
@@ -1036,7 +1041,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   h->q = carve(cur, (size_t)2 * h->y.rs, R);
   h->dq = carve(cur, (size_t)2 * h->y.rs, R);
   h->dqa = carve(cur, (size_t)2 * h->y.rs, R);
-  h->dxP = carve(cur, (size_t)2 * B * xw, R);
+  h->dxP = carve(cur, (size_t)2 * B * ldx, R);
   h->dout_dbg = carve(cur, (size_t)B * 2 * A, R);
   h->dact_dbg = carve(cur, (size_t)B * 2 * A, R);
   h->dact_dbg.rs = h->dout_dbg.rs;
@@ -1113,7 +1118,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
     int tag = 0;
     for (const auto* net : {&L.actor, &L.q[0], &L.q[1]})
       for (const auto& lo : *net) {
-        xavier_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, lo.out, lo.in, seed, tag++);
+        xavier_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, lo.out, lo.in, lo.ld, seed, tag++);
       }
     if (cfg->care) {     // mixture weights ~ N(0,1) (state_encoder.py:146-153); trunk / context MLP Xavier; embedding random
       for (const auto& lo : L.mix) {
@@ -1121,7 +1126,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
         randn_kernel<<<dim3(8, R), 256>>>(h->params + lo.b, L.arena, (long long)cfg->num_encoders * lo.out, seed, tag++);
       }
       for (const auto* net : {&L.trunk, &L.ctx})
-        for (const auto& lo : *net) xavier_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, lo.out, lo.in, seed, tag++);
+        for (const auto& lo : *net) xavier_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, lo.out, lo.in, lo.ld, seed, tag++);
       randn_kernel<<<dim3(64, R), 256>>>(h->params + L.off_emb, L.arena, (long long)cfg->num_tasks * cfg->ctx_in, seed ^ 0x5EEDull, tag++);
     }
     std::vector<float> la((size_t)(cfg->num_tasks > 0 ? cfg->num_tasks : 1), (float)cfg->log_alpha_init);

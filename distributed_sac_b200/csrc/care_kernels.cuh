@@ -37,8 +37,9 @@ struct CareTabArgs {
   int T, K, row_w, off_att;
 };
 
-// grid (T, n_inst, R), block 128
-__global__ void __launch_bounds__(128) care_tables_kernel(CareTabArgs P) {
+// grid (T, n_inst, R), block 512: 16 warps, one output neuron per warp at a time, 8 independent
+// loads in flight per lane (the 768-long dot products are pure latency otherwise)
+__global__ void __launch_bounds__(512) care_tables_kernel(CareTabArgs P) {
   kstamp();
   __shared__ float xe[2048];
   __shared__ float bufA[512], bufB[512];
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(128) care_tables_kernel(CareTabArgs P) {
   float* __restrict__ row = P.tab[inst] + rep * P.rsTab + (long long)t * P.row_w;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int cin = P.trunk.dims[0];
-  for (int i = threadIdx.x; i < cin; i += 128) xe[i] = E[i];
+  for (int i = threadIdx.x; i < cin; i += 512) xe[i] = E[i];
   __syncthreads();
   for (int which = 0; which < 2; ++which) {
     const CareNet& N = which == 0 ? P.trunk : P.ctx;
@@ -58,9 +59,18 @@ __global__ void __launch_bounds__(128) care_tables_kernel(CareTabArgs P) {
       const int nin = N.dims[j], nout = N.dims[j + 1];
       const float* __restrict__ W = par + P.inst_delta[inst] + N.w[j];
       const float* __restrict__ bb = par + P.inst_delta[inst] + N.b[j];
-      for (int o = warp; o < nout; o += 4) {
+      for (int o = warp; o < nout; o += 16) {
+        const float* __restrict__ wr = W + (long long)o * nin;
         float a = 0.f;
-        for (int i = lane; i < nin; i += 32) a = fmaf(cur[i], __ldg(W + (long long)o * nin + i), a);
+        int i = lane;
+        for (; i + 7 * 32 < nin; i += 8 * 32) {
+          float wv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) wv[u] = __ldg(wr + i + u * 32);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) a = fmaf(cur[i + u * 32], wv[u], a);
+        }
+        for (; i < nin; i += 32) a = fmaf(cur[i], __ldg(wr + i), a);
         a = warp_sum(a) + bb[o];
         if (j < N.n - 1) a = fmaxf(a, 0.f);
         if (lane == 0) { nxt[o] = a; row[N.act_off[j] + o] = a; }
@@ -169,10 +179,10 @@ struct CareTabReduceArgs {
   int B, K, co;
 };
 
-// grid (T, R), block 256 = 4 row groups x 64 values
-__global__ void __launch_bounds__(256) care_tab_reduce_kernel(CareTabReduceArgs P) {
+// grid (T, R), block 1024 = 16 row groups x 64 values; partial sums combined in a fixed order
+__global__ void __launch_bounds__(1024) care_tab_reduce_kernel(CareTabReduceArgs P) {
   kstamp();
-  __shared__ float part[4][64];
+  __shared__ float part[16][64];
   __shared__ float tot[64];
   const int t = blockIdx.x, rep = blockIdx.y;
   const int v = threadIdx.x % 64, g = threadIdx.x / 64;
@@ -182,28 +192,31 @@ __global__ void __launch_bounds__(256) care_tab_reduce_kernel(CareTabReduceArgs 
     const int vv = v0 + v;
     float s = 0.f;
     if (vv < nv) {
-      for (int i = g; i < P.B; i += 4) {
+      const float* __restrict__ src = vv < P.K ? P.datt + rep * P.rsDatt + vv : P.dx + rep * P.rsDxRep + (vv - P.K);
+      const long long ld = vv < P.K ? P.K : P.lddx;
+      const long long second = vv < P.K ? 0 : P.rsDxNet;
+      for (int i = g; i < P.B; i += 16) {
         if (tid[i] != t) continue;
-        if (vv < P.K) s += (P.datt + rep * P.rsDatt)[(long long)i * P.K + vv];
-        else {
-          const float* d = P.dx + rep * P.rsDxRep + (long long)i * P.lddx + (vv - P.K);
-          s += d[0] + d[P.rsDxNet];
-        }
+        const float* d = src + (long long)i * ld;
+        s += second ? d[0] + d[second] : d[0];
       }
     }
     part[g][v] = s;
     __syncthreads();
-    if (g == 0) tot[v] = ((part[0][v] + part[1][v]) + part[2][v]) + part[3][v];
+    if (g == 0) {
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) a += part[q][v];
+      tot[v] = a;
+    }
     __syncthreads();
     float* out = P.dtab + rep * P.rsDtab + (long long)t * nv;
     if (g == 0 && vv < nv && vv >= P.K) out[vv] = tot[v];
-    if (v0 == 0) {                                     // softmax backward on the K attention gradients (K <= 32 < 64)
-      if (threadIdx.x == 0) {
-        const float* att = P.tab + rep * P.rsTab + (long long)t * P.row_w + P.off_att;
-        float dot = 0.f;
-        for (int k = 0; k < P.K; ++k) dot += att[k] * tot[k];
-        for (int k = 0; k < P.K; ++k) out[k] = att[k] * (tot[k] - dot);
-      }
+    if (v0 == 0 && threadIdx.x == 0) {                 // softmax backward on the K attention gradients (K <= 32 < 64)
+      const float* att = P.tab + rep * P.rsTab + (long long)t * P.row_w + P.off_att;
+      float dot = 0.f;
+      for (int k = 0; k < P.K; ++k) dot += att[k] * tot[k];
+      for (int k = 0; k < P.K; ++k) out[k] = att[k] * (tot[k] - dot);
     }
     __syncthreads();
   }

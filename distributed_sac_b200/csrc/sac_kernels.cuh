@@ -21,6 +21,7 @@ struct StepConst {
   int B, obs, act, T, xw;         // obs = raw observation width (state + one-hot); xw = in_w + act
   int in_w;                       // width of the state part of the MLP inputs: obs, or ctx_out + mix_out with CARE
   int care;
+  int ldxa, ldx;                  // row pitches of XA ([2B][in_w]) and of XQ/XT/XP/dx ([B][xw]): multiples of 4 floats
   int Ha, Hc;                     // last hidden widths (actor / critic)
   float gamma, reward_scale, action_scale;
   float c_loss;                   // 1/B or 1/B^2 (weighted_loss)
@@ -55,7 +56,7 @@ struct IngestOut {
 
 B200_D void ingest_row(const StepConst& K, const IngestOut& O, int rep, int i, const float* s, const float* a,
                        float r, const float* s2, float d, int lane, int nl) {
-  const int obs = K.obs, act = K.act, xw = K.xw, B = K.B;
+  const int obs = K.obs, act = K.act, xw = K.ldx, xa = K.ldxa, B = K.B;
   float* XQ = O.XQ + rep * O.rsXQ;
   if (K.care) {
     // CARE: the MLP inputs are encoded states produced later by care_mix_kernel; keep the raw rows [s' ; s]
@@ -70,8 +71,8 @@ B200_D void ingest_row(const StepConst& K, const IngestOut& O, int rep, int i, c
     float* XP = O.XP + rep * O.rsXQ;
     for (int j = lane; j < obs; j += nl) {
       float v = s[j], v2 = s2[j];
-      XA[(long long)i * obs + j] = v2;
-      XA[(long long)(B + i) * obs + j] = v;
+      XA[(long long)i * xa + j] = v2;
+      XA[(long long)(B + i) * xa + j] = v;
       XQ[(long long)i * xw + j] = v;
       XP[(long long)i * xw + j] = v;
       XT[(long long)i * xw + j] = v2;
@@ -321,8 +322,8 @@ __global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
     float* pout = P.pout + rep * P.rsPout + (long long)row * NO;
     pout[lane] = mu;
     pout[A + lane] = raw;
-    if (row < B) (P.XT + rep * P.rsX)[(long long)row * K.xw + K.in_w + lane] = p.act;
-    else (P.XP + rep * P.rsX)[(long long)(row - B) * K.xw + K.in_w + lane] = p.act;
+    if (row < B) (P.XT + rep * P.rsX)[(long long)row * K.ldx + K.in_w + lane] = p.act;
+    else (P.XP + rep * P.rsX)[(long long)(row - B) * K.ldx + K.in_w + lane] = p.act;
   }
   // sum over actions in index order (lane 0 accumulates j = 0..A-1)
   float tot = 0.f, tls = 0.f;
@@ -632,13 +633,30 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
     float* m = P.m + rep * P.rsM;
     float* v = P.v + rep * P.rsM;
     const float* g = P.g + rep * P.rsM;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < P.n; i += (long long)nb * 256) {
-      float pi = p[i], mi = m[i], vi = v[i];
-      adam_one(pi, mi, vi, g[i], w1, b2, omb2, step_size, bc2_sqrt, eps);
-      p[i] = pi; m[i] = mi; v[i] = vi;
-      if (P.target_delta != 0) {
-        const float t = p[i + P.target_delta];
-        p[i + P.target_delta] = i >= P.tau2_begin ? P.tau2 * pi + P.one_minus_tau2 * t : K.tau * pi + K.one_minus_tau * t;
+    // 128-bit accesses, all five streams of an element group in flight before the math (slices are
+    // multiples of 4 floats and 16-B aligned by construction of the arena)
+    const long long n4 = P.n >> 2;
+    float4* __restrict__ p4 = reinterpret_cast<float4*>(p);
+    float4* __restrict__ m4 = reinterpret_cast<float4*>(m);
+    float4* __restrict__ v4 = reinterpret_cast<float4*>(v);
+    const float4* __restrict__ g4 = reinterpret_cast<const float4*>(g);
+    float4* __restrict__ t4 = P.target_delta != 0 ? reinterpret_cast<float4*>(p + P.target_delta) : nullptr;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)nb * 256) {
+      float4 pv = p4[i], mv = m4[i], vv = v4[i];
+      const float4 gv = g4[i];
+      float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t4) tv = t4[i];
+      adam_one(pv.x, mv.x, vv.x, gv.x, w1, b2, omb2, step_size, bc2_sqrt, eps);
+      adam_one(pv.y, mv.y, vv.y, gv.y, w1, b2, omb2, step_size, bc2_sqrt, eps);
+      adam_one(pv.z, mv.z, vv.z, gv.z, w1, b2, omb2, step_size, bc2_sqrt, eps);
+      adam_one(pv.w, mv.w, vv.w, gv.w, w1, b2, omb2, step_size, bc2_sqrt, eps);
+      p4[i] = pv; m4[i] = mv; v4[i] = vv;
+      if (t4) {
+        const bool second = (i << 2) >= P.tau2_begin;         // tau2_begin is a multiple of 4 (tensor offsets are)
+        const float ta = second ? P.tau2 : K.tau, tb = second ? P.one_minus_tau2 : K.one_minus_tau;
+        tv.x = ta * pv.x + tb * tv.x; tv.y = ta * pv.y + tb * tv.y;
+        tv.z = ta * pv.z + tb * tv.z; tv.w = ta * pv.w + tb * tv.w;
+        t4[i] = tv;
       }
     }
     return;
@@ -767,7 +785,7 @@ __global__ void fill_synthetic_kernel(float* rows, long long rs_rows, int row_st
 }
 
 // Xavier-uniform init of one [out][in] matrix (nn.init.xavier_uniform_, gain 1), bias zero.
-__global__ void xavier_kernel(float* w, long long rsP, int rows, int cols, unsigned long long seed, int tag) {
+__global__ void xavier_kernel(float* w, long long rsP, int rows, int cols, int ld, unsigned long long seed, int tag) {
   const int rep = blockIdx.y;
   Philox ph(seed + (unsigned long long)rep);
   const float bound = sqrtf(6.f / (float)(rows + cols));
@@ -775,7 +793,7 @@ __global__ void xavier_kernel(float* w, long long rsP, int rows, int cols, unsig
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     uint32_t rnd[4];
     ph((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)tag, 0x1417u, rnd);
-    (w + rep * rsP)[i] = (2.f * u01(rnd[0]) - 1.f) * bound;
+    (w + rep * rsP)[(i / cols) * ld + (i % cols)] = (2.f * u01(rnd[0]) - 1.f) * bound;
   }
 }
 

@@ -417,5 +417,92 @@ class MTSACLearner(_BaseLearner):
         return one_hots @ self.log_alpha.reshape(-1, 1)
 
 
+class CARELearner(MTSACLearner):
+    """MT10_Distributed_CARE/src/learner.py with `use_modified_care: true` (CARE(M)):
+    Learner(train_classes, train_tasks, cfg_path, write_mode, save_period, checkpoint_path).
+
+    One actor / twin-Q critic over the encoded state [mlp_context(z) | attention-mixed K encoders(state)],
+    z = frozen RoBERTa embedding of the task (cfg 'encoder' block; metadata JSONs are read relative to the
+    working directory exactly like context_encoder.py:31-36).  The actor's state encoder is a hard copy of the
+    critic's after every update (learner.py:402), so it is exported from the same tensors."""
+    family = "C10"
+    log_name = "MT10_Distributed_CARE"
+
+    def _set_dims(self):
+        super()._set_dims()
+        c = self.cfg
+        if not c.get("use_modified_care", False):
+            raise NotImplementedError("only CARE(M) (use_modified_care: true) is implemented; CARE(O) has a trainable context encoder")
+        self.use_modified_care = True
+        self.use_weighted_loss = True                      # learner.py:313,349: use_weighted_loss = use_modified_care
+        self.encoder_cfg = c["encoder"]
+
+    def _core_config(self):
+        cc = super()._core_config()
+        e = self.encoder_cfg
+        cc.care = True
+        cc.num_encoders = int(e["num_encoders"])
+        cc.mix_hidden = [int(x) for x in e["hidden_dims_mixtureEnc"]]
+        cc.mix_out = int(e["output_dim_mixtureEnc"])
+        cc.ctx_in = int(e["RoBERTa_embedding_dim"])
+        cc.ctx_hidden = [int(x) for x in e["hidden_dims_contextEnc"]]
+        cc.ctx_out = int(e["output_dim_contextEnc"])
+        cc.tau_se = float(e["state_encoder_tau"])
+        return cc
+
+    def _init_common(self, *a, **kw):
+        super()._init_common(*a, **kw)
+        e = self.encoder_cfg
+        emb_path, names_path = e.get("pretrained_embedding_json_path"), e.get("task_name_json_path")
+        if emb_path and names_path and os.path.exists(emb_path) and os.path.exists(names_path):
+            table, order = cfg_read(emb_path), cfg_read(names_path)
+            E = torch.tensor([table[n] for n in order], dtype=torch.float32)       # context_encoder.py:43-47
+            if E.shape != (self.num_tasks, self.core.cfg.ctx_in):
+                raise ValueError(f"pretrained embedding has shape {tuple(E.shape)}, cfg says ({self.num_tasks}, {self.core.cfg.ctx_in})")
+            self.core.set_named({"embedding": E}, strict=False)
+
+    def _enc_map(self, prefix):
+        cc = self.core.cfg
+        return names.care_encoder_key_map(len(cc.mix_hidden) + 1, len(cc.mix_hidden) + 1, len(cc.ctx_hidden) + 1, prefix)
+
+    def _key_map(self, net):
+        if net == "context_encoder":
+            return {"embedding.0.weight": "embedding"}
+        if net == "actor":            # policy MLP + the tied copy of the critic's state encoder
+            return {**names.actor_key_map("MS", len(self.actor_hidden_dim) + 1), **self._enc_map("cse")}
+        if net in ("critic_se", "target_se"):
+            return self._enc_map("cse" if net == "critic_se" else "tse")
+        which = 1 if "1" in net else 2
+        return names.critic_key_map("MS", len(self.critic_hidden_dim) + 1, which, target="target" in net)
+
+    def get_parameters(self):
+        return {"context_encoder": self._module_state_dict("context_encoder"), "actor": self._module_state_dict("actor")}
+
+    def _critic_checkpoint_entries(self, named):
+        d = super()._critic_checkpoint_entries(named)
+        d["local_critic"].update(self._module_state_dict("critic_se", named=named))
+        d["target_critic"].update(self._module_state_dict("target_se", named=named))
+        d["context_encoder"] = self._module_state_dict("context_encoder", named=named)
+        return d
+
+    def _load_critic_checkpoint_entries(self, ck):
+        super()._load_critic_checkpoint_entries(ck)
+        self._load_module_state_dict("critic_se", ck["local_critic"])
+        self._load_module_state_dict("target_se", ck["target_critic"])
+        if "context_encoder" in ck:
+            self._load_module_state_dict("context_encoder", ck["context_encoder"])
+
+    def _canon(self, nets):
+        out = []
+        for net in nets:
+            if net == "actor":        # actor_optimizer holds mu_log_std_layer only (learner.py:146-149)
+                out += list(names.actor_key_map("MS", len(self.actor_hidden_dim) + 1).values())
+            else:
+                out += list(self._key_map(net).values())
+        if tuple(nets) == ("q1", "q2"):   # critic_optimizer = local_critic.parameters(): state encoder first (learner.py:150-153)
+            out = list(self._enc_map("cse").values()) + out
+        return out
+
+
 # the reference modules all call their class `Learner`
 Learner = LunarLanderLearner

@@ -48,3 +48,18 @@ def critic_key_map(family: str, n_layers: int, which: int, target: bool = False)
                 raise ValueError(family)
             m[ref] = f"{net}.{i}.{kind}"
     return m
+
+
+def care_encoder_key_map(n_mix: int, n_trunk: int, n_ctx: int, prefix: str):
+    """{reference key under `state_encoder.`: canonical key} for one CARE state encoder
+    (MT10_Distributed_CARE/src/state_encoder.py:36-63,196-217: mixtureEncoders.{2l}.{W,b}, trunk.{2j}.*, mlp_context.{2j}.*).
+    prefix = 'cse' (critic's; also what the actor's tied copy exports) or 'tse' (target critic's)."""
+    m = {}
+    for l in range(n_mix):
+        m[f"state_encoder.mixture_encoders.mixtureEncoders.{2 * l}.W"] = f"{prefix}.mix.{l}.W"
+        m[f"state_encoder.mixture_encoders.mixtureEncoders.{2 * l}.b"] = f"{prefix}.mix.{l}.b"
+    for name, n, ref in (("trunk", n_trunk, "trunk"), ("ctx", n_ctx, "mlp_context")):
+        for j in range(n):
+            for kind in ("weight", "bias"):
+                m[f"state_encoder.{ref}.{2 * j}.{kind}"] = f"{prefix}.{name}.{j}.{kind}"
+    return m

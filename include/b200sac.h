@@ -87,6 +87,9 @@ typedef struct b200sac_tensor_desc {
   int32_t rows, cols;                /* weight: (out, in) row-major; bias/log_alpha: (n, 1) */
   int32_t trainable;                 /* 1 -> has Adam m/v at the same offset in the m/v arenas */
   int32_t opt;                       /* 0 critic, 1 actor, 2 alpha, -1 none (targets) */
+  int32_t pitch;                     /* floats between consecutive rows (>= cols): first-layer weights are padded to a
+                                        multiple of 4 so that TMA can address them; pad columns are and stay zero */
+  int32_t reserved;
 } b200sac_tensor_desc;
 
 typedef struct b200sac b200sac_t;               /* learner handle */

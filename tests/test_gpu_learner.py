@@ -113,3 +113,54 @@ def test_run_loop_with_redis_stub(cuda, tmp_path):
     assert params["actor"]["mu_log_std_layer.weight"].shape == (4, 256)
     assert lrn.server.llen("critic_loss") == 7 and lrn.server.llen("alpha") == 7
     lrn.memory.stop()
+
+
+def test_care_learner_surface(cuda, tmp_path):
+    """CARELearner: cfg 'encoder' block + metadata JSONs as in MT10_Distributed_CARE_cfg.json; published blob has the
+    reference's keys/shapes (Player loads context_encoder + actor state_dicts, C10/player.py:82-93)."""
+    import numpy as np
+    from distributed_sac_b200.learner import CARELearner
+    names_ = [f"task-{i}" for i in range(10)]
+    rng = np.random.default_rng(0)
+    emb = {n: rng.standard_normal(768).round(4).tolist() for n in names_}
+    (tmp_path / "emb.json").write_text(json.dumps(emb))
+    (tmp_path / "names.json").write_text(json.dumps(names_))
+    cfg = {"use_modified_care": True, "num_tasks": 10, "device": "cuda", "buffer_size": 40000, "reward_scale": 1,
+           "batch_size": 160, "log_alpha": 0, "tau": 0.005, "update_delay": 6, "random_step": 5000, "start_memory_len": 5000,
+           "print_period_player": 2, "print_period_learner": 10, "gamma": 0.99, "max_episode_time": 500,
+           "actor": {"state_dim": 39, "action_dim": 4, "action_bound": [-1.0, 1.0], "lr_actor": 3e-4, "actor_hidden_dim": [64, 64, 64]},
+           "critic": {"state_dim": 39, "action_dim": 4, "lr_critic": 3e-4, "critic_hidden_dim": [64, 64, 64]},
+           "encoder": {"state_dim": 39, "pretrained_embedding_json_path": str(tmp_path / "emb.json"),
+                       "task_name_json_path": str(tmp_path / "names.json"), "hidden_dims_contextEnc": [50, 50],
+                       "embedding_dim_contextEnc": 50, "output_dim_contextEnc": 50, "RoBERTa_embedding_dim": 768,
+                       "lr_contextEnc": 3e-4, "hidden_dims_mixtureEnc": [50], "output_dim_mixtureEnc": 50, "num_encoders": 6,
+                       "num_tasks": 10, "state_encoder_tau": 0.05}}
+    p = tmp_path / "cfg.json"
+    p.write_text(json.dumps(cfg))
+    os.chdir(tmp_path)
+    lrn = CARELearner(None, names_, str(p), write_mode=False, server=redis_stub.StrictRedis(host=str(tmp_path) + "c"))
+    lrn.memory.ring.fill_synthetic(40000, seed=1)
+    for _ in range(4):
+        cl, al, ent = lrn.update()
+        assert cl == cl and al == al and ent == ent
+    blob = pickle.loads(pickle.dumps(lrn.get_parameters()))
+    assert set(blob) == {"context_encoder", "actor"}
+    E = blob["context_encoder"]["embedding.0.weight"]
+    assert E.shape == (10, 768) and torch.allclose(E, torch.tensor([emb[n] for n in names_]))
+    a = blob["actor"]
+    assert a["state_encoder.mixture_encoders.mixtureEncoders.0.W"].shape == (6, 39, 50)
+    assert a["state_encoder.mixture_encoders.mixtureEncoders.0.b"].shape == (6, 1, 50)
+    assert a["state_encoder.mixture_encoders.mixtureEncoders.2.W"].shape == (6, 50, 50)
+    assert a["state_encoder.trunk.0.weight"].shape == (50, 768) and a["state_encoder.trunk.2.weight"].shape == (6, 50)
+    assert a["state_encoder.mlp_context.4.weight"].shape == (50, 50)
+    assert a["mu_log_std_layer.0.weight"].shape == (64, 100) and a["mu_log_std_layer.6.weight"].shape == (8, 64)
+    path = lrn.save_checkpoint(24)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert "state_encoder.trunk.0.weight" in ck["local_critic"] and "Q_function_2.6.bias" in ck["target_critic"]
+    assert len(ck["critic_optimizer"]["state"]) == 14 + 16 and len(ck["actor_optimizer"]["state"]) == 8
+    before = lrn.core.export_arena()
+    lrn2 = CARELearner(None, names_, str(p), write_mode=False, server=redis_stub.StrictRedis(host=str(tmp_path) + "d"),
+                       seed=5, checkpoint_path=path)
+    assert torch.equal(lrn2.core.export_arena(), before)
+    lrn.memory.stop()
+    lrn2.memory.stop()

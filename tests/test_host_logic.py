@@ -32,11 +32,12 @@ def test_library_exports_every_declared_symbol(lib):
 def test_layout_matches_reference_parameter_counts(lib):
     from distributed_sac_b200.core import CoreConfig, layout
     t, arena, train = layout(CoreConfig())                     # LunarLander: SURVEY 8(a) a11/a12
-    n = lambda pre: sum(r * c for k, (o, r, c, tr, opt) in t.items() if k.startswith(pre))
+    n = lambda pre: sum(r * c for k, (o, r, c, tr, opt, pitch) in t.items() if k.startswith(pre))
     assert n("actor.") == 69124 and n("q1.") == 68865 and n("q1_target.") == 68865
     assert n("actor.") + n("q1.") + n("q2.") + 1 == 206855
     assert t["actor.2.weight"][1:3] == (4, 256) and t["q1.0.weight"][1:3] == (256, 10)
     assert all(off % 4 == 0 for off, *_ in t.values())          # 16-byte aligned tensors (TMA / float4)
+    assert t["q1.0.weight"][5] == 12 and t["actor.0.weight"][5] == 8 and t["q1.1.weight"][5] == 256   # padded first-layer pitch
     assert train < arena and t["log_alpha"][3] == 1 and t["q2_target.2.bias"][3] == 0
     t, arena, train = layout(CoreConfig(state_dim=39, act_dim=4, actor_hidden=[400] * 3, critic_hidden=[400] * 3,
                                         batch=1280, num_tasks=10))
