@@ -201,6 +201,7 @@ struct Launch {
   const GemmProb* probs = nullptr; int G = 0;
   GemmGroup grp;
   const TcProb* tprobs = nullptr;
+  int bn = 64;
   CareTabArgs ctab;
   CareMixArgs cmix;
   CareMixBwdArgs cmixb;
@@ -357,7 +358,7 @@ static bool tc_eligible(const GemmProb& p) {
   return p.M >= 32 && p.N >= 32 && p.K >= 32;
 }
 
-static int make_tc_prob(const GemmProb& p, int rep, TcProb& t) {
+static int make_tc_prob(const GemmProb& p, int rep, TcProb& t, int bn = 64) {
   memset(&t, 0, sizeof(t));
   const float* A = p.A + (long long)rep * p.rsA;
   const float* B = p.B + (long long)rep * p.rsB;
@@ -369,7 +370,7 @@ static int make_tc_prob(const GemmProb& p, int rep, TcProb& t) {
   if (p.mode == GEMM_FWD) {            // A[M][K], B[N][K]: both K-major
     t.a_mn = 0; t.b_mn = 0;
     if (int rc = make_map(&t.tmA, A, p.K, p.M, p.lda, TC_BM)) return rc;
-    if (int rc = make_map(&t.tmB, B, p.K, p.N, p.ldb, TC_BN)) return rc;
+    if (int rc = make_map(&t.tmB, B, p.K, p.N, p.ldb, bn)) return rc;
   } else if (p.mode == GEMM_DGRAD) {   // A = dY[M][K] K-major, B = W[K][N] MN-major
     t.a_mn = 0; t.b_mn = 1;
     if (int rc = make_map(&t.tmA, A, p.K, p.M, p.lda, TC_BM)) return rc;
@@ -404,17 +405,23 @@ static int build_plan(b200sac* h) {
         Launch l;
         int maxM = 0, maxN = 0;
         for (auto& p : tc) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; }
+        // tile width: 128 when the group still fills most of the GPU with 128x128 tiles, else 64
+        long long ctas128 = 0;
+        for (auto& p : tc) ctas128 += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + 127) / 128);
+        int bn = (maxN >= 256 && ctas128 * R >= 96) ? 128 : 64;
+        if (const char* e = getenv("B200SAC_TC_BN")) bn = atoi(e) == 128 ? 128 : 64;
         l.kind = L_GEMM_TC;
-        l.grid = dim3((maxN + TC_BN - 1) / TC_BN, (maxM + TC_BM - 1) / TC_BM, (unsigned)(tc.size() * R));
+        l.bn = bn;
+        l.grid = dim3((maxN + bn - 1) / bn, (maxM + TC_BM - 1) / TC_BM, (unsigned)(tc.size() * R));
         l.block = dim3(TC_THREADS);
-        l.smem = TC_SMEM_BYTES;
+        l.smem = bn == 128 ? TcCfg<128>::kSmemBytes : TcCfg<64>::kSmemBytes;
         l.G = (int)tc.size();
         l.tprobs = (const TcProb*)(uintptr_t)h->h_tprobs.size();
         l.probs = (const GemmProb*)(uintptr_t)h->h_probs.size();   // keep the SIMT descriptors too (labels)
         for (int rep = 0; rep < R; ++rep)
           for (auto& p : tc) {
             TcProb t;
-            if (int rc = make_tc_prob(p, rep, t)) plan_rc = rc;
+            if (int rc = make_tc_prob(p, rep, t, bn)) plan_rc = rc;
             h->h_tprobs.push_back(t);
           }
         for (auto& p : tc) h->h_probs.push_back(p);
@@ -861,7 +868,8 @@ static int build_plan(b200sac* h) {
   if (!h->h_tprobs.empty()) {
     CU(cudaMalloc(&h->d_tprobs, h->h_tprobs.size() * sizeof(TcProb)));
     CU(cudaMemcpy(h->d_tprobs, h->h_tprobs.data(), h->h_tprobs.size() * sizeof(TcProb), cudaMemcpyHostToDevice));
-    CU(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes));
+    CU(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
   }
   CU(cudaMalloc(&h->d_probs, h->h_probs.size() * sizeof(GemmProb)));
   CU(cudaMemcpy(h->d_probs, h->h_probs.data(), h->h_probs.size() * sizeof(GemmProb), cudaMemcpyHostToDevice));
@@ -918,7 +926,8 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
         launch_k(gemm_simt_kernel, l.grid, l.block, 0, st, l.grp);
         break;
       case L_GEMM_TC:
-        launch_k(gemm_tc_kernel, l.grid, l.block, l.smem, st, l.tprobs);
+        if (l.bn == 128) launch_k(gemm_tc_kernel<128>, l.grid, l.block, l.smem, st, l.tprobs);
+        else launch_k(gemm_tc_kernel<64>, l.grid, l.block, l.smem, st, l.tprobs);
         break;
       case L_POLICY: {
         PolicyHeadArgs P = l.pol;
@@ -1417,10 +1426,11 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
     case L_GEMM_TC: {
       const GemmProb& p0 = hp[(size_t)(l.probs - dbase)];
       const GemmProb& pl = hp[(size_t)(l.probs - dbase) + l.G - 1];
-      if (p0.mode == GEMM_FWD) return "gemm_fwd(tcgen05)";
-      if (p0.mode == GEMM_WGRAD && pl.mode == GEMM_DGRAD) return "gemm_wgrad+dgrad(tcgen05)";
-      if (p0.mode == GEMM_WGRAD) return "gemm_wgrad(tcgen05)";
-      return "gemm_dgrad(tcgen05)";
+      const bool w = l.bn == 128;
+      if (p0.mode == GEMM_FWD) return w ? "gemm_fwd(tcgen05 128x128)" : "gemm_fwd(tcgen05)";
+      if (p0.mode == GEMM_WGRAD && pl.mode == GEMM_DGRAD) return w ? "gemm_wgrad+dgrad(tcgen05 128x128)" : "gemm_wgrad+dgrad(tcgen05)";
+      if (p0.mode == GEMM_WGRAD) return w ? "gemm_wgrad(tcgen05 128x128)" : "gemm_wgrad(tcgen05)";
+      return w ? "gemm_dgrad(tcgen05 128x128)" : "gemm_dgrad(tcgen05)";
     }
     case L_GEMM_BIG:
     case L_GEMM_SMALL: {
@@ -1491,14 +1501,18 @@ extern "C" int b200sac_tc_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t 
   p.A = A; p.B = B; p.bias = bias; p.mask = mask; p.C = C; p.C2 = C2;
   p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldmask = ldmask; p.mode = mode; p.relu = relu;
   if (!tc_eligible(p)) return fail(B200SAC_ERR_INVALID, "problem not eligible for the tcgen05 path (need 16-B aligned operands, lda/ldb %% 4 == 0, M,N,K >= 32)");
+  int bn = 64;
+  if (const char* e = getenv("B200SAC_TC_BN")) bn = atoi(e) == 128 ? 128 : 64;
   TcProb t;
-  if (int rc = make_tc_prob(p, 0, t)) return rc;
+  if (int rc = make_tc_prob(p, 0, t, bn)) return rc;
   TcProb* d = nullptr;
   CU(cudaMalloc(&d, sizeof(TcProb)));
   CU(cudaMemcpy(d, &t, sizeof(TcProb), cudaMemcpyHostToDevice));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM, 1);
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(d);
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
+  dim3 grid((N + bn - 1) / bn, (M + TC_BM - 1) / TC_BM, 1);
+  if (bn == 128) gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::kSmemBytes, (cudaStream_t)stream>>>(d);
+  else gemm_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::kSmemBytes, (cudaStream_t)stream>>>(d);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(d);
@@ -1517,15 +1531,21 @@ extern "C" int b200sac_tc_gemm_timeline(int32_t mode, int32_t M, int32_t N, int3
   memset(&p, 0, sizeof(p));
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.mode = mode;
   p.lda = mode == GEMM_WGRAD ? M : K; p.ldb = mode == GEMM_FWD ? K : N; p.ldc = N;
+  int bn = 64;
+  if (const char* e = getenv("B200SAC_TC_BN")) bn = atoi(e) == 128 ? 128 : 64;
   TcProb t;
-  if (int rc = make_tc_prob(p, 0, t)) return rc;
+  if (int rc = make_tc_prob(p, 0, t, bn)) return rc;
   t.dbg = dbg;
   TcProb* d = nullptr;
   CU(cudaMalloc(&d, sizeof(TcProb)));
   CU(cudaMemcpy(d, &t, sizeof(TcProb), cudaMemcpyHostToDevice));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM, 1);
-  for (int it = 0; it < 3; ++it) gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES>>>(d);
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
+  dim3 grid((N + bn - 1) / bn, (M + TC_BM - 1) / TC_BM, 1);
+  for (int it = 0; it < 3; ++it) {
+    if (bn == 128) gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::kSmemBytes>>>(d);
+    else gemm_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::kSmemBytes>>>(d);
+  }
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out96, dbg, 96 * 8, cudaMemcpyDeviceToHost));
   cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(dbg); cudaFree(d);

@@ -33,16 +33,26 @@
 
 namespace bsac {
 
-constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 32, TC_STAGES = 4;
+constexpr int TC_BM = 128, TC_BK = 32;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                  // 16 KiB
-constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;                  //  8 KiB
-constexpr int TC_STAGE_BYTES = 2 * (TC_A_BYTES + TC_B_BYTES);  // hi + lo of both operands = 48 KiB
 constexpr int TC_THREADS = 192;
 constexpr int TC_SPLIT_THREADS = 128;
-constexpr int TC_NMAIN = 6;         // A_hi*B_hi is spread over up to 6 accumulators (contiguous K ranges)
-constexpr int TC_TMEM_COLS = 512;   // 6 main + 1 cross-term accumulator x 64 fp32 columns = 448 -> 512 (power of two)
+constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_BSUM_BYTES = 16 * TC_BM * 4;                  // [16 partials][128 m] fp32
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_BSUM_BYTES + 256 + 1024;   // + barriers + align slack
+
+// Two tile widths: 128x64 (many CTAs: latency-critical small problems) and 128x128 (the 400-wide shapes:
+// an N=128 MMA amortises the A-operand shared-memory reads over twice the columns).
+template <int BN>
+struct TcCfg {
+  static constexpr int kBN = BN;
+  static constexpr int kBBytes = BN * TC_BK * 4;                           // 8 / 16 KiB
+  static constexpr int kStageBytes = 2 * (TC_A_BYTES + kBBytes);           // hi + lo of both operands: 48 / 64 KiB
+  static constexpr int kStages = BN == 64 ? 4 : 3;
+  static constexpr int kNMain = BN == 64 ? 6 : 3;                          // (kNMain + 1) * BN <= 512 TMEM columns
+  static constexpr int kSmemBytes = kStages * kStageBytes + TC_BSUM_BYTES + 256 + 1024;   // + barriers + align slack
+};
+constexpr int TC_BN = 64;            // default tile width (descriptor-eligibility bounds, tests)
+constexpr int TC_SMEM_BYTES = TcCfg<64>::kSmemBytes;
 
 struct alignas(128) TcProb {
   CUtensorMap tmA;
@@ -145,19 +155,23 @@ B200_D uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_by
   return d;
 }
 
-// number of main accumulators for nk k-chunks: ~2 chunks (8 MMAs) each, at most TC_NMAIN
-B200_D int tc_nmain(int nk) {
+// number of main accumulators for nk k-chunks: ~2 chunks (8 MMAs) each, at most `cap`
+B200_D int tc_nmain(int nk, int cap) {
   int n = nk / 2;
-  return n < 1 ? 1 : (n > TC_NMAIN ? TC_NMAIN : n);
+  return n < 1 ? 1 : (n > cap ? cap : n);
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
-B200_D uint32_t tc_instr_desc(int a_mn, int b_mn) {
+B200_D uint32_t tc_instr_desc(int a_mn, int b_mn, int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+         ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __restrict__ probs) {
+  using Cfg = TcCfg<BN>;
+  constexpr int TC_BN = BN, TC_B_BYTES = Cfg::kBBytes, TC_STAGE_BYTES = Cfg::kStageBytes, TC_STAGES = Cfg::kStages,
+                TC_NMAIN = Cfg::kNMain;
   kstamp();
   extern __shared__ uint8_t smem_raw[];
   const TcProb* P = probs + blockIdx.z;
@@ -232,8 +246,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      const uint32_t idesc = tc_instr_desc(a_mn, b_mn);
-      const int nmain = tc_nmain(nk);                    // chunk kc accumulates into main[(kc * nmain) / nk]
+      const uint32_t idesc = tc_instr_desc(a_mn, b_mn, TC_BN);
+      const int nmain = tc_nmain(nk, TC_NMAIN);          // chunk kc accumulates into main[(kc * nmain) / nk]
       for (int kc = 0; kc < nk; ++kc) {
         const int s = kc % TC_STAGES;
         const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
@@ -247,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         const uint64_t dB0 = tc_smem_desc(st + 2 * TC_A_BYTES, b_mn ? 4096u : 16u, b_mn ? 512u : 1024u, b_mn ? 1u : 2u);
         const uint64_t stepA = a_mn ? (1024u >> 4) : (32u >> 4), stepB = b_mn ? (1024u >> 4) : (32u >> 4);
         const int mi = (kc * nmain) / nk;
-        const uint32_t d_main = tmem_base + 64u * (uint32_t)mi, d_cross = tmem_base + 64u * TC_NMAIN;
+        const uint32_t d_main = tmem_base + (uint32_t)(TC_BN * mi), d_cross = tmem_base + (uint32_t)(TC_BN * TC_NMAIN);
         const bool new_main = (kc == 0) || (((kc - 1) * nmain) / nk != mi);
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
@@ -345,7 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
     const float* __restrict__ mask = P->mask;
     float* __restrict__ Cout = P->C;
     const int ldmask = P->ldmask;
-    const int nmain = tc_nmain(nk);
+    const int nmain = tc_nmain(nk, TC_NMAIN);
     // All MMAs have completed (accum barrier), so the pipeline stages are free: each warp transposes its
     // 32x32 block through a padded smem scratch so that global stores / mask loads are row-contiguous.
     float* scratch = reinterpret_cast<float*>(gbase) + (warp - 2) * (32 * 33);
@@ -356,11 +370,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
       tc_ld32(lane_addr, v);                                  // main[0]
       if (t == 0 && c == 0) TC_STAMP(85);
       for (int mi = 1; mi < nmain; ++mi) {
-        tc_ld32(lane_addr + 64u * (uint32_t)mi, w);
+        tc_ld32(lane_addr + (uint32_t)(TC_BN * mi), w);
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
       }
-      tc_ld32(lane_addr + 64u * TC_NMAIN, w);                 // cross terms
+      tc_ld32(lane_addr + (uint32_t)(TC_BN * TC_NMAIN), w);   // cross terms
       if (t == 0 && c == 0) TC_STAMP(86);
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) scratch[lane * 33 + jj] = __uint_as_float(v[jj]) + __uint_as_float(w[jj]);
