@@ -191,7 +191,7 @@ struct Buf {           // [R][n] fp32 (or int32) slab slice
   long long rs = 0;    // replica stride in floats
 };
 
-enum LaunchKind { L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
+enum LaunchKind { L_POLICY_DOUT, L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
 
 struct Launch {
   LaunchKind kind;
@@ -202,6 +202,7 @@ struct Launch {
   GemmGroup grp;
   const TcProb* tprobs = nullptr;
   int bn = 64;
+  PolicyDoutArgs pdo;
   CareTabArgs ctab;
   CareMixArgs cmix;
   CareMixBwdArgs cmixb;
@@ -268,6 +269,8 @@ struct b200sac {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   int stage_slot = 0;
   bool stage_used[2] = {false, false};
+  int prefetch_slot = -1;         // host-ring step_sampled: minibatch already drawn, gathered and in flight (H2D)
+  b200sac_replay* prefetch_rb = nullptr;
   float* loss_h = nullptr;        // mapped pinned loss ring [kLossSlots][R][4], written by the tail kernels
   float* loss_h_dev = nullptr;    // its device-side address
 };
@@ -650,7 +653,24 @@ static int build_plan(b200sac* h) {
       P.h = hb.p; P.rsHnet = (long long)B * Hc; P.rsHrep = hb.rs; P.ldh = Hc;
       P.dh = h->dhQ[Lc - 1].p; P.rsDhNet = (long long)B * Hc; P.rsDhRep = h->dhQ[Lc - 1].rs; P.lddh = Hc;
     } else {
-      P.NO = 2 * A; P.Kdim = Ha; P.nets = 1; P.policy_mode = 1;
+      const bool split = (long long)B * A > 2048;      // large batch: one tiny kernel computes d(mu|log_std) for all rows
+      if (split) {
+        Launch pl;
+        pl.kind = L_POLICY_DOUT;
+        PolicyDoutArgs& Q = pl.pdo;
+        memset(&Q, 0, sizeof(Q));
+        Q.dx = h->dxP.p; Q.rsDxNet = (long long)B * h->K.ldx; Q.rsDxRep = h->dxP.rs; Q.lddx = h->K.ldx;
+        Q.psave = h->psave.p + (long long)B * A * kSaveW; Q.rsSave = h->psave.rs;
+        Q.tid = (const int*)h->tid.p; Q.rsR = h->r.rs;
+        Q.log_alpha = W(L.off_alpha); Q.rsP = rsP;
+        Q.dout = h->dout_dbg.p; Q.dact = h->dact_dbg.p; Q.rsDout = h->dout_dbg.rs;
+        Q.M = B;
+        pl.grid = dim3((B * A + 255) / 256, R);
+        pl.block = dim3(256);
+        h->plan.push_back(pl);
+      }
+      P.NO = 2 * A; P.Kdim = Ha; P.nets = 1; P.policy_mode = split ? 0 : 1;
+      if (split) { P.dout = h->dout_dbg.p; P.rsDoutNet = 0; P.rsDoutRep = h->dout_dbg.rs; }
       const LayerOff& lo = L.actor[La];
       P.W[0] = W(lo.w); P.dW[0] = Gp(lo.w); P.db[0] = Gp(lo.b);
       P.h = h->hA[La - 1].p + (long long)B * Ha; P.rsHrep = h->hA[La - 1].rs; P.ldh = Ha;   // rows B..2B-1 (= s half)
@@ -906,6 +926,9 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
     Launch& l = h->plan[i];
     if (evs) CU(cudaEventRecord(evs[i], st));
     switch (l.kind) {
+      case L_POLICY_DOUT:
+        launch_k(policy_dout_kernel, l.grid, l.block, 0, st, h->K, l.pdo);
+        break;
       case L_CARE_TAB:
         launch_k(care_tables_kernel, l.grid, l.block, 0, st, l.ctab);
         break;
@@ -1376,6 +1399,7 @@ static int staged_step(b200sac* h, cudaStream_t st, int slot, bool with_eps) {
 
 static int acquire_slot(b200sac* h, int* slot) {
   int s = h->stage_slot;
+  if (s == h->prefetch_slot) h->prefetch_slot = -1;          // the slot is being reused: its prefetched batch is void
   h->stage_slot ^= 1;
   if (h->stage_used[s]) {
     CU(cudaEventSynchronize(h->ev_consumed[s]));          // host may overwrite the pinned slot
@@ -1441,6 +1465,7 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
       if (p0.mode == GEMM_WGRAD) return "gemm_wgrad(ffma)";
       return "gemm_dgrad(ffma)";
     }
+    case L_POLICY_DOUT: return "policy_dout";
     case L_CARE_TAB: return "care_tables";
     case L_CARE_MIX: return "care_mix";
     case L_CARE_MIXBWD: return "care_mix_bwd";
@@ -1449,7 +1474,7 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
     case L_POLICY: return "policy_head";
     case L_CHEADS: return "critic_heads";
     case L_AQHEADS: return "actor_q_heads";
-    case L_HEADBWD: return l.hb.policy_mode ? "head_bwd(policy)" : "head_bwd(q)";
+    case L_HEADBWD: return (l.hb.policy_mode || l.hb.NO > 1) ? "head_bwd(policy)" : "head_bwd(q)";
     case L_ADAM: return l.ad.which == 0 ? "adam_critic+polyak" : "adam_actor+alpha";
   }
   return "?";
@@ -1678,6 +1703,7 @@ extern "C" int b200sac_replay_destroy(b200sac_replay_t* rb) {
   if (!rb) return 0;
   cudaSetDevice(rb->h->device);
   // graphs that captured this ring's pointers must go
+  if (rb->h->prefetch_rb == rb) { rb->h->prefetch_slot = -1; rb->h->prefetch_rb = nullptr; }
   for (auto it = rb->h->graphs.begin(); it != rb->h->graphs.end();) {
     if (it->first.p[8] == rb) { cudaGraphExecDestroy(it->second); it = rb->h->graphs.erase(it); }
     else ++it;
@@ -1825,10 +1851,14 @@ extern "C" int b200sac_step_sampled(b200sac_t* h, b200sac_replay_t* rb, int32_t 
       if (int rc = launch_step(h, st, 2, p, 1, rb)) return rc;
     return sb.end();
   }
-  // pinned-host ring: draw + gather on the host into the pinned slot, H2D on the side stream
+  // pinned-host ring: draw + gather on the host into the pinned slot, H2D on the side stream.  The NEXT
+  // minibatch is prepared right after the current step has been launched, so host sampling, the gather and
+  // the copy overlap the GPU step (the reference samples at the start of update(); here the draw for step k+1
+  // happens while step k runs -- the same RNG sequence, the ring contents as of that moment).
   std::vector<long long> idx;
   const int rs = h->row_stride;
-  for (int i = 0; i < n_steps; ++i) {
+  const size_t rows_bytes = (size_t)h->R * B * rs * sizeof(float);
+  auto prepare = [&](int* slot_out) -> int {
     int slot;
     if (int rc = acquire_slot(h, &slot)) return rc;
     {
@@ -1840,7 +1870,26 @@ extern "C" int b200sac_step_sampled(b200sac_t* h, b200sac_replay_t* rb, int32_t 
         for (int j = 0; j < B; ++j) memcpy(dst + (size_t)j * rs, base + (size_t)idx[j] * rs, rs * sizeof(float));
       }
     }
-    if (int rc = staged_step(h, st, slot, false)) return rc;
+    CU(cudaMemcpyAsync(h->stage_d[slot], h->stage_h[slot], rows_bytes, cudaMemcpyHostToDevice, h->side));
+    CU(cudaEventRecord(h->ev_copied[slot], h->side));
+    *slot_out = slot;
+    return 0;
+  };
+  if (h->prefetch_slot >= 0 && h->prefetch_rb != rb) h->prefetch_slot = -1;     // belongs to another ring: drop it
+  for (int i = 0; i < n_steps; ++i) {
+    int slot = h->prefetch_slot;
+    if (slot < 0)
+      if (int rc = prepare(&slot)) return rc;
+    h->prefetch_slot = -1;
+    CU(cudaStreamWaitEvent(st, h->ev_copied[slot], 0));
+    const void* p[2] = {h->stage_d[slot], nullptr};
+    if (int rc = launch_step(h, st, 1, p, 2, nullptr)) return rc;
+    CU(cudaEventRecord(h->ev_consumed[slot], st));
+    h->stage_used[slot] = true;
+    int next;
+    if (int rc = prepare(&next)) return rc;      // overlaps the step just launched
+    h->prefetch_slot = next;
+    h->prefetch_rb = rb;
   }
   return sb.end();
 }

@@ -458,6 +458,49 @@ struct HeadBwdArgs {
   float* dact_dbg;
 };
 
+// d(loss)/d(mu | log_std) of one (row, action) from the values the policy head saved: the closed-form backward of
+// LL/model.py:50-60 in the reference's evaluation order (oracle/sac_manual.py).
+B200_D void policy_dout_point(const StepConst& K, const float* __restrict__ sv, float da, float alpha, float& dmu, float& dls) {
+  const float k = K.action_scale;
+  const float std = sv[0], diff = sv[1], t = sv[2], act = sv[3], jac = sv[4], eps = sv[5], mask = sv[6];
+  const float glp = K.c_loss * alpha;
+  const float var = std * std;
+  const float d_act = da + glp * (2.f * (act / k) / k) * k / jac;
+  const float g_u_t = d_act * k * (1.f - t * t);
+  const float g_u = g_u_t + glp * (-(diff) / var);
+  dmu = g_u + glp * (diff / var);
+  const float dstd = g_u * eps + glp * ((diff * diff) / (var * std) - 1.f / std);
+  dls = dstd * std * mask;
+}
+
+struct PolicyDoutArgs {
+  const float* dx; long long rsDxNet, rsDxRep; int lddx;
+  const float* psave; long long rsSave;
+  const int* tid; long long rsR;
+  const float* log_alpha; long long rsP;
+  float* dout; float* dact; long long rsDout;     // [M][2A], [M][A]
+  int M;
+};
+
+// Large batches: compute the policy-head output gradient once (instead of in every head_bwd CTA).
+__global__ void __launch_bounds__(256) policy_dout_kernel(StepConst K, PolicyDoutArgs P) {
+  kstamp();
+  const int rep = blockIdx.y, A = K.act;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= P.M * A) return;
+  const int m = e / A, j = e % A;
+  const float* __restrict__ sv = P.psave + rep * P.rsSave + ((long long)m * A + j) * kSaveW;
+  const float* __restrict__ dx0 = P.dx + rep * P.rsDxRep + (long long)m * P.lddx + K.in_w + j;
+  const float da = dx0[0] + dx0[P.rsDxNet];
+  const float alpha = (float)exp((double)(P.log_alpha + rep * P.rsP)[(P.tid + rep * P.rsR)[m]]);
+  float dmu, dls;
+  policy_dout_point(K, sv, da, alpha, dmu, dls);
+  float* o = P.dout + rep * P.rsDout + (long long)m * 2 * A;
+  o[j] = dmu;
+  o[A + j] = dls;
+  (P.dact + rep * P.rsDout)[(long long)m * A + j] = da;
+}
+
 constexpr int kHbCols = 8;     // hidden columns per CTA
 constexpr int kHbRows = 32;    // row groups per CTA (256 threads = 8 cols x 32 row groups)
 
@@ -472,23 +515,18 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
 
   if (P.policy_mode) {
     const int A = K.act;
-    const float k = K.action_scale;
+    __shared__ float s_alpha[64];                       // exp(log_alpha[t]) once per task, not per (row, action)
+    const int Teff = K.T > 0 ? K.T : 1;
+    if (tid < Teff) s_alpha[tid] = (float)exp((double)(P.log_alpha + rep * P.rsP)[tid]);
+    __syncthreads();
     for (int e = tid; e < M * A; e += 256) {
       const int m = e / A, j = e % A;
       const float* __restrict__ sv = P.psave + rep * P.rsSave + ((long long)m * A + j) * kSaveW;
-      const float std = sv[0], diff = sv[1], t = sv[2], act = sv[3], jac = sv[4], eps = sv[5], mask = sv[6];
       const float* __restrict__ dx0 = P.dx + rep * P.rsDxRep + (long long)m * P.lddx + K.in_w + j;
       const float da = dx0[0] + dx0[P.rsDxNet];
       const int tk = (P.tid + rep * P.rsR)[m];
-      const float alpha = (float)exp((double)(P.log_alpha + rep * P.rsP)[tk]);
-      const float glp = K.c_loss * alpha;
-      const float var = std * std;
-      const float d_act = da + glp * (2.f * (act / k) / k) * k / jac;
-      const float g_u_t = d_act * k * (1.f - t * t);
-      const float g_u = g_u_t + glp * (-(diff) / var);
-      const float dmu = g_u + glp * (diff / var);
-      const float dstd = g_u * eps + glp * ((diff * diff) / (var * std) - 1.f / std);
-      const float dls = dstd * std * mask;
+      float dmu, dls;
+      policy_dout_point(K, sv, da, s_alpha[tk], dmu, dls);
       sd[m * NO + j] = dmu;
       sd[m * NO + A + j] = dls;
       if (P.dout_dbg && blockIdx.x == 0) {
@@ -700,19 +738,28 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
     }
     const int Teff = K.T > 0 ? K.T : 1;
     float* la = P.log_alpha + rep * P.rsP;
-    float aloss = 0.f;
-    for (int t = 0; t < Teff; ++t) {
-      float gs = 0.f;
-      for (int i = tid; i < B; i += 256) {
-        if ((P.tid + rep * P.rsR)[i] == t) gs += (P.logp_cur + rep * P.rsLogp)[i] + K.hbar;
+    __shared__ float s_gs[64];
+    {   // per-task sums of (logp + Hbar): one warp per task, lanes stride the rows, shuffle tree -> fixed order
+      const int warp = tid / 32, lane = tid % 32;
+      const int* __restrict__ tv = P.tid + rep * P.rsR;
+      const float* __restrict__ lp = P.logp_cur + rep * P.rsLogp;
+      for (int t = warp; t < Teff; t += 8) {
+        float gs = 0.f;
+        for (int i = lane; i < B; i += 32)
+          if (tv[i] == t) gs += lp[i] + K.hbar;
+        gs = warp_sum(gs);
+        if (lane == 0) s_gs[t] = gs;
       }
-      gs = block_sum(gs);
-      if (tid == 0) {
-        const float grad = -gs * K.inv_B;            // d/dlog_alpha[t] of -mean(log_alpha_i (logp_i + Hbar))
-        aloss += la[t] * grad;                       // loss value = sum_t log_alpha[t] * grad[t]
+    }
+    __syncthreads();
+    float aloss = 0.f;
+    if (tid == 0) {
+      float ss, bc;
+      adam_scalars(K.lr_alpha, P.cnt[rep].b1p[2], P.cnt[rep].b2p[2], ss, bc);
+      for (int t = 0; t < Teff; ++t) {
+        const float grad = -s_gs[t] * K.inv_B;         // d/dlog_alpha[t] of -mean(log_alpha_i (logp_i + Hbar))
+        aloss += la[t] * grad;                         // loss value = sum_t log_alpha[t] * grad[t]
         (P.g_alpha + rep * P.rsM)[t] = grad;
-        float ss, bc;
-        adam_scalars(K.lr_alpha, P.cnt[rep].b1p[2], P.cnt[rep].b2p[2], ss, bc);
         float pi = la[t], mi = (P.m_alpha + rep * P.rsM)[t], vi = (P.v_alpha + rep * P.rsM)[t];
         adam_one(pi, mi, vi, grad, (float)(1.0 - K.beta1), (float)K.beta2, (float)(1.0 - K.beta2), ss, bc,
                  (float)K.adam_eps);
