@@ -24,8 +24,8 @@ class Cfg(C.Structure):
         ("log_alpha_init", C.c_double),
         ("num_encoders", C.c_int32), ("n_mix_hidden", C.c_int32), ("mix_hidden", C.c_int32 * MAX_HIDDEN),
         ("mix_out", C.c_int32), ("ctx_in", C.c_int32), ("n_ctx_hidden", C.c_int32),
-        ("ctx_hidden", C.c_int32 * MAX_HIDDEN), ("ctx_out", C.c_int32), ("reserved1", C.c_int32),
-        ("tau_se", C.c_double),
+        ("ctx_hidden", C.c_int32 * MAX_HIDDEN), ("ctx_out", C.c_int32), ("emb_dim", C.c_int32),
+        ("tau_se", C.c_double), ("lr_ctx", C.c_double),
     ]
 
 

@@ -45,6 +45,9 @@ class CoreConfig:
     ctx_hidden: List[int] = field(default_factory=lambda: [50, 50])
     ctx_out: int = 50
     tau_se: float = 0.05
+    care_original: bool = False          # CARE(O): trainable context encoder (use_modified_care: false)
+    emb_dim: int = 50
+    lr_ctx: float = 3e-4
 
     @property
     def obs_dim(self):
@@ -67,8 +70,9 @@ class CoreConfig:
         c.action_scale = self.action_scale
         c.beta1, c.beta2, c.adam_eps = self.beta1, self.beta2, self.adam_eps
         c.log_alpha_init = self.log_alpha_init
-        c.care = int(self.care)
+        c.care = (2 if self.care_original else 1) if self.care else 0
         if self.care:
+            c.emb_dim, c.lr_ctx = self.emb_dim, self.lr_ctx
             c.num_encoders, c.mix_out, c.ctx_in, c.ctx_out = self.num_encoders, self.mix_out, self.ctx_in, self.ctx_out
             c.n_mix_hidden, c.n_ctx_hidden = len(self.mix_hidden), len(self.ctx_hidden)
             for i, v in enumerate(self.mix_hidden):
@@ -190,12 +194,15 @@ class SacCore:
         self.import_arena(flat, which, replica)
 
     def get_steps(self, replica=0):
-        s = (C.c_int64 * 3)()
+        s = (C.c_int64 * 4)()
         _lib.check(self.lib.b200sac_get_steps(self._h, replica, s))
-        return tuple(int(x) for x in s)     # (critic, actor, alpha)
+        n = 4 if (self.cfg.care and self.cfg.care_original) else 3
+        return tuple(int(x) for x in s)[:n]     # (critic, actor, alpha[, context encoder])
 
     def set_steps(self, steps, replica=0):
-        s = (C.c_int64 * 3)(*[int(x) for x in steps])
+        cur = list(self.get_steps(replica)) + [0]
+        vals = [int(x) for x in steps] + cur[len(steps):4]
+        s = (C.c_int64 * 4)(*vals[:4])
         _lib.check(self.lib.b200sac_set_steps(self._h, replica, s))
 
     def soft_update(self, tau: float):

@@ -57,7 +57,8 @@ struct Layout {
   std::vector<LayerOff> actor, q[2], qt[2];
   // CARE: the critic's state encoder (the target's sits at + target_delta with the same relative layout)
   std::vector<LayerOff> mix, trunk, ctx;      // mix: w = [K][out][in], b = [K][out]
-  int64_t cse_begin = 0, off_emb = 0;
+  std::vector<LayerOff> cenc;                 // CARE(O): the trainable context encoder (header + mlp), no target copy
+  int64_t cse_begin = 0, off_emb = 0, cenc_begin = 0, cenc_n = 0;
   int in_w = 0;                               // width of the state part of the MLP inputs
   int64_t off_alpha = 0, arena = 0, trainable = 0;
   int64_t actor_begin = 0, actor_n = 0, critic_begin = 0, critic_n = 0, target_delta = 0;
@@ -82,6 +83,13 @@ static int check_cfg(const b200sac_cfg* c) {
     return fail(B200SAC_ERR_INVALID, "batch must be a multiple of num_tasks");
   if (c->replicas < 1 || c->replicas > 4096) return fail(B200SAC_ERR_INVALID, "1 <= replicas <= 4096 required");
   if (c->precision != 0 && c->precision != 1) return fail(B200SAC_ERR_INVALID, "precision must be 0 (fp32 FFMA) or 1 (3xTF32 tcgen05)");
+  if (c->care != 0 && c->care != 1 && c->care != 2) return fail(B200SAC_ERR_INVALID, "care must be 0, 1 (CARE(M)) or 2 (CARE(O))");
+  if (c->care == 2) {
+    if (c->emb_dim < 1 || c->emb_dim > 256) return fail(B200SAC_ERR_INVALID, "1 <= emb_dim <= 256 required for CARE(O)");
+    if (c->emb_dim != c->ctx_out)
+      return fail(B200SAC_ERR_INVALID, "CARE(O): the attention trunk reads the context code, so embedding_dim_contextEnc (%d) must equal output_dim_contextEnc (%d) (state_encoder.py:120-122)", c->emb_dim, c->ctx_out);
+    if (c->n_ctx_hidden + 3 > kCareMaxLayers) return fail(B200SAC_ERR_INVALID, "too many context-encoder layers");
+  }
   if (c->care) {
     if (c->num_tasks < 1) return fail(B200SAC_ERR_INVALID, "CARE needs num_tasks >= 1 (one-hot task id in the observation)");
     if (c->num_encoders < 1 || c->num_encoders > 32) return fail(B200SAC_ERR_INVALID, "1 <= num_encoders <= 32 required");
@@ -146,9 +154,12 @@ static void build_layout(const b200sac_cfg* c, Layout& L) {
     }
     char pfx[24];
     snprintf(pfx, sizeof(pfx), "%s.trunk", pre);
-    add_net(pfx, record ? &L.trunk : nullptr, c->ctx_in, c->mix_hidden, c->n_mix_hidden, c->num_encoders, tr, opt);
-    snprintf(pfx, sizeof(pfx), "%s.ctx", pre);
-    add_net(pfx, record ? &L.ctx : nullptr, c->ctx_in, c->ctx_hidden, c->n_ctx_hidden, c->ctx_out, tr, opt);
+    add_net(pfx, record ? &L.trunk : nullptr, c->care == 2 ? c->emb_dim : c->ctx_in, c->mix_hidden, c->n_mix_hidden,
+            c->num_encoders, tr, opt);
+    if (c->care == 1) {          // CARE(M): mlp_context lives inside every state encoder
+      snprintf(pfx, sizeof(pfx), "%s.ctx", pre);
+      add_net(pfx, record ? &L.ctx : nullptr, c->ctx_in, c->ctx_hidden, c->n_ctx_hidden, c->ctx_out, tr, opt);
+    }
   };
   L.actor_begin = off;
   add_net("actor", &L.actor, L.in_w, c->actor_hidden, c->n_actor_hidden, 2 * c->act_dim, 1, 1, true);
@@ -160,6 +171,16 @@ static void build_layout(const b200sac_cfg* c, Layout& L) {
   if (c->care) add_encoder("cse", true, 1, 0);
   L.critic_n = off - L.critic_begin;
   L.off_alpha = add("log_alpha", c->num_tasks > 0 ? c->num_tasks : 1, 1, 1, 2);
+  if (c->care == 2) {            // context encoder: Linear(ctx_in, 2e) ReLU Linear(2e, e) ReLU + mlp e -> ctx_hidden -> ctx_out
+    L.cenc_begin = off;
+    int hid[B200SAC_MAX_HIDDEN + 2];
+    int nh = 0;
+    hid[nh++] = 2 * c->emb_dim;
+    hid[nh++] = c->emb_dim;
+    for (int i = 0; i < c->n_ctx_hidden; ++i) hid[nh++] = c->ctx_hidden[i];
+    add_net("cenc", &L.cenc, c->ctx_in, hid, nh, c->ctx_out, 1, 3);
+    L.cenc_n = off - L.cenc_begin;
+  }
   L.trainable = off;
   int64_t tb = off;
   add_net("q1_target", &L.qt[0], L.in_w + c->act_dim, c->critic_hidden, c->n_critic_hidden, 1, 0, -1, true);
@@ -469,6 +490,7 @@ static int build_plan(b200sac* h) {
     P.params = h->params; P.rsP = rsP; P.emb_off = L.off_emb;
     P.trunk = h->care_trunk; P.ctx = h->care_ctx;
     P.T = c.num_tasks; P.K = Kenc; P.row_w = h->care_row_w; P.off_att = h->care_off_att;
+    P.original = c.care == 2 ? 1 : 0;
     for (size_t i = 0; i < insts.size(); ++i) {
       P.inst_delta[i] = insts[i] == 1 ? L.target_delta : 0;
       P.tab[i] = h->careTab[insts[i]].p;
@@ -784,6 +806,7 @@ static int build_plan(b200sac* h) {
       Q.grads = h->grads; Q.rsG = rsG;
       Q.trunk = h->care_trunk; Q.ctx = h->care_ctx;
       Q.T = c.num_tasks; Q.K = Kenc; Q.co = c.ctx_out;
+      Q.original = c.care == 2 ? 1 : 0; Q.off_ctx = h->care_off_ctx;
       size_t fl = 0;
       for (int j = 0; j < Q.trunk.n; ++j) fl += (size_t)c.num_tasks * Q.trunk.dims[j + 1];
       for (int j = 0; j < Q.ctx.n; ++j) fl += (size_t)c.num_tasks * Q.ctx.dims[j + 1];
@@ -798,17 +821,17 @@ static int build_plan(b200sac* h) {
     l.kind = L_ADAM;
     AdamArgs& P = l.ad;
     memset(&P, 0, sizeof(P));
-    const int64_t beg = which == 0 ? L.critic_begin : L.actor_begin;
-    const int64_t n = which == 0 ? L.critic_n : L.actor_n;
+    const int64_t beg = which == 0 ? L.critic_begin : (which == 1 ? L.actor_begin : L.cenc_begin);
+    const int64_t n = which == 0 ? L.critic_n : (which == 1 ? L.actor_n : L.cenc_n);
     P.p = h->params + beg; P.m = h->adam_m + beg; P.v = h->adam_v + beg; P.g = h->grads + beg;
     P.rsP = rsP; P.rsM = rsG; P.n = n;
     P.target_delta = which == 0 ? L.target_delta : 0;
     P.tau2_begin = (which == 0 && c.care) ? (L.cse_begin - L.critic_begin) : (long long)1 << 60;
     P.tau2 = (float)c.tau_se; P.one_minus_tau2 = (float)(1.0 - c.tau_se);
-    P.which = which;
-    P.lr = which == 0 ? c.lr_critic : c.lr_actor;
+    P.which = which == 2 ? 4 : which;                    // counter slot: 0 critic, 1 actor, 4 context encoder
+    P.lr = which == 0 ? c.lr_critic : (which == 1 ? c.lr_actor : c.lr_ctx);
     P.cnt = h->cnt;
-    P.tail = which == 0 ? TAIL_CRITIC_LOSS : TAIL_ALPHA_AND_LOSSES;
+    P.tail = which == 0 ? TAIL_CRITIC_LOSS : (which == 1 ? TAIL_ALPHA_AND_LOSSES : TAIL_NONE);
     P.lq = h->lq.p; P.la = h->la.p; P.rsY = h->y.rs;
     P.logp_cur = h->logp.p + B; P.logstd_sum = h->logstd.p + B; P.rsLogp = h->logp.rs;
     P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
@@ -818,7 +841,7 @@ static int build_plan(b200sac* h) {
     int nb = (int)((n + 256 * 4 - 1) / (256 * 4));
     if (nb < 1) nb = 1;
     if (nb > 592) nb = 592;
-    l.grid = dim3(nb + 1, R);
+    l.grid = dim3(nb + (P.tail != TAIL_NONE ? 1 : 0), R);
     l.block = dim3(256);
     h->plan.push_back(l);
   };
@@ -882,6 +905,7 @@ static int build_plan(b200sac* h) {
     gemm_launch(ps);
   }
   adam(1);
+  if (c.care == 2) adam(2);        // update(): context_encoder_optimizer.step() (learner.py:399), gradients from the critic loss
 
   if (plan_rc) return plan_rc;
   // upload problem tables and rebase
@@ -1043,7 +1067,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   CUH(cudaMemset(h->grads, 0, sizeof(float) * L.trainable * R));
   {
     std::vector<Counters> c0((size_t)R);
-    for (auto& c : c0) { memset(&c, 0, sizeof(c)); for (int i = 0; i < 3; ++i) c.b1p[i] = c.b2p[i] = 1.0; }
+    for (auto& c : c0) { memset(&c, 0, sizeof(c)); for (int i = 0; i < 5; ++i) c.b1p[i] = c.b2p[i] = 1.0; }
     CUH(cudaMemcpy(h->cnt, c0.data(), sizeof(Counters) * R, cudaMemcpyHostToDevice));
   }
   CUH(cudaMemset(h->losses, 0, sizeof(float) * kLossSlots * R * 4));
@@ -1096,11 +1120,13 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
     CareNet& tr = h->care_trunk;
     CareNet& cx = h->care_ctx;
     memset(&tr, 0, sizeof(tr)); memset(&cx, 0, sizeof(cx));
-    tr.n = (int)L.trunk.size(); cx.n = (int)L.ctx.size();
-    tr.dims[0] = cx.dims[0] = cfg->ctx_in;
+    const std::vector<LayerOff>& cxl = cfg->care == 2 ? L.cenc : L.ctx;      // CARE(O): the context net is the shared encoder
+    tr.n = (int)L.trunk.size(); cx.n = (int)cxl.size();
+    tr.dims[0] = cfg->care == 2 ? cfg->emb_dim : cfg->ctx_in;
+    cx.dims[0] = cfg->ctx_in;
     for (int j = 0; j < tr.n; ++j) { tr.dims[j + 1] = L.trunk[j].out; tr.w[j] = L.trunk[j].w; tr.b[j] = L.trunk[j].b; tr.act_off[j] = off; off += L.trunk[j].out; }
     h->care_off_att = off; off += Kenc;
-    for (int j = 0; j < cx.n; ++j) { cx.dims[j + 1] = L.ctx[j].out; cx.w[j] = L.ctx[j].w; cx.b[j] = L.ctx[j].b; cx.act_off[j] = off; off += L.ctx[j].out; }
+    for (int j = 0; j < cx.n; ++j) { cx.dims[j + 1] = cxl[j].out; cx.w[j] = cxl[j].w; cx.b[j] = cxl[j].b; cx.act_off[j] = off; off += cxl[j].out; }
     h->care_off_ctx = cx.act_off[cx.n - 1];
     h->care_row_w = off;
     for (int i = 0; i < 3; ++i) h->careTab[i] = carve(cur, (size_t)T * off, R);
@@ -1157,7 +1183,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
         randn_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, (long long)cfg->num_encoders * lo.out * lo.in, seed, tag++);
         randn_kernel<<<dim3(8, R), 256>>>(h->params + lo.b, L.arena, (long long)cfg->num_encoders * lo.out, seed, tag++);
       }
-      for (const auto* net : {&L.trunk, &L.ctx})
+      for (const auto* net : {&L.trunk, &L.ctx, &L.cenc})
         for (const auto& lo : *net) xavier_kernel<<<dim3(64, R), 256>>>(h->params + lo.w, L.arena, lo.out, lo.in, lo.ld, seed, tag++);
       randn_kernel<<<dim3(64, R), 256>>>(h->params + L.off_emb, L.arena, (long long)cfg->num_tasks * cfg->ctx_in, seed ^ 0x5EEDull, tag++);
     }
@@ -1236,24 +1262,25 @@ extern "C" int b200sac_import(b200sac_t* h, int32_t which, int32_t replica, cons
   return 0;
 }
 
-extern "C" int b200sac_get_steps(b200sac_t* h, int32_t replica, int64_t steps[3]) {
+extern "C" int b200sac_get_steps(b200sac_t* h, int32_t replica, int64_t steps[4]) {
   if (!h || !steps || replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(h->device));
   Counters c;
   CU(cudaMemcpy(&c, h->cnt + replica, sizeof(c), cudaMemcpyDeviceToHost));
-  steps[0] = c.v[0]; steps[1] = c.v[1]; steps[2] = c.v[2];
+  steps[0] = c.v[0]; steps[1] = c.v[1]; steps[2] = c.v[2]; steps[3] = c.v[4];
   return 0;
 }
 
-extern "C" int b200sac_set_steps(b200sac_t* h, int32_t replica, const int64_t steps[3]) {
+extern "C" int b200sac_set_steps(b200sac_t* h, int32_t replica, const int64_t steps[4]) {
   if (!h || !steps || replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(h->device));
   Counters c;
   CU(cudaMemcpy(&c, h->cnt + replica, sizeof(c), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 3; ++i) {
-    c.v[i] = steps[i];
-    c.b1p[i] = pow(h->cfg.beta1, (double)steps[i]);
-    c.b2p[i] = pow(h->cfg.beta2, (double)steps[i]);
+  for (int i = 0; i < 4; ++i) {
+    const int slot = i == 3 ? 4 : i;
+    c.v[slot] = steps[i];
+    c.b1p[slot] = pow(h->cfg.beta1, (double)steps[i]);
+    c.b2p[slot] = pow(h->cfg.beta2, (double)steps[i]);
   }
   CU(cudaMemcpy(h->cnt + replica, &c, sizeof(c), cudaMemcpyHostToDevice));
   return 0;
@@ -1475,7 +1502,7 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
     case L_CHEADS: return "critic_heads";
     case L_AQHEADS: return "actor_q_heads";
     case L_HEADBWD: return (l.hb.policy_mode || l.hb.NO > 1) ? "head_bwd(policy)" : "head_bwd(q)";
-    case L_ADAM: return l.ad.which == 0 ? "adam_critic+polyak" : "adam_actor+alpha";
+    case L_ADAM: return l.ad.which == 0 ? "adam_critic+polyak" : (l.ad.which == 1 ? "adam_actor+alpha" : "adam_context_encoder");
   }
   return "?";
 }
@@ -1721,8 +1748,9 @@ extern "C" int b200sac_replay_push(b200sac_replay_t* rb, int32_t replica, int64_
   if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica out of range");
   CU(cudaSetDevice(h->device));
   const int obs = h->K.obs, A = h->K.act, T = h->cfg.num_tasks, rs = h->row_stride;
+  // pack the rows, bucketed by task, then copy each bucket as at most two contiguous runs (ring wrap)
+  std::vector<std::vector<float>> bucket((size_t)rb->Teff);
   std::vector<float> row((size_t)rs, 0.f);
-  std::lock_guard<std::mutex> lk(rb->mu);
   for (int64_t i = 0; i < n; ++i) {
     memcpy(row.data(), s + i * obs, obs * sizeof(float));
     memcpy(row.data() + obs, a + i * A, A * sizeof(float));
@@ -1735,13 +1763,28 @@ extern "C" int b200sac_replay_push(b200sac_replay_t* rb, int32_t replica, int64_
       for (int q = 1; q < T; ++q)
         if (row[obs - T + q] > best) { best = row[obs - T + q]; task = q; }
     }
+    bucket[(size_t)task].insert(bucket[(size_t)task].end(), row.begin(), row.end());
+  }
+  std::lock_guard<std::mutex> lk(rb->mu);
+  for (int task = 0; task < rb->Teff; ++task) {
+    const float* src = bucket[(size_t)task].data();
+    long long cnt = (long long)(bucket[(size_t)task].size() / (size_t)rs);
+    if (cnt > rb->cap_per_task) {                  // more than a full ring: only the newest cap rows survive (deque maxlen)
+      src += (size_t)(cnt - rb->cap_per_task) * rs;
+      cnt = rb->cap_per_task;
+    }
     long long& hd = rb->head[(size_t)replica * rb->Teff + task];
     long long& fl = rb->fill[(size_t)replica * rb->Teff + task];
-    float* dst = rb->rows + (size_t)replica * rb->rs_rows + ((size_t)task * rb->cap_per_task + hd) * rs;
-    if (rb->where == 0) CU(cudaMemcpy(dst, row.data(), rs * sizeof(float), cudaMemcpyHostToDevice));
-    else memcpy(dst, row.data(), rs * sizeof(float));
-    hd = (hd + 1) % rb->cap_per_task;
-    if (fl < rb->cap_per_task) fl += 1;
+    long long done = 0;
+    while (done < cnt) {
+      const long long run = std::min(cnt - done, rb->cap_per_task - hd);
+      float* dst = rb->rows + (size_t)replica * rb->rs_rows + ((size_t)task * rb->cap_per_task + hd) * rs;
+      if (rb->where == 0) CU(cudaMemcpy(dst, src + (size_t)done * rs, (size_t)run * rs * sizeof(float), cudaMemcpyHostToDevice));
+      else memcpy(dst, src + (size_t)done * rs, (size_t)run * rs * sizeof(float));
+      hd = (hd + run) % rb->cap_per_task;
+      fl = std::min(fl + run, rb->cap_per_task);
+      done += run;
+    }
   }
   if (rb->where == 0)
     CU(cudaMemcpy(rb->d_fill + (size_t)replica * rb->Teff, rb->fill.data() + (size_t)replica * rb->Teff,

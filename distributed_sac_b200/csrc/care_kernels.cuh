@@ -35,6 +35,7 @@ struct CareTabArgs {
   long long emb_off;
   CareNet trunk, ctx;
   int T, K, row_w, off_att;
+  int original;                       // CARE(O): ctx = the shared, trainable context encoder on relu(E[t]); the trunk reads its output
 };
 
 // grid (T, n_inst, R), block 512: 16 warps, one output neuron per warp at a time, 8 independent
@@ -45,20 +46,27 @@ __global__ void __launch_bounds__(512) care_tables_kernel(CareTabArgs P) {
   __shared__ float bufA[512], bufB[512];
   const int t = blockIdx.x, inst = blockIdx.y, rep = blockIdx.z;
   const float* __restrict__ par = P.params + rep * P.rsP;
-  const float* __restrict__ E = par + P.emb_off + (long long)t * P.trunk.dims[0];
+  const float* __restrict__ E = par + P.emb_off + (long long)t * P.ctx.dims[0];
   float* __restrict__ row = P.tab[inst] + rep * P.rsTab + (long long)t * P.row_w;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int cin = P.trunk.dims[0];
+  const int cin = P.ctx.dims[0];       // embedding row; == trunk input for CARE(M), the header input for CARE(O)
   for (int i = threadIdx.x; i < cin; i += 512) xe[i] = E[i];
   __syncthreads();
-  for (int which = 0; which < 2; ++which) {
-    const CareNet& N = which == 0 ? P.trunk : P.ctx;
-    const float* cur = xe;
+  __shared__ float zc[512];                             // CARE(O): context code z = cenc(relu(E[t])), the trunk's input
+  if (P.original) {
+    for (int i = threadIdx.x; i < cin; i += 512) xe[i] = fmaxf(xe[i], 0.f);    // Embedding -> ReLU -> header (context_encoder.py:73-77)
+    __syncthreads();
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool is_ctx = (pass == 0);                    // context net first: in CARE(O) the trunk consumes its output
+    const CareNet& N = is_ctx ? P.ctx : P.trunk;
+    const long long delta = (is_ctx && P.original) ? 0 : P.inst_delta[inst];    // the context encoder has no target copy
+    const float* cur = (!is_ctx && P.original) ? zc : xe;
     float* nxt = bufA;
     for (int j = 0; j < N.n; ++j) {
       const int nin = N.dims[j], nout = N.dims[j + 1];
-      const float* __restrict__ W = par + P.inst_delta[inst] + N.w[j];
-      const float* __restrict__ bb = par + P.inst_delta[inst] + N.b[j];
+      const float* __restrict__ W = par + delta + N.w[j];
+      const float* __restrict__ bb = par + delta + N.b[j];
       for (int o = warp; o < nout; o += 16) {
         const float* __restrict__ wr = W + (long long)o * nin;
         float a = 0.f;
@@ -79,7 +87,11 @@ __global__ void __launch_bounds__(512) care_tables_kernel(CareTabArgs P) {
       cur = nxt;
       nxt = (nxt == bufA) ? bufB : bufA;
     }
-    if (which == 0 && threadIdx.x == 0) {          // softmax over the K logits (F.softmax, dim=-1)
+    if (is_ctx && P.original) {
+      for (int i = threadIdx.x; i < N.dims[N.n]; i += 512) zc[i] = cur[i];
+      __syncthreads();
+    }
+    if (!is_ctx && threadIdx.x == 0) {                  // softmax over the K logits (F.softmax, dim=-1)
       const float* lg = cur;
       float mx = lg[0];
       for (int k = 1; k < P.K; ++k) mx = fmaxf(mx, lg[k]);
@@ -229,6 +241,7 @@ struct CareTabWgradArgs {
   float* grads; long long rsG;
   CareNet trunk, ctx;
   int T, K, co;
+  int original, off_ctx;              // CARE(O): trunk layer-0 input = z (table, off_ctx); ctx layer-0 input = relu(E[t])
 };
 
 // grid (nblk, R), block 256.  Every CTA re-derives the (tiny) per-task backward chains in shared memory, then
@@ -280,7 +293,13 @@ __global__ void __launch_bounds__(256) care_tab_wgrad_kernel(CareTabWgradArgs P)
         if (q < nw) {
           const int o = (int)(q / nin), i = (int)(q % nin);
           for (int t = 0; t < T; ++t) {
-            const float a = j == 0 ? par[P.emb_off + (long long)t * nin + i] : tab[(long long)t * P.row_w + N.act_off[j - 1] + i];
+            float a;
+            if (j > 0) a = tab[(long long)t * P.row_w + N.act_off[j - 1] + i];
+            else if (P.original && n == 0) a = tab[(long long)t * P.row_w + P.off_ctx + i];          // trunk(z.detach())
+            else {
+              a = par[P.emb_off + (long long)t * nin + i];
+              if (P.original) a = fmaxf(a, 0.f);                                                  // header(relu(E))
+            }
             s = fmaf(sm[dz_off[n][j] + t * nout + o], a, s);
           }
           (P.grads + rep * P.rsG)[N.w[j] + q] = s;

@@ -34,7 +34,8 @@ struct StepConst {
 
 // Mutable per-replica counters in device memory: v[0..2] Adam steps critic/actor/alpha, v[3] step index;
 // b1p/b2p[i] = beta^v[i], kept as running products so no kernel needs a double-precision pow().
-struct Counters { long long v[4]; double b1p[3]; double b2p[3]; };
+// v[4] = Adam step of the CARE(O) context encoder.
+struct Counters { long long v[5]; double b1p[5]; double b2p[5]; };
 
 // ------------------------------------------------------------------------------------------
 // Ingest: scatter one minibatch into the four pre-concatenated layer-0 inputs
@@ -96,9 +97,9 @@ B200_D void ingest_row(const StepConst& K, const IngestOut& O, int rep, int i, c
 
 B200_D void bump_counters(Counters* cnt, int rep, double beta1, double beta2) {
   Counters* c = cnt + rep;
-  c->v[0] += 1; c->v[1] += 1; c->v[2] += 1; c->v[3] += 1;
+  c->v[0] += 1; c->v[1] += 1; c->v[2] += 1; c->v[3] += 1; c->v[4] += 1;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { c->b1p[i] *= beta1; c->b2p[i] *= beta2; }
+  for (int i = 0; i < 5; ++i) { c->b1p[i] *= beta1; c->b2p[i] *= beta2; }
 }
 
 // minibatch given as five separate arrays [R][B][w]

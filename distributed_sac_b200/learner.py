@@ -230,7 +230,7 @@ class _BaseLearner:
 
     def save_checkpoint(self, episode_idx):
         named = self.core.get_named()
-        sc, sa, sl = self.core.get_steps()
+        sc, sa, sl = self.core.get_steps()[:3]
         state = {"episode_idx": episode_idx, "total_step": self.total_step}
         state.update(self._critic_checkpoint_entries(named))
         state["critic_optimizer"] = self._adam_state_dict(self._canon(("q1", "q2")), self.lr_critic, sc)
@@ -431,10 +431,8 @@ class CARELearner(MTSACLearner):
     def _set_dims(self):
         super()._set_dims()
         c = self.cfg
-        if not c.get("use_modified_care", False):
-            raise NotImplementedError("only CARE(M) (use_modified_care: true) is implemented; CARE(O) has a trainable context encoder")
-        self.use_modified_care = True
-        self.use_weighted_loss = True                      # learner.py:313,349: use_weighted_loss = use_modified_care
+        self.use_modified_care = bool(c.get("use_modified_care", False))
+        self.use_weighted_loss = self.use_modified_care    # learner.py:313,349: use_weighted_loss = use_modified_care
         self.encoder_cfg = c["encoder"]
 
     def _core_config(self):
@@ -448,6 +446,9 @@ class CARELearner(MTSACLearner):
         cc.ctx_hidden = [int(x) for x in e["hidden_dims_contextEnc"]]
         cc.ctx_out = int(e["output_dim_contextEnc"])
         cc.tau_se = float(e["state_encoder_tau"])
+        cc.care_original = not self.use_modified_care     # CARE(O): trainable context encoder with its own Adam
+        cc.emb_dim = int(e["embedding_dim_contextEnc"])
+        cc.lr_ctx = float(e["lr_contextEnc"])
         return cc
 
     def _init_common(self, *a, **kw):
@@ -463,11 +464,25 @@ class CARELearner(MTSACLearner):
 
     def _enc_map(self, prefix):
         cc = self.core.cfg
-        return names.care_encoder_key_map(len(cc.mix_hidden) + 1, len(cc.mix_hidden) + 1, len(cc.ctx_hidden) + 1, prefix)
+        n_ctx = len(cc.ctx_hidden) + 1 if self.use_modified_care else 0      # CARE(O) has no mlp_context in the state encoder
+        return names.care_encoder_key_map(len(cc.mix_hidden) + 1, len(cc.mix_hidden) + 1, n_ctx, prefix)
+
+    def _cenc_map(self):
+        """CARE(O) context encoder keys: embedding = Sequential(Embedding, ReLU, header[Linear, ReLU, Linear, ReLU]),
+        mlp = build_mlp(...) (context_encoder.py:59-89)."""
+        m = {"embedding.2.0.weight": "cenc.0.weight", "embedding.2.0.bias": "cenc.0.bias",
+             "embedding.2.2.weight": "cenc.1.weight", "embedding.2.2.bias": "cenc.1.bias"}
+        for j in range(len(self.core.cfg.ctx_hidden) + 1):
+            for kind in ("weight", "bias"):
+                m[f"mlp.{2 * j}.{kind}"] = f"cenc.{2 + j}.{kind}"
+        return m
 
     def _key_map(self, net):
         if net == "context_encoder":
-            return {"embedding.0.weight": "embedding"}
+            km = {"embedding.0.weight": "embedding"}
+            if not self.use_modified_care:
+                km.update(self._cenc_map())
+            return km
         if net == "actor":            # policy MLP + the tied copy of the critic's state encoder
             return {**names.actor_key_map("MS", len(self.actor_hidden_dim) + 1), **self._enc_map("cse")}
         if net in ("critic_se", "target_se"):
@@ -483,6 +498,9 @@ class CARELearner(MTSACLearner):
         d["local_critic"].update(self._module_state_dict("critic_se", named=named))
         d["target_critic"].update(self._module_state_dict("target_se", named=named))
         d["context_encoder"] = self._module_state_dict("context_encoder", named=named)
+        if not self.use_modified_care:
+            d["context_encoder_optimizer"] = self._adam_state_dict(list(self._cenc_map().values()),
+                                                                   self.core.cfg.lr_ctx, self.core.get_steps()[3])
         return d
 
     def _load_critic_checkpoint_entries(self, ck):
@@ -491,6 +509,8 @@ class CARELearner(MTSACLearner):
         self._load_module_state_dict("target_se", ck["target_critic"])
         if "context_encoder" in ck:
             self._load_module_state_dict("context_encoder", ck["context_encoder"])
+        if not self.use_modified_care and "context_encoder_optimizer" in ck:
+            self._load_adam(ck["context_encoder_optimizer"], list(self._cenc_map().values()), 3)
 
     def _canon(self, nets):
         out = []

@@ -61,8 +61,10 @@ typedef struct b200sac_cfg {
   int32_t weighted_loss;             /* MTSAC use_weighted_loss (== extra 1/batch) */
   int32_t replicas;                  /* independent learners in this handle (>= 1) */
   int32_t precision;                 /* 0 = fp32 FFMA; 1 = 3xTF32 on tcgen05 for hidden layers */
-  int32_t care;                      /* 1 = CARE(M): context embedding + mixture-of-encoders state encoders
-                                        (MT10_Distributed_CARE/src/{context,state}_encoder.py, use_modified_care) */
+  int32_t care;                      /* CARE state encoders (MT10_Distributed_CARE/src/{context,state}_encoder.py):
+                                        1 = CARE(M) use_modified_care=true: frozen embedding, per-encoder mlp_context;
+                                        2 = CARE(O) use_modified_care=false (= MT1_Distributed_CARE): trainable context
+                                            encoder z = mlp(header(relu(E[t]))) with its own Adam (lr_ctx) */
   double gamma, tau, reward_scale;
   double lr_actor, lr_critic, lr_alpha;
   double action_scale;               /* k = (hi - lo) / 2 */
@@ -77,8 +79,9 @@ typedef struct b200sac_cfg {
   int32_t n_ctx_hidden;              /* hidden_dims_contextEnc */
   int32_t ctx_hidden[B200SAC_MAX_HIDDEN];
   int32_t ctx_out;                   /* output_dim_contextEnc */
-  int32_t reserved1;
+  int32_t emb_dim;                   /* embedding_dim_contextEnc: CARE(O) header = Linear(ctx_in, 2e), Linear(2e, e) */
   double tau_se;                     /* state_encoder_tau */
+  double lr_ctx;                     /* lr_contextEnc (CARE(O) context-encoder Adam) */
 } b200sac_cfg;
 
 typedef struct b200sac_tensor_desc {
@@ -86,7 +89,7 @@ typedef struct b200sac_tensor_desc {
   int64_t offset;                    /* in floats, inside one replica's parameter arena */
   int32_t rows, cols;                /* weight: (out, in) row-major; bias/log_alpha: (n, 1) */
   int32_t trainable;                 /* 1 -> has Adam m/v at the same offset in the m/v arenas */
-  int32_t opt;                       /* 0 critic, 1 actor, 2 alpha, -1 none (targets) */
+  int32_t opt;                       /* 0 critic, 1 actor, 2 alpha, 3 context encoder, -1 none (targets, embedding) */
   int32_t pitch;                     /* floats between consecutive rows (>= cols): first-layer weights are padded to a
                                         multiple of 4 so that TMA can address them; pad columns are and stay zero */
   int32_t reserved;
@@ -118,9 +121,9 @@ int b200sac_import(b200sac_t* h, int32_t which, int32_t replica, const float* bu
 /* Device address of an arena (replica 0; replicas are contiguous, stride = arena floats).  For
  * zero-copy views and for the one-time NCCL broadcast of initial weights done by the host shim. */
 int b200sac_arena_ptr(b200sac_t* h, int32_t which, float** dev_ptr, int64_t* floats_per_replica);
-/* Adam step counters {critic, actor, alpha} of one replica. */
-int b200sac_get_steps(b200sac_t* h, int32_t replica, int64_t steps[3]);
-int b200sac_set_steps(b200sac_t* h, int32_t replica, const int64_t steps[3]);
+/* Adam step counters {critic, actor, alpha, context encoder (CARE(O), else unused)} of one replica. */
+int b200sac_get_steps(b200sac_t* h, int32_t replica, int64_t steps[4]);
+int b200sac_set_steps(b200sac_t* h, int32_t replica, const int64_t steps[4]);
 
 /* One gradient step from caller-provided DEVICE minibatches, each
  * [replicas][batch][width] fp32: s,s2 width obs(=state_dim+num_tasks), a width act, r,d width 1.

@@ -1,7 +1,10 @@
-"""CPU oracle for the CARE(M) gradient step -- TEST INFRASTRUCTURE, NOT PRODUCT.
+"""CPU oracle for the CARE gradient step (both variants) -- TEST INFRASTRUCTURE, NOT PRODUCT.
 
-Clean-room PyTorch fp32 autograd restatement of MT10_Distributed_CARE with
-`use_modified_care: true` (BASELINE.json config 5).  Same import rules as
+Clean-room PyTorch fp32 autograd restatement of MT10_Distributed_CARE:
+  CARE(M) `use_modified_care: true`  (BASELINE.json config 5): frozen embedding -> per-encoder mlp_context, weighted loss
+  CARE(O) `use_modified_care: false` (also the algorithm of MT1_Distributed_CARE): TRAINABLE context encoder
+          z = mlp(header(relu(E[t]))) with its own Adam (context_encoder.py:59-89, learner.py:137-141,399),
+          z feeds the attention trunk (detached) and is concatenated as-is; plain (unweighted) losses.  Same import rules as
 oracle/sac_port.py.  Pinned to the unmodified reference by the fixture
 tests/golden/care_small_s4.npz (oracle/gen_golden.py drives the real
 `Learner.update()`), checked in tests/test_oracle_golden.py.
@@ -21,6 +24,7 @@ Canonical parameter names (on top of oracle/sac_port.py's actor/q1/q2/*_target/l
   cse.ctx.{j}.weight|bias                                mlp_context
   tse.*                                                  target critic's state encoder
   embedding                                              (T, 768) frozen
+  cenc.{j}.weight|bias                                   CARE(O) only: context encoder = header (2 Linear) + mlp, trainable
 The actor's state encoder is always a hard copy of `cse` taken at the end of update()
 (learner.py:402), so it is not a separate set of names: `ase.*` is derived on export.
 """
@@ -50,6 +54,9 @@ class CareSpec:
     ctx_out: int = 50                                               # output_dim_contextEnc
     tau_se: float = 0.05                                            # state_encoder_tau
     weighted_loss: bool = True                                      # use_modified_care => weighted (== /B)
+    modified: bool = True                                           # use_modified_care
+    emb_dim: int = 50                                               # embedding_dim_contextEnc (CARE(O) header width)
+    lr_ctx: float = 3e-4                                            # lr_contextEnc
     gamma: float = 0.99
     tau: float = 0.005
     reward_scale: float = 1.0
@@ -83,13 +90,31 @@ def mix_dims(spec):
 
 
 def trunk_dims(spec):
-    d = [spec.ctx_in] + list(spec.mix_hidden) + [spec.num_encoders]
+    d = [spec.ctx_in if spec.modified else spec.emb_dim] + list(spec.mix_hidden) + [spec.num_encoders]
     return list(zip(d[:-1], d[1:]))
 
 
 def ctx_dims(spec):
+    """CARE(M): mlp_context inside every state encoder.  CARE(O): none there."""
+    if not spec.modified:
+        return []
     d = [spec.ctx_in] + list(spec.ctx_hidden) + [spec.ctx_out]
     return list(zip(d[:-1], d[1:]))
+
+
+def cenc_dims(spec):
+    """CARE(O) context encoder: header Linear(768, 2e), Linear(2e, e) then mlp e -> ctx_hidden -> ctx_out."""
+    if spec.modified:
+        return []
+    d = [spec.ctx_in, 2 * spec.emb_dim, spec.emb_dim] + list(spec.ctx_hidden) + [spec.ctx_out]
+    return list(zip(d[:-1], d[1:]))
+
+
+def cenc_names(spec):
+    n = []
+    for j, _ in enumerate(cenc_dims(spec)):
+        n += [f"cenc.{j}.weight", f"cenc.{j}.bias"]
+    return n
 
 
 def encoder_names(spec, prefix):
@@ -116,6 +141,10 @@ def init_params(spec: CareSpec, seed=0, embedding=None):
                 bound = math.sqrt(6.0 / (i + o))
                 p[f"{pre}.{name}.{j}.weight"] = (torch.rand(o, i, generator=g) * 2 - 1) * bound
                 p[f"{pre}.{name}.{j}.bias"] = torch.zeros(o)
+    for j, (i, o) in enumerate(cenc_dims(spec)):
+        bound = math.sqrt(6.0 / (i + o))
+        p[f"cenc.{j}.weight"] = (torch.rand(o, i, generator=g) * 2 - 1) * bound
+        p[f"cenc.{j}.bias"] = torch.zeros(o)
     p["embedding"] = embedding.clone().float() if embedding is not None else torch.randn(spec.num_tasks, spec.ctx_in, generator=g) * 0.3
     return p
 
@@ -148,8 +177,15 @@ def state_encode(spec, p, pre, z_context, mtobs, detach_z_encs=False):
     alpha = torch.softmax(_seq(p, f"{pre}.trunk", z_context.detach(), len(trunk_dims(spec))), dim=-1).unsqueeze(-1)
     z_enc = (z_encs * alpha).sum(dim=1)
     z_enc = z_enc / alpha.sum(dim=1)
-    zc = _seq(p, f"{pre}.ctx", z_context, len(ctx_dims(spec)))
+    zc = _seq(p, f"{pre}.ctx", z_context, len(ctx_dims(spec))) if spec.modified else z_context
     return torch.cat([zc, z_enc], dim=1)
+
+
+def context_encode(spec, p, tid):
+    """contextEncoder.forward (context_encoder.py:110-127)."""
+    if spec.modified:
+        return p["embedding"][tid]
+    return _seq(p, "cenc", torch.relu(p["embedding"][tid]), len(cenc_dims(spec)))
 
 
 class CarePortLearner:
@@ -166,15 +202,19 @@ class CarePortLearner:
         self.opt_actor = torch.optim.Adam([self.p[n] for n in self.actor_names], lr=spec.lr_actor)
         self.opt_critic = torch.optim.Adam([self.p[n] for n in self.critic_names], lr=spec.lr_critic)
         self.opt_alpha = torch.optim.Adam([self.p["log_alpha"]], lr=spec.lr_actor)
+        self.ctx_names = cenc_names(spec)
+        self.opt_ctx = torch.optim.Adam([self.p[n] for n in self.ctx_names], lr=spec.lr_ctx) if self.ctx_names else None
         if adam_state is not None:
             self.load_adam(adam_state)
 
     def trainable_names(self):
-        return self.actor_names + self.critic_names + ["log_alpha"]
+        return self.actor_names + self.critic_names + ["log_alpha"] + self.ctx_names
 
     def _opt_of(self, name):
         if name == "log_alpha":
             return self.opt_alpha, 2
+        if name.startswith("cenc."):
+            return self.opt_ctx, 3
         return (self.opt_actor, 1) if name.startswith("actor.") else (self.opt_critic, 0)
 
     def load_adam(self, st):
@@ -185,7 +225,7 @@ class CarePortLearner:
                                        "exp_avg_sq": torch.as_tensor(st["v"][name]).clone().float()}
 
     def adam_state(self):
-        m, v, step = {}, {}, [0, 0, 0]
+        m, v, step = {}, {}, [0, 0, 0] + ([0] if self.ctx_names else [])
         for name in self.trainable_names():
             opt, slot = self._opt_of(name)
             st = opt.state.get(self.p[name], None)
@@ -227,10 +267,10 @@ class CarePortLearner:
         eps_cur = torch.randn(B, spec.act_dim) if eps_cur is None else eps_cur
         tid = torch.argmax(s[:, -spec.num_tasks:], dim=1)
         alpha = p["log_alpha"].detach()[tid].exp().unsqueeze(1)
-        for opt in (self.opt_critic, self.opt_actor, self.opt_alpha):
+        for opt in (self.opt_critic, self.opt_actor, self.opt_alpha) + ((self.opt_ctx,) if self.opt_ctx else ()):
             opt.zero_grad()
         div = float(B) if spec.weighted_loss else 1.0
-        z = p["embedding"][tid]                                   # contextEncoder.forward, frozen lookup
+        z = context_encode(spec, p, tid)                          # contextEncoder.forward
 
         with torch.no_grad():
             a2, logp2, _ = self._policy("ase", z, s2, eps_next, False)
@@ -239,7 +279,7 @@ class CarePortLearner:
 
         q1, q2 = self._q("cse", "q1", "q2", z, s, a)
         q_loss = torch.mean((y - q1) ** 2) / div + torch.mean((y - q2) ** 2) / div
-        q_loss.backward()
+        q_loss.backward()                                         # also deposits d/d(context encoder) in CARE(O)
         self.opt_critic.step()
 
         a_cur, logp, log_std = self._policy("ase", z.detach(), s, eps_cur, True)
@@ -264,7 +304,10 @@ class CarePortLearner:
             for k in encoder_names(spec, "cse"):
                 t, l = p["tse" + k[3:]], p[k]
                 t.copy_(spec.tau_se * l + (1.0 - spec.tau_se) * t)
-            # update(): context_encoder_optimizer.step() has nothing trainable in CARE(M); then the hard tie
+        if self.opt_ctx is not None:
+            self.opt_ctx.step()                                   # update(): context_encoder_optimizer.step() (learner.py:399)
+        with torch.no_grad():
+            # the hard tie (learner.py:402)
             for k in encoder_names(spec, "cse"):
                 p["ase" + k[3:]].copy_(p[k])
 

@@ -186,10 +186,15 @@ def _care_named(lrn):
         mixl = [m for m in se.mixture_encoders.mixtureEncoders if hasattr(m, "W")]
         for l, m in enumerate(mixl):
             out[f"{pre}.mix.{l}.W"], out[f"{pre}.mix.{l}.b"] = m.W, m.b
-        for name, seq in (("trunk", se.trunk), ("ctx", se.mlp_context)):
+        for name, seq in (("trunk", se.trunk), ("ctx", getattr(se, "mlp_context", []))):
             for j, m in enumerate([m for m in seq if hasattr(m, "out_features")]):
                 out[f"{pre}.{name}.{j}.weight"], out[f"{pre}.{name}.{j}.bias"] = m.weight, m.bias
     out["embedding"] = lrn.context_encoder.embedding[0].weight
+    if not lrn.use_modified_care:        # CARE(O): embedding = Sequential(Embedding, ReLU, header), then mlp
+        ce = lrn.context_encoder
+        lin = [m for m in ce.embedding[2] if hasattr(m, "out_features")] + [m for m in ce.mlp if hasattr(m, "out_features")]
+        for j, m in enumerate(lin):
+            out[f"cenc.{j}.weight"], out[f"cenc.{j}.bias"] = m.weight, m.bias
     out["log_alpha"] = lrn.log_alpha
     return out
 
@@ -205,8 +210,9 @@ def make_care_case(name, n_steps, cfg_overrides, seed=0, data_seed=4321):
                        mix_out=int(enc["output_dim_mixtureEnc"]), ctx_in=int(enc["RoBERTa_embedding_dim"]),
                        ctx_hidden=list(enc["hidden_dims_contextEnc"]), ctx_out=int(enc["output_dim_contextEnc"]),
                        tau_se=float(enc["state_encoder_tau"]), weighted_loss=bool(lrn.use_modified_care), gamma=lrn.gamma,
-                       tau=lrn.tau, reward_scale=float(lrn.reward_scale), lr_actor=lrn.lr_actor, lr_critic=lrn.lr_critic)
-    assert lrn.use_modified_care, "only CARE(M) is restated"
+                       tau=lrn.tau, reward_scale=float(lrn.reward_scale), lr_actor=lrn.lr_actor, lr_critic=lrn.lr_critic,
+                       modified=bool(lrn.use_modified_care), emb_dim=int(enc["embedding_dim_contextEnc"]),
+                       lr_ctx=float(enc["lr_contextEnc"]))
     named = _care_named(lrn)
     d = {"spec": json.dumps(spec.to_json()), "family": "C10", "n_steps": n_steps}
     for k, p in named.items():
@@ -214,7 +220,7 @@ def make_care_case(name, n_steps, cfg_overrides, seed=0, data_seed=4321):
     trainable = [k for k in named if not (k.startswith("tse.") or "_target" in k or k == "embedding")]
     for k in trainable:
         d["m_in/" + k] = np.zeros_like(d["p_in/" + k]); d["v_in/" + k] = np.zeros_like(d["p_in/" + k])
-    d["step_in"] = np.zeros(3, np.int64)
+    d["step_in"] = np.zeros(3 if lrn.use_modified_care else 4, np.int64)
     g = torch.Generator().manual_seed(data_seed + 17)
     batches, eps_n, eps_c, losses = [], [], [], []
     for i in range(n_steps):
@@ -244,14 +250,15 @@ def make_care_case(name, n_steps, cfg_overrides, seed=0, data_seed=4321):
     d["eps_next"] = np.stack([e.numpy() for e in eps_n]); d["eps_cur"] = np.stack([e.numpy() for e in eps_c])
     for k, p in named.items():
         d["p_out/" + k] = p.detach().clone().numpy()
-    opts = {"critic": lrn.critic_optimizer, "actor": lrn.actor_optimizer, "alpha": lrn.log_alpha_optimizer}
-    steps = {"critic": 0, "actor": 0, "alpha": 0}
+    opts = {"critic": lrn.critic_optimizer, "actor": lrn.actor_optimizer, "alpha": lrn.log_alpha_optimizer,
+            "ctx": lrn.context_encoder_optimizer}
+    steps = {"critic": 0, "actor": 0, "alpha": 0, "ctx": 0}
     for k in trainable:
-        tag = "alpha" if k == "log_alpha" else ("actor" if k.startswith("actor.") else "critic")
+        tag = "alpha" if k == "log_alpha" else ("actor" if k.startswith("actor.") else ("ctx" if k.startswith("cenc.") else "critic"))
         st = opts[tag].state[named[k]]
         d["m_out/" + k], d["v_out/" + k] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
         steps[tag] = int(st["step"])
-    d["step_out"] = np.array([steps["critic"], steps["actor"], steps["alpha"]], np.int64)
+    d["step_out"] = np.array([steps["critic"], steps["actor"], steps["alpha"]] + ([] if lrn.use_modified_care else [steps["ctx"]]), np.int64)
     # the actor's tied encoder must equal the critic's after update() (learner.py:402)
     ase = dict(lrn.actor.state_encoder.named_parameters()); cse = dict(lrn.local_critic.state_encoder.named_parameters())
     assert all(torch.equal(ase[k], cse[k]) for k in ase)
@@ -266,6 +273,11 @@ CARE_CASES = {
         encoder=dict(hidden_dims_contextEnc=[24, 20], output_dim_contextEnc=16, embedding_dim_contextEnc=16,
                      hidden_dims_mixtureEnc=[28], output_dim_mixtureEnc=12, num_encoders=4))),
 }
+
+CARE_CASES["care_o_small_s4"] = dict(n_steps=4, seed=8, cfg_overrides=dict(
+    use_modified_care=False, batch_size=120, actor=dict(actor_hidden_dim=[64, 48, 32]), critic=dict(critic_hidden_dim=[40, 72, 56]),
+    encoder=dict(hidden_dims_contextEnc=[24, 20], output_dim_contextEnc=12, embedding_dim_contextEnc=12,
+                 hidden_dims_mixtureEnc=[28], output_dim_mixtureEnc=12, num_encoders=4)))
 
 CASES = {
     # full-size LunarLander learner, seeded Xavier init, distinct target nets, fresh Adam

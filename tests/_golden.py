@@ -105,6 +105,7 @@ def care_core_config(spec, replicas=1, **kw):
              reward_scale=spec.reward_scale, lr_actor=spec.lr_actor, lr_critic=spec.lr_critic,
              action_scale=spec.action_scale, beta1=spec.beta1, beta2=spec.beta2, adam_eps=spec.adam_eps,
              care=True, num_encoders=spec.num_encoders, mix_hidden=list(spec.mix_hidden), mix_out=spec.mix_out,
-             ctx_in=spec.ctx_in, ctx_hidden=list(spec.ctx_hidden), ctx_out=spec.ctx_out, tau_se=spec.tau_se)
+             ctx_in=spec.ctx_in, ctx_hidden=list(spec.ctx_hidden), ctx_out=spec.ctx_out, tau_se=spec.tau_se,
+             care_original=not spec.modified, emb_dim=spec.emb_dim, lr_ctx=spec.lr_ctx)
     d.update(kw)
     return CoreConfig(**d)

@@ -16,11 +16,12 @@ def cuda():
     return torch.device("cuda", 0)
 
 
+@pytest.mark.parametrize("name", ["care_small_s4", "care_o_small_s4"], ids=["CARE(M)", "CARE(O)"])
 @pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "tc3xtf32"])
-def test_care_step_matches_reference_fixture(cuda, precision):
+def test_care_step_matches_reference_fixture(cuda, precision, name):
     from distributed_sac_b200 import _lib
     from distributed_sac_b200.core import SacCore
-    c = CareCase()
+    c = CareCase(name)
     core = SacCore(care_core_config(c.spec, precision=precision), 0, seed=0)
     core.set_named(c.p_in)
     for i in range(c.n_steps):
@@ -38,11 +39,12 @@ def test_care_step_matches_reference_fixture(cuda, precision):
     core.close()
 
 
-def test_care_full_size_matches_port(cuda):
+@pytest.mark.parametrize("modified", [True, False], ids=["CARE(M)", "CARE(O)"])
+def test_care_full_size_matches_port(cuda, modified):
     """BASELINE.json config 5 shape: 39+10 obs, K=6 encoders, 768-d context, 400^3 MLPs, batch 1280."""
     from distributed_sac_b200 import _lib
     from distributed_sac_b200.core import SacCore
-    spec = cp.CareSpec()
+    spec = cp.CareSpec(modified=modified, weighted_loss=modified)
     p = cp.init_params(spec, seed=2)
     port = cp.CarePortLearner(spec, p)
     core = SacCore(care_core_config(spec, precision=1), 0, seed=0)

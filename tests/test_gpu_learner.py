@@ -115,7 +115,8 @@ def test_run_loop_with_redis_stub(cuda, tmp_path):
     lrn.memory.stop()
 
 
-def test_care_learner_surface(cuda, tmp_path):
+@pytest.mark.parametrize("modified", [True, False], ids=["CARE(M)", "CARE(O)"])
+def test_care_learner_surface(cuda, tmp_path, modified):
     """CARELearner: cfg 'encoder' block + metadata JSONs as in MT10_Distributed_CARE_cfg.json; published blob has the
     reference's keys/shapes (Player loads context_encoder + actor state_dicts, C10/player.py:82-93)."""
     import numpy as np
@@ -125,7 +126,7 @@ def test_care_learner_surface(cuda, tmp_path):
     emb = {n: rng.standard_normal(768).round(4).tolist() for n in names_}
     (tmp_path / "emb.json").write_text(json.dumps(emb))
     (tmp_path / "names.json").write_text(json.dumps(names_))
-    cfg = {"use_modified_care": True, "num_tasks": 10, "device": "cuda", "buffer_size": 40000, "reward_scale": 1,
+    cfg = {"use_modified_care": modified, "num_tasks": 10, "device": "cuda", "buffer_size": 40000, "reward_scale": 1,
            "batch_size": 160, "log_alpha": 0, "tau": 0.005, "update_delay": 6, "random_step": 5000, "start_memory_len": 5000,
            "print_period_player": 2, "print_period_learner": 10, "gamma": 0.99, "max_episode_time": 500,
            "actor": {"state_dim": 39, "action_dim": 4, "action_bound": [-1.0, 1.0], "lr_actor": 3e-4, "actor_hidden_dim": [64, 64, 64]},
@@ -151,13 +152,21 @@ def test_care_learner_surface(cuda, tmp_path):
     assert a["state_encoder.mixture_encoders.mixtureEncoders.0.W"].shape == (6, 39, 50)
     assert a["state_encoder.mixture_encoders.mixtureEncoders.0.b"].shape == (6, 1, 50)
     assert a["state_encoder.mixture_encoders.mixtureEncoders.2.W"].shape == (6, 50, 50)
-    assert a["state_encoder.trunk.0.weight"].shape == (50, 768) and a["state_encoder.trunk.2.weight"].shape == (6, 50)
-    assert a["state_encoder.mlp_context.4.weight"].shape == (50, 50)
+    assert a["state_encoder.trunk.0.weight"].shape == (50, 768 if modified else 50) and a["state_encoder.trunk.2.weight"].shape == (6, 50)
+    if modified:
+        assert a["state_encoder.mlp_context.4.weight"].shape == (50, 50)
+    else:       # CARE(O): trainable context encoder published to the players (C10/player.py:82-93)
+        ce = blob["context_encoder"]
+        assert "state_encoder.mlp_context.0.weight" not in a
+        assert ce["embedding.2.0.weight"].shape == (100, 768) and ce["embedding.2.2.weight"].shape == (50, 100)
+        assert ce["mlp.0.weight"].shape == (50, 50) and ce["mlp.4.bias"].shape == (50,)
     assert a["mu_log_std_layer.0.weight"].shape == (64, 100) and a["mu_log_std_layer.6.weight"].shape == (8, 64)
     path = lrn.save_checkpoint(24)
     ck = torch.load(path, map_location="cpu", weights_only=False)
     assert "state_encoder.trunk.0.weight" in ck["local_critic"] and "Q_function_2.6.bias" in ck["target_critic"]
-    assert len(ck["critic_optimizer"]["state"]) == 14 + 16 and len(ck["actor_optimizer"]["state"]) == 8
+    assert len(ck["critic_optimizer"]["state"]) == (14 if modified else 8) + 16 and len(ck["actor_optimizer"]["state"]) == 8
+    if not modified:
+        assert len(ck["context_encoder_optimizer"]["state"]) == 10 and int(ck["context_encoder_optimizer"]["state"][0]["step"]) == 4
     before = lrn.core.export_arena()
     lrn2 = CARELearner(None, names_, str(p), write_mode=False, server=redis_stub.StrictRedis(host=str(tmp_path) + "d"),
                        seed=5, checkpoint_path=path)

@@ -5,8 +5,12 @@ import care_port as cp
 from _golden import CareCase, REL, check_state, rel_l2, rel_scalar
 
 
-def test_care_port_matches_reference_fixture():
-    c = CareCase()
+import pytest
+
+
+@pytest.mark.parametrize("name", ["care_small_s4", "care_o_small_s4"])
+def test_care_port_matches_reference_fixture(name):
+    c = CareCase(name)
     torch.set_num_threads(4)
     lrn = cp.CarePortLearner(c.spec, c.p_in)
     for i in range(c.n_steps):
