@@ -457,6 +457,26 @@ def main():
                 lrn.update_many(Ke)
                 barrier()
                 t_pipe = time.perf_counter() - t0
+            # run()-loop body: update + publication of the actor blob (LL/learner.py:296-299), two ways:
+            #   blocking  = update(); get_parameters()              (what the reference does, one after the other)
+            #   overlapped = enqueue step; publish_begin(); read losses; publish_wait()   (what Learner.run() here does)
+            import pickle as _pk
+            Kp = max(50, min(Ke, 500))
+            pub_bytes = 0
+            with torch.cuda.stream(stream):
+                t0 = time.perf_counter()
+                for _ in range(Kp):
+                    lrn.update()
+                    blob = _pk.dumps(lrn.get_parameters())
+                t_pub_block = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                for _ in range(Kp):
+                    lrn.memory.enqueue_step(lrn.core)
+                    lrn.publish_begin()
+                    lrn.core.read_losses(1)
+                    blob = _pk.dumps(lrn.publish_wait())
+                t_pub_over = time.perf_counter() - t0
+                pub_bytes = 4 * sum(v.numel() for m in _pk.loads(blob).values() for v in m.values())
             h2d = lrn.core.cfg.batch * row_bytes
             d2h = 16
             lrn.memory.stop()
@@ -465,7 +485,12 @@ def main():
     e2e = {"value": world * Ke / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "api": "Learner.update() per step (host sample+gather -> pinned staging -> cudaMemcpyAsync on a side stream -> "
                   "graph launch -> losses written to mapped pinned memory -> stream sync)",
-           "steps": Ke, "pipelined_update_many": {"value": world * Ke / t_pipe, "unit": "steps/s"}}
+           "steps": Ke, "pipelined_update_many": {"value": world * Ke / t_pipe, "unit": "steps/s"},
+           "with_publication": {"unit": "steps/s", "d2h_bytes_per_step": pub_bytes + d2h, "steps": Kp,
+                                "update_then_get_parameters": world * Kp / t_pub_block,
+                                "overlapped_run_loop": world * Kp / t_pub_over,
+                                "note": "per step: update + {'actor': state_dict} snapshot -> pinned host -> pickle.dumps, "
+                                        "as Learner.run() publishes it for the players"}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -152,21 +152,45 @@ class SacCore:
         _lib.check(self.lib.b200sac_arena_ptr(self._h, which, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def _unpack(self, name, flat, off):
+        """One layout-table entry read out of `flat` (a float32 tensor) at float offset `off`, in the reference's shape."""
+        _, rows, cols, _t, _o, pitch = self.table[name]
+        t = flat[off:off + rows * pitch].reshape(rows, pitch)[:, :cols].reshape(-1)
+        if ".mix." in name:            # stored as [K][out][in] | [K][out]; the reference holds (K,in,out) | (K,1,out)
+            K = self.cfg.num_encoders
+            return (t.reshape(K, rows // K, cols).permute(0, 2, 1).contiguous() if name.endswith(".W")
+                    else t.reshape(K, 1, rows // K).clone())
+        is_mat = name.endswith(".weight") or name == "embedding"
+        return t.reshape(rows, cols).clone() if is_mat else t.clone()
+
+    # ---- publication path (Learner.get_parameters, LL/learner.py:272-276) ---------------------------
+    def publish_begin(self, tensor_names, replica=0):
+        """Enqueue a consistent snapshot of the named parameter tensors and start its async copy to pinned host
+        memory (b200sac_publish_begin); steps enqueued afterwards overlap it.  Collect with publish_wait()."""
+        ents = sorted((self.table[n][0], self.table[n][1] * self.table[n][5], n) for n in tensor_names)
+        ranges, where, at = [], {}, 0            # merge adjacent tensors into as few copies as possible
+        for off, cnt, n in ents:
+            if ranges and ranges[-1][0] + ranges[-1][1] == off:
+                ranges[-1][1] += cnt
+            else:
+                ranges.append([off, cnt])
+            where[n] = at
+            at += cnt
+        offs = (C.c_int64 * len(ranges))(*[r[0] for r in ranges])
+        cnts = (C.c_int64 * len(ranges))(*[r[1] for r in ranges])
+        _lib.check(self.lib.b200sac_publish_begin(self._h, replica, len(ranges), offs, cnts, _stream()))
+        self._pub_where = where
+
+    def publish_wait(self) -> Dict[str, torch.Tensor]:
+        ptr, n = C.POINTER(C.c_float)(), C.c_int64()
+        _lib.check(self.lib.b200sac_publish_wait(self._h, C.byref(ptr), C.byref(n)))
+        import numpy as np
+        flat = torch.from_numpy(np.ctypeslib.as_array(ptr, shape=(n.value,)))     # view of the pinned buffer; _unpack clones
+        return {name: self._unpack(name, flat, at) for name, at in self._pub_where.items()}
+
     def get_named(self, which=_lib.PARAMS, replica=0) -> Dict[str, torch.Tensor]:
         flat = self.export_arena(which, replica)
-        out = {}
-        for name, (off, rows, cols, trainable, _opt, pitch) in self.table.items():
-            if which != _lib.PARAMS and not trainable:
-                continue
-            t = flat[off:off + rows * pitch].reshape(rows, pitch)[:, :cols].reshape(-1)
-            if ".mix." in name:        # stored as [K][out][in] | [K][out]; the reference holds (K,in,out) | (K,1,out)
-                K = self.cfg.num_encoders
-                out[name] = (t.reshape(K, rows // K, cols).permute(0, 2, 1).contiguous() if name.endswith(".W")
-                             else t.reshape(K, 1, rows // K).clone())
-                continue
-            is_mat = name.endswith(".weight") or name == "embedding"
-            out[name] = t.reshape(rows, cols).clone() if is_mat else t.clone()
-        return out
+        return {name: self._unpack(name, flat, d[0]) for name, d in self.table.items() if which == _lib.PARAMS or d[3]}
 
     def set_named(self, tensors: Dict[str, torch.Tensor], which=_lib.PARAMS, replica=0, strict=True):
         flat = self.export_arena(which, replica)

@@ -292,6 +292,13 @@ struct b200sac {
   bool stage_used[2] = {false, false};
   int prefetch_slot = -1;         // host-ring step_sampled: minibatch already drawn, gathered and in flight (H2D)
   b200sac_replay* prefetch_rb = nullptr;
+  // publication path (b200sac_publish_*): device snapshot -> pinned host, on its own stream
+  cudaStream_t pub = nullptr;
+  cudaEvent_t ev_pub_snap = nullptr, ev_pub_done = nullptr;
+  float* pub_d = nullptr;         // device snapshot (consistent: taken in stream order between two steps)
+  float* pub_h = nullptr;         // pinned host copy handed to the caller
+  int64_t pub_cap = 0, pub_n = 0;
+  bool pub_pending = false;
   float* loss_h = nullptr;        // mapped pinned loss ring [kLossSlots][R][4], written by the tail kernels
   float* loss_h_dev = nullptr;    // its device-side address
 };
@@ -337,6 +344,11 @@ static int destroy_impl(b200sac* h) {
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
   if (h->loss_h) cudaFreeHost(h->loss_h);
+  if (h->pub) { cudaStreamSynchronize(h->pub); cudaStreamDestroy(h->pub); }
+  if (h->ev_pub_snap) cudaEventDestroy(h->ev_pub_snap);
+  if (h->ev_pub_done) cudaEventDestroy(h->ev_pub_done);
+  cudaFree(h->pub_d);
+  if (h->pub_h) cudaFreeHost(h->pub_h);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->own) cudaStreamDestroy(h->own);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
@@ -1311,6 +1323,69 @@ struct StreamBridge {
     return 0;
   }
 };
+
+// ------------------------------------------------------------------------------------------
+// Publication path: Learner.get_parameters() -> pickle -> Redis runs after EVERY update in the reference
+// (LunarLander_Distributed_SAC/src/learner.py:272-276,298-299; MT10_Distributed_CARE/src/learner.py:412-417,442-443)
+// and costs one synchronous .cpu() per tensor.  Here: a device-to-device snapshot of the requested arena
+// ranges is enqueued in stream order (so it is the state after the steps enqueued so far, never a torn
+// one), the D2H copy into pinned memory runs on a private stream behind the next steps, and the host
+// only blocks in publish_wait.
+// ------------------------------------------------------------------------------------------
+extern "C" int b200sac_publish_begin(b200sac_t* h, int32_t replica, int32_t n_ranges, const int64_t* offsets, const int64_t* counts,
+                                     void* stream) {
+  if (!h || !offsets || !counts || n_ranges <= 0) return fail(B200SAC_ERR_INVALID, "bad argument");
+  if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica %d out of range", replica);
+  int64_t total = 0;
+  for (int i = 0; i < n_ranges; ++i) {
+    if (offsets[i] < 0 || counts[i] <= 0 || offsets[i] + counts[i] > h->L.arena)
+      return fail(B200SAC_ERR_INVALID, "range %d [%lld, +%lld) outside the %lld-float parameter arena", i, (long long)offsets[i],
+                  (long long)counts[i], (long long)h->L.arena);
+    total += counts[i];
+  }
+  CU(cudaSetDevice(h->device));
+  if (!h->pub) {
+    CU(cudaStreamCreateWithFlags(&h->pub, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_pub_snap, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_pub_done, cudaEventDisableTiming));
+  }
+  if (h->pub_pending) CU(cudaEventSynchronize(h->ev_pub_done));     // an unread snapshot is simply superseded
+  if (total > h->pub_cap) {
+    CU(cudaStreamSynchronize(h->pub));
+    cudaFree(h->pub_d); h->pub_d = nullptr;
+    if (h->pub_h) { cudaFreeHost(h->pub_h); h->pub_h = nullptr; }
+    CU(cudaMalloc(&h->pub_d, (size_t)total * sizeof(float)));
+    CU(cudaHostAlloc(&h->pub_h, (size_t)total * sizeof(float), cudaHostAllocDefault));
+    h->pub_cap = total;
+  }
+  StreamBridge sb(h, stream);
+  if (int rc = sb.begin()) return rc;
+  const float* base = h->params + (size_t)replica * h->L.arena;
+  int64_t at = 0;
+  for (int i = 0; i < n_ranges; ++i) {
+    CU(cudaMemcpyAsync(h->pub_d + at, base + offsets[i], (size_t)counts[i] * sizeof(float), cudaMemcpyDeviceToDevice, sb.run));
+    at += counts[i];
+  }
+  CU(cudaEventRecord(h->ev_pub_snap, sb.run));
+  if (int rc = sb.end()) return rc;
+  CU(cudaStreamWaitEvent(h->pub, h->ev_pub_snap, 0));
+  CU(cudaMemcpyAsync(h->pub_h, h->pub_d, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, h->pub));
+  CU(cudaEventRecord(h->ev_pub_done, h->pub));
+  h->pub_n = total;
+  h->pub_pending = true;
+  return 0;
+}
+
+extern "C" int b200sac_publish_wait(b200sac_t* h, const float** host_ptr, int64_t* n_floats) {
+  if (!h || !host_ptr || !n_floats) return fail(B200SAC_ERR_INVALID, "null argument");
+  if (!h->pub_pending) return fail(B200SAC_ERR_STATE, "publish_wait without publish_begin");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventSynchronize(h->ev_pub_done));
+  h->pub_pending = false;
+  *host_ptr = h->pub_h;
+  *n_floats = h->pub_n;
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // step variants.  variant 0: split device arrays; 1: packed rows (dense, staged); 2: replay gather

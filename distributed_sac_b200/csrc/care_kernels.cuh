@@ -41,7 +41,7 @@ struct CareTabArgs {
 // grid (T, n_inst, R), block 512: 16 warps, one output neuron per warp at a time, 8 independent
 // loads in flight per lane (the 768-long dot products are pure latency otherwise)
 __global__ void __launch_bounds__(512) care_tables_kernel(CareTabArgs P) {
-  kstamp();
+  KStamp ks_;
   __shared__ float xe[2048];
   __shared__ float bufA[512], bufB[512];
   const int t = blockIdx.x, inst = blockIdx.y, rep = blockIdx.z;
@@ -114,7 +114,7 @@ struct CareMixArgs {
 
 // one warp per row; grid (ceil(rows/8), R), block 256
 __global__ void __launch_bounds__(256) care_mix_kernel(CareMixArgs P) {
-  kstamp();
+  KStamp ks_;
   const int rep = blockIdx.y, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int r = blockIdx.x * 8 + warp;
   if (r >= P.rows) return;
@@ -151,7 +151,7 @@ struct CareMixBwdArgs {
 
 // one warp per row; grid (ceil(B/8), R)
 __global__ void __launch_bounds__(256) care_mix_bwd_kernel(CareMixBwdArgs P) {
-  kstamp();
+  KStamp ks_;
   const int rep = blockIdx.y, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int i = blockIdx.x * 8 + warp;
   if (i >= P.B) return;
@@ -193,7 +193,7 @@ struct CareTabReduceArgs {
 
 // grid (T, R), block 1024 = 16 row groups x 64 values; partial sums combined in a fixed order
 __global__ void __launch_bounds__(1024) care_tab_reduce_kernel(CareTabReduceArgs P) {
-  kstamp();
+  KStamp ks_;
   __shared__ float part[16][64];
   __shared__ float tot[64];
   const int t = blockIdx.x, rep = blockIdx.y;
@@ -247,7 +247,7 @@ struct CareTabWgradArgs {
 // grid (nblk, R), block 256.  Every CTA re-derives the (tiny) per-task backward chains in shared memory, then
 // takes a slice of the weight / bias gradient elements: dW_j[o][i] = sum_t dz_j[t][o] * a_{j-1}[t][i].
 __global__ void __launch_bounds__(256) care_tab_wgrad_kernel(CareTabWgradArgs P) {
-  kstamp();
+  KStamp ks_;
   extern __shared__ float sm[];
   const int rep = blockIdx.y, T = P.T;
   const float* __restrict__ par = P.params + rep * P.rsP;

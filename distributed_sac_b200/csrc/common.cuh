@@ -60,20 +60,34 @@ B200_D void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
 // true per-kernel times inside the CUDA graph (launch gaps included) -- unlike ncu's cold, serialised ones.
 struct StampBuf { unsigned long long* t; int* idx; int cap; };
 __device__ StampBuf g_stamp = {nullptr, nullptr, 0};
-// Every step kernel starts with kstamp(): (1) programmatic dependent launch -- wait until the
+// Every step kernel starts with `KStamp ks_;`: (1) programmatic dependent launch -- wait until the
 // predecessor grid has completed and flushed (no-op when launched without the PDL attribute), then let
 // the successor start launching right away (it blocks at its own wait), so launch latency overlaps
-// execution; (2) the optional timeline stamp.
-B200_D void kstamp() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (g_stamp.t != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    unsigned long long ns;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-    const int i = atomicAdd(g_stamp.idx, 1);
-    if (i < g_stamp.cap) g_stamp.t[i] = ns;
+// execution; (2) the optional timeline stamp.  The stamp's enable pointer lives in global memory; loading
+// it costs an L2 round trip, so thread 0 of CTA 0 only ISSUES the load at entry (with the entry time in a
+// register) and consumes it in the destructor, i.e. when the kernel is done -- nothing on the critical
+// path waits for it.
+struct KStamp {
+  unsigned long long t0;
+  unsigned long long* buf;
+  bool first;
+  B200_D KStamp() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    first = (threadIdx.x | threadIdx.y | blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+    t0 = 0; buf = nullptr;
+    if (first) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      buf = *(unsigned long long* volatile*)&g_stamp.t;
+    }
   }
-}
+  B200_D ~KStamp() {
+    if (first && buf != nullptr) {
+      const int i = atomicAdd(g_stamp.idx, 1);
+      if (i < g_stamp.cap) buf[i] = t0;
+    }
+  }
+};
 
 B200_D float warp_sum(float v) {
 #pragma unroll

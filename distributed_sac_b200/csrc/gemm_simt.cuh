@@ -122,8 +122,21 @@ B200_D void gs_compute(const float* __restrict__ As, const float* __restrict__ B
   }
 }
 
+#ifdef GS_PROF   // scripts/micro/simt_lat.cu only: %globaltimer at four points of CTA (0,0,0)
+__device__ unsigned long long g_gs_prof[4096];
+__device__ int g_gs_prof_n = 0;
+#define GS_MARK(i) do { if (prof_on) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_t[i])); } while (0)
+#else
+#define GS_MARK(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(GS_THREADS) gemm_simt_kernel(const __grid_constant__ GemmGroup grp) {
-  kstamp();
+  KStamp ks_;
+#ifdef GS_PROF
+  unsigned long long prof_t[4] = {0, 0, 0, 0};
+  const bool prof_on = (threadIdx.x | blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+#endif
+  GS_MARK(0);
   const int G = grp.G;
   const int g = blockIdx.z % G, rep = blockIdx.z / G;
   const GemmProb& P = grp.p[g];
@@ -146,6 +159,25 @@ __global__ void __launch_bounds__(GS_THREADS) gemm_simt_kernel(const __grid_cons
   float bsum = 0.f;   // WGRAD bias gradient, threads tid < 32 of the n-tile-0 CTAs
   const bool do_bsum = (P.mode == GEMM_WGRAD) && (P.C2 != nullptr) && (blockIdx.x == 0);
 
+  // Epilogue operands (bias row / ReLU mask) are fetched NOW, together with the first operand tiles, so the
+  // epilogue does not pay a second dependent L2 round trip.
+  float ebias[2] = {0.f, 0.f};
+  bool ekeep[2][2] = {{true, true}, {true, true}};
+  if (P.mode == GEMM_FWD && P.bias != nullptr) {
+    const float* __restrict__ bias = P.bias + (long long)rep * P.rsBias;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { const int n = n0 + tx + 16 * j; if (n < N) ebias[j] = __ldg(bias + n); }
+  } else if (P.mode == GEMM_DGRAD && P.mask != nullptr) {
+    const float* __restrict__ mask = P.mask + (long long)rep * P.rsMask;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+        if (m < M && n < N) ekeep[i][j] = __ldg(mask + (long long)m * P.ldmask + n) > 0.f;
+      }
+  }
+
   // Super-chunks of GS_INFLIGHT x 64 k columns: all loads of a super-chunk are issued before the first
   // is consumed, so a K <= 256 problem pays one global-memory round trip instead of one per chunk.
   for (int ks = 0; ks < K; ks += GS_KC * GS_INFLIGHT) {
@@ -166,6 +198,7 @@ __global__ void __launch_bounds__(GS_THREADS) gemm_simt_kernel(const __grid_cons
         gs_stash(As[buf], ak, tid, ra[c]);
         gs_stash(Bs[buf], bk, tid, rb[c]);
         __syncthreads();
+        if (c == 0 && ks == 0) GS_MARK(1);
         if (ak) {
           if (bk) gs_compute<true, true>(As[buf], Bs[buf], tx, ty, acc);
           else gs_compute<true, false>(As[buf], Bs[buf], tx, ty, acc);
@@ -181,9 +214,8 @@ __global__ void __launch_bounds__(GS_THREADS) gemm_simt_kernel(const __grid_cons
     __syncthreads();
   }
 
+  GS_MARK(2);
   float* __restrict__ C = P.C + (long long)rep * P.rsC;
-  const float* __restrict__ bias = P.bias ? P.bias + (long long)rep * P.rsBias : nullptr;
-  const float* __restrict__ mask = P.mask ? P.mask + (long long)rep * P.rsMask : nullptr;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int m = m0 + ty + 16 * i;
@@ -194,15 +226,22 @@ __global__ void __launch_bounds__(GS_THREADS) gemm_simt_kernel(const __grid_cons
       if (n >= N) continue;
       float v = acc[i][j];
       if (P.mode == GEMM_FWD) {
-        if (bias) v += bias[n];
+        v += ebias[j];
         if (P.relu) v = fmaxf(v, 0.f);
       } else if (P.mode == GEMM_DGRAD) {
-        if (mask && !(mask[(long long)m * P.ldmask + n] > 0.f)) v = 0.f;
+        if (!ekeep[i][j]) v = 0.f;
       }
       C[(long long)m * P.ldc + n] = v;
     }
   }
   if (do_bsum && tid < GS_T && (m0 + tid) < M) (P.C2 + (long long)rep * P.rsC2)[m0 + tid] = bsum;
+#ifdef GS_PROF
+  GS_MARK(3);
+  if (prof_on) {
+    const int i = atomicAdd(&g_gs_prof_n, 1);
+    if (i < 1024) for (int q = 0; q < 4; ++q) g_gs_prof[i * 4 + q] = prof_t[q];
+  }
+#endif
 }
 
 }  // namespace bsac

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
   using Cfg = TcCfg<BN>;
   constexpr int TC_BN = BN, TC_B_BYTES = Cfg::kBBytes, TC_STAGE_BYTES = Cfg::kStageBytes, TC_STAGES = Cfg::kStages,
                 TC_NMAIN = Cfg::kNMain;
-  kstamp();
+  KStamp ks_;
   extern __shared__ uint8_t smem_raw[];
   const TcProb* P = probs + blockIdx.z;
   const int M = P->M, N = P->N, K = P->K;

@@ -107,7 +107,7 @@ __global__ void ingest_split_kernel(StepConst K, IngestOut O, const float* __res
                                     const float* __restrict__ a, const float* __restrict__ r,
                                     const float* __restrict__ s2, const float* __restrict__ d,
                                     const float* __restrict__ eps_next, const float* __restrict__ eps_cur) {
-  kstamp();
+  KStamp ks_;
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
   const int B = K.B;
@@ -129,7 +129,7 @@ __global__ void ingest_split_kernel(StepConst K, IngestOut O, const float* __res
 // (device replay ring) or dense (pinned-host staging after the H2D copy).
 __global__ void ingest_rows_kernel(StepConst K, IngestOut O, const float* __restrict__ rows, long long rs_rows,
                                    int row_stride, const int* __restrict__ idx, long long rs_idx) {
-  kstamp();
+  KStamp ks_;
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
   const int B = K.B;
@@ -153,7 +153,7 @@ constexpr int kHashSlots = 4096;   // >= 2 * max batch (batch <= 2048)
 __global__ void sample_indices_kernel(StepConst K, const Counters* __restrict__ cnt, const long long* __restrict__ fill,
                                       long long cap_per_task, int* __restrict__ idx_out, long long rs_idx,
                                       unsigned long long seed) {
-  kstamp();
+  KStamp ks_;
   __shared__ int keys[kHashSlots];
   __shared__ int owner[kHashSlots];
   __shared__ int unresolved;
@@ -268,7 +268,7 @@ B200_D PolicyPoint policy_point(float mu, float raw, float eps, float k) {
 }
 
 __global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
-  kstamp();
+  KStamp ks_;
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int row = blockIdx.x * (blockDim.x / 32) + warp;
@@ -360,7 +360,7 @@ B200_D float warp_dot(const float* __restrict__ x, const float* __restrict__ w, 
 }
 
 __global__ void critic_heads_kernel(StepConst K, CriticHeadArgs P) {
-  kstamp();
+  KStamp ks_;
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int row = blockIdx.x * (blockDim.x / 32) + warp;
@@ -409,7 +409,7 @@ struct ActorQHeadArgs {
 };
 
 __global__ void actor_q_heads_kernel(StepConst K, ActorQHeadArgs P) {
-  kstamp();
+  KStamp ks_;
   const int rep = blockIdx.y;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int row = blockIdx.x * (blockDim.x / 32) + warp;
@@ -485,7 +485,7 @@ struct PolicyDoutArgs {
 
 // Large batches: compute the policy-head output gradient once (instead of in every head_bwd CTA).
 __global__ void __launch_bounds__(256) policy_dout_kernel(StepConst K, PolicyDoutArgs P) {
-  kstamp();
+  KStamp ks_;
   const int rep = blockIdx.y, A = K.act;
   const int e = blockIdx.x * 256 + threadIdx.x;
   if (e >= P.M * A) return;
@@ -506,7 +506,7 @@ constexpr int kHbCols = 8;     // hidden columns per CTA
 constexpr int kHbRows = 32;    // row groups per CTA (256 threads = 8 cols x 32 row groups)
 
 __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs P) {
-  kstamp();
+  KStamp ks_;
   extern __shared__ float sm[];
   const int net = blockIdx.y, rep = blockIdx.z;
   const int M = P.M, NO = P.NO, KD = P.Kdim;
@@ -652,7 +652,7 @@ B200_D void adam_one(float& p, float& m, float& v, float g, float w1, float b2, 
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
-  kstamp();
+  KStamp ks_;
   const int rep = blockIdx.y;
   __shared__ float red[256];
   __shared__ float s_ss, s_bc;

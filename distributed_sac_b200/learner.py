@@ -162,8 +162,23 @@ class _BaseLearner:
         while len(self.memory) <= self.start_memory_len:
             time.sleep(0.1)
 
+    # ---- parameter publication (LL/learner.py:272-276; consumed by Player.pull_parameters, player.py:75-85) ----
+    _published = ("actor",)
+
+    def publish_begin(self):
+        """Start an asynchronous snapshot of the published modules (b200sac_publish_begin): a device-side copy in
+        stream order after the steps enqueued so far, then D2H into pinned memory on a private stream."""
+        self._pub_maps = [(net, self._key_map(net)) for net in self._published]
+        self.core.publish_begin({canon for _, m in self._pub_maps for canon in m.values()})
+
+    def publish_wait(self):
+        named = self.core.publish_wait()
+        return {net: {ref: named[canon] for ref, canon in m.items()} for net, m in self._pub_maps}
+
     def get_parameters(self):
-        return {"actor": self._module_state_dict("actor")}
+        """{'actor': state_dict on the CPU} with the reference's key names -- only the published slices cross PCIe."""
+        self.publish_begin()
+        return self.publish_wait()
 
     def my_print(self, content):
         os.makedirs(os.path.dirname(self.log_file), exist_ok=True)
@@ -276,9 +291,11 @@ class _BaseLearner:
         for update_iteration in itertools.count():
             if update_iteration % self.update_delay != 0:
                 continue
-            res = self.update()
+            self.memory.enqueue_step(self.core)        # update(), split so the snapshot's D2H overlaps the loss read
+            self.publish_begin()
+            res = self._loss_tuple(self.core.read_losses(1)[0])
             self.server.set("update_iteration", _pickle.dumps(update_iteration))
-            self.server.set("parameters", _pickle.dumps(self.get_parameters()))
+            self.server.set("parameters", _pickle.dumps(self.publish_wait()))
             if self.write_mode:
                 self.write(update_iteration, *res)
                 if update_iteration % self.print_period == 0:
@@ -490,8 +507,7 @@ class CARELearner(MTSACLearner):
         which = 1 if "1" in net else 2
         return names.critic_key_map("MS", len(self.critic_hidden_dim) + 1, which, target="target" in net)
 
-    def get_parameters(self):
-        return {"context_encoder": self._module_state_dict("context_encoder"), "actor": self._module_state_dict("actor")}
+    _published = ("context_encoder", "actor")      # C10/learner.py:412-417
 
     def _critic_checkpoint_entries(self, named):
         d = super()._critic_checkpoint_entries(named)

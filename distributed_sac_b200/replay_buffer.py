@@ -73,9 +73,12 @@ class ReplayBuffer(threading.Thread):
         """(states, actions, rewards, next_states, dones) fp32 on `device` (replay_buffer.py:63-73)."""
         return tuple(t.to(self.device, non_blocking=False) for t in self.ring.sample())
 
-    def step_core(self, core):
-        """sample + one gradient step, fused in the library (pinned staging, side-stream H2D)."""
+    def enqueue_step(self, core):
+        """sample + one gradient step, fused in the library (pinned staging, side-stream H2D); asynchronous."""
         core.step_sampled(self.ring, 1)
+
+    def step_core(self, core):
+        self.enqueue_step(core)
         return core.read_losses(1)[0]
 
     def __len__(self):

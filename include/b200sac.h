@@ -17,6 +17,7 @@
  *                            build_model/build_optimizer/get_parameters/save_checkpoint
  *                            LunarLander_Distributed_SAC/src/learner.py:100-124,144-163,272-276
  *   b200sac_soft_update      Learner.soft_update()            learner.py:126-137
+ *   b200sac_publish_*        Learner.get_parameters()         learner.py:272-276 (called at :298-299)
  *
  * Conventions: plain pointers and sizes only (no torch types).  Every function
  * returns 0 on success or a negative b200sac_status; a message for the calling
@@ -155,6 +156,17 @@ int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host, void* str
 /* Polyak update of the target critics outside a step (Learner.soft_update; tau = 1 is
  * the hard copy Learner.run() does before training, learner.py:287-288). */
 int b200sac_soft_update(b200sac_t* h, double tau, void* stream);
+
+/* Publication path = Learner.get_parameters() (LunarLander_Distributed_SAC/src/learner.py:272-276,298-299;
+ * MT10_Distributed_CARE/src/learner.py:412-417,442-443), which the reference runs after every update.
+ * publish_begin enqueues, in stream order, a consistent device snapshot of `n_ranges` ranges
+ * [offsets[i], offsets[i]+counts[i]) of replica `replica`'s parameter arena (offsets from b200sac_layout)
+ * and starts its copy to pinned host memory on a private stream; it does not block, and steps enqueued
+ * afterwards overlap the copy.  publish_wait blocks until that copy has landed and returns the packed
+ * ranges; the pointer is owned by the handle and valid until the next publish_begin. */
+int b200sac_publish_begin(b200sac_t* h, int32_t replica, int32_t n_ranges, const int64_t* offsets, const int64_t* counts,
+                          void* stream);
+int b200sac_publish_wait(b200sac_t* h, const float** host_ptr, int64_t* n_floats);
 
 /* Debug / parity access to per-step intermediates of replica `replica`:
  * name in {"y","q1","q2","a_next","logp_next","a_cur","logp_cur","qmin","d_action","d_head","r","d"}. */

@@ -173,3 +173,27 @@ def test_care_learner_surface(cuda, tmp_path, modified):
     assert torch.equal(lrn2.core.export_arena(), before)
     lrn.memory.stop()
     lrn2.memory.stop()
+
+
+def test_publication_snapshot_is_consistent_and_async(cuda, tmp_path):
+    """get_parameters() through b200sac_publish_*: (1) bit-identical to the full-arena export; (2) a snapshot
+    begun after step k and collected after further steps were enqueued is the state after step k, not a torn
+    or later one (it is what an unmodified Player would load, LL/player.py:75-85)."""
+    lrn = _ll_learner(tmp_path, seed=11)
+    twin = _ll_learner(tmp_path, seed=11)
+    for l in (lrn, twin):
+        l.memory.ring.fill_synthetic(20000, seed=2)
+    for _ in range(3):
+        lrn.update(); twin.update()
+    full = lrn._module_state_dict("actor")                       # slow path: whole arena D2H
+    blob = lrn.get_parameters()["actor"]
+    assert set(blob) == set(full) and all(torch.equal(blob[k], full[k]) for k in full)
+    lrn.publish_begin()                                          # snapshot after step 3 ...
+    lrn.core.step_sampled(lrn.memory.ring, 40)                   # ... while 40 more steps are enqueued behind it
+    snap = lrn.publish_wait()["actor"]
+    assert all(torch.equal(snap[k], full[k]) for k in full)
+    twin.core.step_sampled(twin.memory.ring, 40)                 # same seed, same ring: replicas stay bit-identical
+    after, ref = lrn.get_parameters()["actor"], twin.get_parameters()["actor"]
+    assert all(torch.equal(after[k], ref[k]) for k in ref)
+    assert not torch.equal(after["mu_log_std_layer.weight"], full["mu_log_std_layer.weight"])
+    lrn.memory.stop(); twin.memory.stop()
