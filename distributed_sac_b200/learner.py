@@ -459,10 +459,10 @@ class CARELearner(MTSACLearner):
         cc.num_encoders = int(e["num_encoders"])
         cc.mix_hidden = [int(x) for x in e["hidden_dims_mixtureEnc"]]
         cc.mix_out = int(e["output_dim_mixtureEnc"])
-        cc.ctx_in = int(e["RoBERTa_embedding_dim"])
+        cc.ctx_in = int(e.get("RoBERTa_embedding_dim", 768))      # MT1_Distributed_CARE's cfg has no such key (width of the JSON rows)
         cc.ctx_hidden = [int(x) for x in e["hidden_dims_contextEnc"]]
         cc.ctx_out = int(e["output_dim_contextEnc"])
-        cc.tau_se = float(e["state_encoder_tau"])
+        cc.tau_se = float(e.get("state_encoder_tau", 0.05))        # hard-coded 0.05 in MT1_Distributed_CARE/src/learner.py:311
         cc.care_original = not self.use_modified_care     # CARE(O): trainable context encoder with its own Adam
         cc.emb_dim = int(e["embedding_dim_contextEnc"])
         cc.lr_ctx = float(e["lr_contextEnc"])

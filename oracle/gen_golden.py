@@ -199,10 +199,14 @@ def _care_named(lrn):
     return out
 
 
-def make_care_case(name, n_steps, cfg_overrides, seed=0, data_seed=4321):
+def make_care_case(name, n_steps, cfg_overrides, seed=0, data_seed=4321, variant="C10"):
     import care_port as cp
-    lrn, _ = rh.make_learner("C10", cfg_overrides, seed=seed)
-    enc = lrn.encoder_cfg
+    lrn, _ = rh.make_learner(variant, cfg_overrides, seed=seed)
+    enc = dict(lrn.encoder_cfg)
+    if variant == "C1":        # MT1_Distributed_CARE is CARE(O) with these two constants hard-coded
+        lrn.use_modified_care = False                                      # (no such switch in MT1/src/learner.py)
+        enc.setdefault("RoBERTa_embedding_dim", lrn.context_encoder.embedding[0].weight.shape[1])   # C1/context_encoder.py:30-36
+        enc.setdefault("state_encoder_tau", 0.05)                          # C1/learner.py:311
     lin = lambda seq: [m.out_features for m in seq if hasattr(m, "out_features")]
     spec = cp.CareSpec(state_dim=lrn.actor.state_dim, act_dim=lrn.actor.action_dim, num_tasks=lrn.num_tasks,
                        actor_hidden=lin(lrn.actor.mu_log_std_layer)[:-1], critic_hidden=lin(lrn.local_critic.Q_function_1)[:-1],
@@ -214,7 +218,7 @@ def make_care_case(name, n_steps, cfg_overrides, seed=0, data_seed=4321):
                        modified=bool(lrn.use_modified_care), emb_dim=int(enc["embedding_dim_contextEnc"]),
                        lr_ctx=float(enc["lr_contextEnc"]))
     named = _care_named(lrn)
-    d = {"spec": json.dumps(spec.to_json()), "family": "C10", "n_steps": n_steps}
+    d = {"spec": json.dumps(spec.to_json()), "family": variant, "n_steps": n_steps}
     for k, p in named.items():
         d["p_in/" + k] = p.detach().clone().numpy()
     trainable = [k for k in named if not (k.startswith("tse.") or "_target" in k or k == "embedding")]
@@ -278,6 +282,12 @@ CARE_CASES["care_o_small_s4"] = dict(n_steps=4, seed=8, cfg_overrides=dict(
     use_modified_care=False, batch_size=120, actor=dict(actor_hidden_dim=[64, 48, 32]), critic=dict(critic_hidden_dim=[40, 72, 56]),
     encoder=dict(hidden_dims_contextEnc=[24, 20], output_dim_contextEnc=12, embedding_dim_contextEnc=12,
                  hidden_dims_mixtureEnc=[28], output_dim_mixtureEnc=12, num_encoders=4)))
+
+# MT1_Distributed_CARE (one task, plain ReplayBuffer, CARE(O) arithmetic) driven through ITS OWN learner.py
+CARE_CASES["care_mt1_small_s3"] = dict(n_steps=3, seed=9, variant="C1", cfg_overrides=dict(
+    batch_size=96, actor=dict(actor_hidden_dim=[48, 40, 32]), critic=dict(critic_hidden_dim=[56, 44, 36]),
+    encoder=dict(hidden_dims_contextEnc=[20, 24], output_dim_contextEnc=12, embedding_dim_contextEnc=12,   # C1 asserts ctx_out == mix_out; trunk eats z
+                 hidden_dims_mixtureEnc=[24], output_dim_mixtureEnc=12, num_encoders=3)))
 
 CASES = {
     # full-size LunarLander learner, seeded Xavier init, distinct target nets, fresh Adam

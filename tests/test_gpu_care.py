@@ -16,7 +16,7 @@ def cuda():
     return torch.device("cuda", 0)
 
 
-@pytest.mark.parametrize("name", ["care_small_s4", "care_o_small_s4"], ids=["CARE(M)", "CARE(O)"])
+@pytest.mark.parametrize("name", ["care_small_s4", "care_o_small_s4", "care_mt1_small_s3"], ids=["CARE(M)", "CARE(O)", "MT1-CARE"])
 @pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "tc3xtf32"])
 def test_care_step_matches_reference_fixture(cuda, precision, name):
     from distributed_sac_b200 import _lib

@@ -8,7 +8,7 @@ from _golden import CareCase, REL, check_state, rel_l2, rel_scalar
 import pytest
 
 
-@pytest.mark.parametrize("name", ["care_small_s4", "care_o_small_s4"])
+@pytest.mark.parametrize("name", ["care_small_s4", "care_o_small_s4", "care_mt1_small_s3"])
 def test_care_port_matches_reference_fixture(name):
     c = CareCase(name)
     torch.set_num_threads(4)
