@@ -61,6 +61,7 @@ SYMBOLS = {
     "b200sac_profile_step": (C.c_int, [_VP, _VP, C.c_int32, _VP, C.c_int32, C.POINTER(C.c_int32), C.c_char_p, C.c_int32, _VP]),
     "b200sac_graph_timeline": (C.c_int, [_VP, _VP, C.c_int32, _VP, C.c_int32, C.POINTER(C.c_int32), _VP]),
     "b200sac_tc_gemm_test": (C.c_int, [C.c_int32] * 4 + [_VP, C.c_int32, _VP, C.c_int32, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, _VP]),
+    "b200sac_gemm_test": (C.c_int, [C.c_int32] * 5 + [_VP, C.c_int32, _VP, C.c_int32, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, _VP]),
     "b200sac_launches_per_step": (C.c_int, [_VP, C.POINTER(C.c_int32)]),
     "b200sac_replay_create": (C.c_int, [_VP, C.c_int64, C.c_int32, C.c_uint64, C.POINTER(_VP)]),
     "b200sac_replay_destroy": (C.c_int, [_VP]),

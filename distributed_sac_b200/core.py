@@ -153,15 +153,17 @@ class SacCore:
         return p.value, n.value
 
     def _unpack(self, name, flat, off):
-        """One layout-table entry read out of `flat` (a float32 tensor) at float offset `off`, in the reference's shape."""
+        """One layout-table entry read out of `flat` (float32 numpy array) at float offset `off`, as a fresh CPU tensor in
+        the reference's shape.  numpy copies on purpose: a 256x256 torch .clone() fans out to the intra-op thread pool,
+        which costs milliseconds on a busy host -- this runs after every update (publication path)."""
         _, rows, cols, _t, _o, pitch = self.table[name]
-        t = flat[off:off + rows * pitch].reshape(rows, pitch)[:, :cols].reshape(-1)
+        a = flat[off:off + rows * pitch].reshape(rows, pitch)[:, :cols]
         if ".mix." in name:            # stored as [K][out][in] | [K][out]; the reference holds (K,in,out) | (K,1,out)
             K = self.cfg.num_encoders
-            return (t.reshape(K, rows // K, cols).permute(0, 2, 1).contiguous() if name.endswith(".W")
-                    else t.reshape(K, 1, rows // K).clone())
-        is_mat = name.endswith(".weight") or name == "embedding"
-        return t.reshape(rows, cols).clone() if is_mat else t.clone()
+            a = (a.reshape(K, rows // K, cols).transpose(0, 2, 1) if name.endswith(".W") else a.reshape(K, 1, rows // K))
+        elif not (name.endswith(".weight") or name == "embedding"):
+            a = a.reshape(-1)
+        return torch.from_numpy(np.array(a, dtype=np.float32, order="C", copy=True))
 
     # ---- publication path (Learner.get_parameters, LL/learner.py:272-276) ---------------------------
     def publish_begin(self, tensor_names, replica=0):
@@ -184,12 +186,11 @@ class SacCore:
     def publish_wait(self) -> Dict[str, torch.Tensor]:
         ptr, n = C.POINTER(C.c_float)(), C.c_int64()
         _lib.check(self.lib.b200sac_publish_wait(self._h, C.byref(ptr), C.byref(n)))
-        import numpy as np
-        flat = torch.from_numpy(np.ctypeslib.as_array(ptr, shape=(n.value,)))     # view of the pinned buffer; _unpack clones
+        flat = np.ctypeslib.as_array(ptr, shape=(n.value,))       # view of the pinned buffer; _unpack copies out of it
         return {name: self._unpack(name, flat, at) for name, at in self._pub_where.items()}
 
     def get_named(self, which=_lib.PARAMS, replica=0) -> Dict[str, torch.Tensor]:
-        flat = self.export_arena(which, replica)
+        flat = self.export_arena(which, replica).numpy()
         return {name: self._unpack(name, flat, d[0]) for name, d in self.table.items() if which == _lib.PARAMS or d[3]}
 
     def set_named(self, tensors: Dict[str, torch.Tensor], which=_lib.PARAMS, replica=0, strict=True):

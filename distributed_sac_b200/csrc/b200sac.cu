@@ -21,6 +21,7 @@
 
 #include "../../include/b200sac.h"
 #include "gemm_simt.cuh"
+#include "gemm_thin.cuh"
 #include "gemm_tc.cuh"
 #include "sac_kernels.cuh"
 #include "care_kernels.cuh"
@@ -212,7 +213,7 @@ struct Buf {           // [R][n] fp32 (or int32) slab slice
   long long rs = 0;    // replica stride in floats
 };
 
-enum LaunchKind { L_POLICY_DOUT, L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
+enum LaunchKind { L_POLICY_DOUT, L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_THIN, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
 
 struct Launch {
   LaunchKind kind;
@@ -474,10 +475,21 @@ static int build_plan(b200sac* h) {
     }
     Launch l;
     int maxM = 0, maxN = 0;
-    for (auto& p : ps) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; }
+    bool thin = getenv("B200SAC_NO_THIN") == nullptr;
+    for (auto& p : ps) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; thin = thin && gemm_is_thin(p); }
     l.kind = L_GEMM_SMALL;
     l.grid = dim3((maxN + GS_T - 1) / GS_T, (maxM + GS_T - 1) / GS_T, (unsigned)(ps.size() * R));
     l.block = dim3(GS_THREADS);
+    if (thin) {        // input-layer weight / input gradients (N = obs+act <= 16): gemm_thin.cuh
+      int rows = 1;
+      for (auto& p : ps) {
+        const int per = p.mode == GEMM_WGRAD ? GT_ROWS_WGRAD : GT_ROWS_DGRAD, r = (p.M + per - 1) / per;
+        rows = r > rows ? r : rows;
+      }
+      l.kind = L_GEMM_THIN;
+      l.grid = dim3(1, rows, (unsigned)(ps.size() * R));
+      l.block = dim3(GT_THREADS);
+    }
     l.G = (int)ps.size();
     if (ps.size() > GS_MAXG) plan_rc = fail(B200SAC_ERR_INVALID, "internal: more than %d problems in one GEMM group", GS_MAXG);
     memset(&l.grp, 0, sizeof(l.grp));
@@ -930,7 +942,7 @@ static int build_plan(b200sac* h) {
   CU(cudaMalloc(&h->d_probs, h->h_probs.size() * sizeof(GemmProb)));
   CU(cudaMemcpy(h->d_probs, h->h_probs.data(), h->h_probs.size() * sizeof(GemmProb), cudaMemcpyHostToDevice));
   for (auto& l : h->plan) {
-    if (l.kind == L_GEMM_BIG || l.kind == L_GEMM_SMALL || l.kind == L_GEMM_TC) l.probs = h->d_probs + (size_t)(uintptr_t)l.probs;
+    if (l.kind == L_GEMM_BIG || l.kind == L_GEMM_SMALL || l.kind == L_GEMM_THIN || l.kind == L_GEMM_TC) l.probs = h->d_probs + (size_t)(uintptr_t)l.probs;
     if (l.kind == L_GEMM_TC) l.tprobs = h->d_tprobs + (size_t)(uintptr_t)l.tprobs;
   }
   size_t max_smem = 0;
@@ -983,6 +995,9 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
       case L_GEMM_BIG:
       case L_GEMM_SMALL:
         launch_k(gemm_simt_kernel, l.grid, l.block, 0, st, l.grp);
+        break;
+      case L_GEMM_THIN:
+        launch_k(gemm_thin_kernel, l.grid, l.block, 0, st, l.grp);
         break;
       case L_GEMM_TC:
         if (l.bn == 128) launch_k(gemm_tc_kernel<128>, l.grid, l.block, l.smem, st, l.tprobs);
@@ -1567,6 +1582,10 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
       if (p0.mode == GEMM_WGRAD) return "gemm_wgrad(ffma)";
       return "gemm_dgrad(ffma)";
     }
+    case L_GEMM_THIN: {
+      const GemmProb& p0 = hp[(size_t)(l.probs - dbase)];
+      return p0.mode == GEMM_WGRAD ? "gemm_wgrad(thin)" : "gemm_dgrad(thin)";
+    }
     case L_POLICY_DOUT: return "policy_dout";
     case L_CARE_TAB: return "care_tables";
     case L_CARE_MIX: return "care_mix";
@@ -1618,8 +1637,44 @@ extern "C" int b200sac_profile_step(b200sac_t* h, b200sac_replay_t* rb, int32_t 
   return sb.end();
 }
 
-// Stand-alone run of the tcgen05 GEMM kernel on caller-provided DEVICE arrays (parity tests).
+// Stand-alone run of one GEMM engine on caller-provided DEVICE arrays (parity tests):
+// engine 0 = 32x32-tile FFMA (gemm_simt.cuh), 1 = tcgen05 3xTF32 (gemm_tc.cuh), 2 = thin backward (gemm_thin.cuh).
+static int tc_gemm_test_impl(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B, int32_t ldb,
+                             const float* bias, const float* mask, int32_t ldmask, float* C, int32_t ldc, float* C2, int32_t relu,
+                             void* stream);
+extern "C" int b200sac_gemm_test(int32_t engine, int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
+                                 const float* B, int32_t ldb, const float* bias, const float* mask, int32_t ldmask, float* C,
+                                 int32_t ldc, float* C2, int32_t relu, void* stream) {
+  if (engine == 1) return tc_gemm_test_impl(mode, M, N, K, A, lda, B, ldb, bias, mask, ldmask, C, ldc, C2, relu, stream);
+  if (!A || !B || !C || M < 1 || N < 1 || K < 1 || mode < 0 || mode > 2) return fail(B200SAC_ERR_INVALID, "bad argument");
+  GemmGroup grp;
+  memset(&grp, 0, sizeof(grp));
+  grp.G = 1;
+  GemmProb& p = grp.p[0];
+  p.A = A; p.B = B; p.bias = bias; p.mask = mask; p.C = C; p.C2 = C2;
+  p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldmask = ldmask; p.mode = mode; p.relu = relu;
+  if (engine == 0) {
+    gemm_simt_kernel<<<dim3((N + GS_T - 1) / GS_T, (M + GS_T - 1) / GS_T, 1), GS_THREADS, 0, (cudaStream_t)stream>>>(grp);
+  } else if (engine == 2) {
+    if (!gemm_is_thin(p)) return fail(B200SAC_ERR_INVALID, "thin engine needs a backward problem with N <= %d", GT_NMAX);
+    const int per = mode == GEMM_WGRAD ? GT_ROWS_WGRAD : GT_ROWS_DGRAD;
+    gemm_thin_kernel<<<dim3(1, (M + per - 1) / per, 1), GT_THREADS, 0, (cudaStream_t)stream>>>(grp);
+  } else {
+    return fail(B200SAC_ERR_INVALID, "unknown GEMM engine %d", engine);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(B200SAC_ERR_CUDA, "GEMM engine %d failed: %s", engine, cudaGetErrorString(e));
+  return 0;
+}
+
 extern "C" int b200sac_tc_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
+                                    const float* B, int32_t ldb, const float* bias, const float* mask, int32_t ldmask,
+                                    float* C, int32_t ldc, float* C2, int32_t relu, void* stream) {
+  return tc_gemm_test_impl(mode, M, N, K, A, lda, B, ldb, bias, mask, ldmask, C, ldc, C2, relu, stream);
+}
+
+static int tc_gemm_test_impl(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
                                     const float* B, int32_t ldb, const float* bias, const float* mask, int32_t ldmask,
                                     float* C, int32_t ldc, float* C2, int32_t relu, void* stream) {
   if (!A || !B || !C) return fail(B200SAC_ERR_INVALID, "null argument");

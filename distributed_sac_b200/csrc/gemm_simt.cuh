@@ -92,9 +92,9 @@ B200_D void gs_stash(float* __restrict__ S, bool kcontig, int tid, const float4 
 }
 
 template <bool AK, bool BK>
-B200_D void gs_compute(const float* __restrict__ As, const float* __restrict__ Bs, int tx, int ty, float (&acc)[2][2]) {
+B200_D void gs_compute(const float* __restrict__ As, const float* __restrict__ Bs, int tx, int ty, int kend, float (&acc)[2][2]) {
 #pragma unroll 4
-  for (int k4 = 0; k4 < GS_KC; k4 += 4) {
+  for (int k4 = 0; k4 < kend; k4 += 4) {        // kend: valid k columns of this chunk rounded up to 4 (the tail is zero-filled)
     float a[2][4], b[2][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -199,15 +199,16 @@ __global__ void __launch_bounds__(GS_THREADS) gemm_simt_kernel(const __grid_cons
         gs_stash(Bs[buf], bk, tid, rb[c]);
         __syncthreads();
         if (c == 0 && ks == 0) GS_MARK(1);
+        const int kend = (K - k0 >= GS_KC) ? GS_KC : ((K - k0 + 3) & ~3);   // thin first layers: K = 8..53
         if (ak) {
-          if (bk) gs_compute<true, true>(As[buf], Bs[buf], tx, ty, acc);
-          else gs_compute<true, false>(As[buf], Bs[buf], tx, ty, acc);
+          if (bk) gs_compute<true, true>(As[buf], Bs[buf], tx, ty, kend, acc);
+          else gs_compute<true, false>(As[buf], Bs[buf], tx, ty, kend, acc);
         } else {
-          gs_compute<false, false>(As[buf], Bs[buf], tx, ty, acc);
+          gs_compute<false, false>(As[buf], Bs[buf], tx, ty, kend, acc);
         }
         if (do_bsum && tid < GS_T) {
 #pragma unroll 8
-          for (int kk = 0; kk < GS_KC; ++kk) bsum += As[buf][kk * GS_LDM + tid];
+          for (int kk = 0; kk < kend; ++kk) bsum += As[buf][kk * GS_LDM + tid];
         }
       }
     }

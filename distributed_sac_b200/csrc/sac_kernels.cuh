@@ -277,18 +277,47 @@ __global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
   const float* hr = P.h + rep * P.rsH + (long long)row * P.ldh;
   const float* W = P.W + rep * P.rsP;
   const float* bias = P.b + rep * P.rsP;
+  // the noise of this (row, action) does not depend on the head: fetch / generate it while the GEMV operands arrive
+  float e = 0.f;
+  if (lane < A) {
+    if (P.use_eps_buf) {
+      e = (P.eps + rep * P.rsEps)[(long long)row * A + lane];
+    } else {
+      Philox ph(K.seed ^ (0xA0761D6478BD642Full * (unsigned long long)(rep + 1)));
+      const long long step = P.cnt[rep].v[3];
+      uint32_t rnd[4];
+      ph((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)row, 0x51u + (uint32_t)lane, rnd);
+      float z0, z1;
+      box_muller(rnd[0], rnd[1], z0, z1);
+      e = z0;
+    }
+  }
+  float bj[kMaxHeadOut];
+#pragma unroll
+  for (int j = 0; j < kMaxHeadOut; ++j) bj[j] = j < NO ? bias[j] : 0.f;
   float acc[kMaxHeadOut];
 #pragma unroll
   for (int j = 0; j < kMaxHeadOut; ++j) acc[j] = 0.f;
-  for (int k = lane; k < H; k += 32) {
-    const float hv = hr[k];
+  for (int k0 = 0; k0 < H; k0 += 128) {       // four lane-strides of h and of every head row in flight per round trip
+    float hv[4], wv[4][kMaxHeadOut];
 #pragma unroll
-    for (int j = 0; j < kMaxHeadOut; ++j)
-      if (j < NO) acc[j] = fmaf(hv, __ldg(W + (long long)j * H + k), acc[j]);
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + lane + 32 * u;
+      hv[u] = k < H ? hr[k] : 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxHeadOut; ++j) wv[u][j] = (j < NO && k < H) ? __ldg(W + (long long)j * H + k) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (k0 + lane + 32 * u < H) {
+#pragma unroll
+        for (int j = 0; j < kMaxHeadOut; ++j)
+          if (j < NO) acc[j] = fmaf(hv[u], wv[u][j], acc[j]);
+      }
   }
 #pragma unroll
   for (int j = 0; j < kMaxHeadOut; ++j)
-    if (j < NO) acc[j] = warp_sum(acc[j]) + bias[j];
+    if (j < NO) acc[j] = warp_sum(acc[j]) + bj[j];
   // lane j < A owns action j
   float mu = 0.f, raw = 0.f;
 #pragma unroll
@@ -301,18 +330,6 @@ __global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
   }
   float lp = 0.f, lsd = 0.f;
   if (lane < A) {
-    float e;
-    if (P.use_eps_buf) {
-      e = (P.eps + rep * P.rsEps)[(long long)row * A + lane];
-    } else {
-      Philox ph(K.seed ^ (0xA0761D6478BD642Full * (unsigned long long)(rep + 1)));
-      const long long step = P.cnt[rep].v[3];
-      uint32_t rnd[4];
-      ph((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)row, 0x51u + (uint32_t)lane, rnd);
-      float z0, z1;
-      box_muller(rnd[0], rnd[1], z0, z1);
-      e = z0;
-    }
     const PolicyPoint p = policy_point(mu, raw, e, K.action_scale);
     lp = p.logp_j;
     lsd = p.logstd;
@@ -353,10 +370,26 @@ struct CriticHeadArgs {
   float* y; float* q; float* dq; float* lq; long long rsY;   // y[B], q[2][B], dq[2][B], lq[B]
 };
 
-B200_D float warp_dot(const float* __restrict__ x, const float* __restrict__ w, int n, int lane) {
+// Lane-strided dot product; eight strides (256 columns) of both operands are in flight before the first FMA so a
+// 256-wide head costs one memory round trip instead of eight.  Per-lane accumulation order is unchanged (k ascending).
+B200_D float warp_dot_partial(const float* __restrict__ x, const float* __restrict__ w, int n, int lane) {
   float a = 0.f;
-  for (int k = lane; k < n; k += 32) a = fmaf(x[k], __ldg(w + k), a);
-  return warp_sum(a);
+  for (int k0 = 0; k0 < n; k0 += 256) {
+    float xv[8], wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + lane + 32 * u;
+      xv[u] = k < n ? x[k] : 0.f;
+      wv[u] = k < n ? __ldg(w + k) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (k0 + lane + 32 * u < n) a = fmaf(xv[u], wv[u], a);
+  }
+  return a;
+}
+B200_D float warp_dot(const float* __restrict__ x, const float* __restrict__ w, int n, int lane) {
+  return warp_sum(warp_dot_partial(x, w, n, lane));
 }
 
 __global__ void critic_heads_kernel(StepConst K, CriticHeadArgs P) {
@@ -369,15 +402,17 @@ __global__ void critic_heads_kernel(StepConst K, CriticHeadArgs P) {
   const float* hT = P.hT + rep * P.rsHrep + (long long)row * P.ldh;
   const float* hQ = P.hQ + rep * P.rsHrep + (long long)row * P.ldh;
   const long long po = rep * P.rsP;
-  const float qt1 = warp_dot(hT, P.Wt[0] + po, H, lane) + (P.bt[0] + po)[0];
-  const float qt2 = warp_dot(hT + P.rsHnet, P.Wt[1] + po, H, lane) + (P.bt[1] + po)[0];
-  const float q1 = warp_dot(hQ, P.Wq[0] + po, H, lane) + (P.bq[0] + po)[0];
-  const float q2 = warp_dot(hQ + P.rsHnet, P.Wq[1] + po, H, lane) + (P.bq[1] + po)[0];
+  // per-row scalars and the four heads' operands are all requested before anything is consumed
+  const int t = (P.tid + rep * P.rsR)[row];
+  const float r = (P.r + rep * P.rsR)[row], d = (P.d + rep * P.rsR)[row];
+  const float lp = (P.logp + rep * P.rsLogp)[row];
+  const float b_t1 = (P.bt[0] + po)[0], b_t2 = (P.bt[1] + po)[0], b_q1 = (P.bq[0] + po)[0], b_q2 = (P.bq[1] + po)[0];
+  const float p_t1 = warp_dot_partial(hT, P.Wt[0] + po, H, lane), p_t2 = warp_dot_partial(hT + P.rsHnet, P.Wt[1] + po, H, lane);
+  const float p_q1 = warp_dot_partial(hQ, P.Wq[0] + po, H, lane), p_q2 = warp_dot_partial(hQ + P.rsHnet, P.Wq[1] + po, H, lane);
+  const float la_t = (P.log_alpha + po)[t];
+  const float qt1 = warp_sum(p_t1) + b_t1, qt2 = warp_sum(p_t2) + b_t2, q1 = warp_sum(p_q1) + b_q1, q2 = warp_sum(p_q2) + b_q2;
   if (lane == 0) {
-    const int t = (P.tid + rep * P.rsR)[row];
-    const float alpha = (float)exp((double)(P.log_alpha + po)[t]);
-    const float r = (P.r + rep * P.rsR)[row], d = (P.d + rep * P.rsR)[row];
-    const float lp = (P.logp + rep * P.rsLogp)[row];
+    const float alpha = (float)exp((double)la_t);
     const float t1 = K.reward_scale * r;
     const float t2 = K.gamma * (1.f - d);
     const float t3 = fminf(qt1, qt2) - alpha * lp;
@@ -417,12 +452,14 @@ __global__ void actor_q_heads_kernel(StepConst K, ActorQHeadArgs P) {
   if (row >= B) return;
   const float* hP = P.hP + rep * P.rsHrep + (long long)row * P.ldh;
   const long long po = rep * P.rsP;
-  const float q1 = warp_dot(hP, P.Wq[0] + po, H, lane) + (P.bq[0] + po)[0];
-  const float q2 = warp_dot(hP + P.rsHnet, P.Wq[1] + po, H, lane) + (P.bq[1] + po)[0];
+  const int t = (P.tid + rep * P.rsR)[row];
+  const float lp = (P.logp + rep * P.rsLogp)[row];
+  const float b_q1 = (P.bq[0] + po)[0], b_q2 = (P.bq[1] + po)[0];
+  const float p_q1 = warp_dot_partial(hP, P.Wq[0] + po, H, lane), p_q2 = warp_dot_partial(hP + P.rsHnet, P.Wq[1] + po, H, lane);
+  const float la_t = (P.log_alpha + po)[t];
+  const float q1 = warp_sum(p_q1) + b_q1, q2 = warp_sum(p_q2) + b_q2;
   if (lane == 0) {
-    const int t = (P.tid + rep * P.rsR)[row];
-    const float alpha = (float)exp((double)(P.log_alpha + po)[t]);
-    const float lp = (P.logp + rep * P.rsLogp)[row];
+    const float alpha = (float)exp((double)la_t);
     const float qm = fminf(q1, q2);
     float g1, g2;
     if (q1 == q2) { g1 = g2 = -0.5f * K.c_loss; }
@@ -588,19 +625,28 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
       for (int q = 0; q < kHbRows; ++q) ssum += red[(q * kHbCols + tx) * NO + ty];
       (P.dW[net] + rep * P.rsG)[(long long)ty * KD + kcol] = ssum;
     }
-    if (blockIdx.x == 0) {             // bias gradient: fixed-order tree over rows
+    if (blockIdx.x == 0) {             // bias gradient: per-thread row sums -> warp shuffle tree -> 8 warp partials (fixed order)
       __syncthreads();
-      for (int j = 0; j < NO; ++j) {
-        float ssum = 0.f;
-        for (int m = tid; m < M; m += 256) ssum += sd[m * NO + j];
-        red[tid] = ssum;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-          if (tid < o) red[tid] += red[tid + o];
-          __syncthreads();
+      float part[kMaxHeadOut];
+#pragma unroll
+      for (int j = 0; j < kMaxHeadOut; ++j) part[j] = 0.f;
+      for (int m = tid; m < M; m += 256) {
+#pragma unroll
+        for (int j = 0; j < kMaxHeadOut; ++j)
+          if (j < NO) part[j] += sd[m * NO + j];
+      }
+#pragma unroll
+      for (int j = 0; j < kMaxHeadOut; ++j)
+        if (j < NO) {
+          const float v = warp_sum(part[j]);
+          if ((tid & 31) == 0) red[(tid >> 5) * kMaxHeadOut + j] = v;
         }
-        if (tid == 0) (P.db[net] + rep * P.rsG)[j] = red[0];
-        __syncthreads();
+      __syncthreads();
+      if (tid < NO) {
+        float ssum = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) ssum += red[wq * kMaxHeadOut + tid];
+        (P.db[net] + rep * P.rsG)[tid] = ssum;
       }
     }
   }
@@ -701,47 +747,42 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
     return;
   }
   // ---- tail jobs (one CTA per replica) ----
-  const int tid = threadIdx.x, B = K.B;
-  auto block_sum = [&](float x) -> float {
-    red[tid] = x;
+  const int tid = threadIdx.x, B = K.B, lane = tid & 31, warp = tid >> 5;
+  // two block sums at once: warp shuffle trees, then the 8 warp partials in index order (fixed order -> reproducible)
+  auto block_sum2 = [&](float x, float y, float& sx, float& sy) {
+    x = warp_sum(x); y = warp_sum(y);
+    if (lane == 0) { red[warp] = x; red[8 + warp] = y; }
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (tid < o) red[tid] += red[tid + o];
-      __syncthreads();
-    }
-    const float r = red[0];
+    sx = 0.f; sy = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { sx += red[q]; sy += red[8 + q]; }
     __syncthreads();
-    return r;
   };
   const long long slot = (P.cnt[rep].v[3] - 1) % kLossSlots;
   float* L = P.losses + ((long long)slot * P.R + rep) * 4;
   float* LH = P.losses_host + ((long long)slot * P.R + rep) * 4;
   if (P.tail == TAIL_CRITIC_LOSS) {
-    float s = 0.f;
+    float s = 0.f, dummy;
     for (int i = tid; i < B; i += 256) s += (P.lq + rep * P.rsY)[i];
-    s = block_sum(s);
+    block_sum2(s, 0.f, s, dummy);
     if (tid == 0) { L[0] = s * K.c_loss; LH[0] = L[0]; }
     return;
   }
   // TAIL_ALPHA_AND_LOSSES: actor loss, entropy, temperature gradient + its Adam step
   {
+    const int Teff = K.T > 0 ? K.T : 1;
+    float* la = P.log_alpha + rep * P.rsP;
+    __shared__ float s_gs[64];
+    __shared__ float s_la[64], s_m[64], s_v[64];
+    // everything the serial part needs is requested up front, next to the reduction inputs
+    if (tid < Teff) { s_la[tid] = la[tid]; s_m[tid] = (P.m_alpha + rep * P.rsM)[tid]; s_v[tid] = (P.v_alpha + rep * P.rsM)[tid]; }
+    const double b1p = P.cnt[rep].b1p[2], b2p = P.cnt[rep].b2p[2];
     float s = 0.f, e = 0.f;
     for (int i = tid; i < B; i += 256) {
       s += (P.la + rep * P.rsY)[i];
       e += (P.logstd_sum + rep * P.rsLogp)[i];
     }
-    s = block_sum(s);
-    e = block_sum(e);
-    if (tid == 0) {
-      L[1] = s * K.c_loss;
-      L[3] = 0.5f * K.act * (1.0f + 1.8378770664093453f) + e * K.inv_B;   // 0.5 A (1+log 2pi) + mean(sum log_std)
-      LH[1] = L[1]; LH[3] = L[3];
-    }
-    const int Teff = K.T > 0 ? K.T : 1;
-    float* la = P.log_alpha + rep * P.rsP;
-    __shared__ float s_gs[64];
     {   // per-task sums of (logp + Hbar): one warp per task, lanes stride the rows, shuffle tree -> fixed order
-      const int warp = tid / 32, lane = tid % 32;
       const int* __restrict__ tv = P.tid + rep * P.rsR;
       const float* __restrict__ lp = P.logp_cur + rep * P.rsLogp;
       for (int t = warp; t < Teff; t += 8) {
@@ -752,22 +793,25 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
         if (lane == 0) s_gs[t] = gs;
       }
     }
-    __syncthreads();
-    float aloss = 0.f;
+    block_sum2(s, e, s, e);          // its barriers also publish s_gs / s_la / s_m / s_v
     if (tid == 0) {
+      L[1] = s * K.c_loss;
+      L[3] = 0.5f * K.act * (1.0f + 1.8378770664093453f) + e * K.inv_B;   // 0.5 A (1+log 2pi) + mean(sum log_std)
+      LH[1] = L[1]; LH[3] = L[3];
       float ss, bc;
-      adam_scalars(K.lr_alpha, P.cnt[rep].b1p[2], P.cnt[rep].b2p[2], ss, bc);
+      adam_scalars(K.lr_alpha, b1p, b2p, ss, bc);
+      float aloss = 0.f;
       for (int t = 0; t < Teff; ++t) {
         const float grad = -s_gs[t] * K.inv_B;         // d/dlog_alpha[t] of -mean(log_alpha_i (logp_i + Hbar))
-        aloss += la[t] * grad;                         // loss value = sum_t log_alpha[t] * grad[t]
+        aloss += s_la[t] * grad;                       // loss value = sum_t log_alpha[t] * grad[t]
         (P.g_alpha + rep * P.rsM)[t] = grad;
-        float pi = la[t], mi = (P.m_alpha + rep * P.rsM)[t], vi = (P.v_alpha + rep * P.rsM)[t];
+        float pi = s_la[t], mi = s_m[t], vi = s_v[t];
         adam_one(pi, mi, vi, grad, (float)(1.0 - K.beta1), (float)K.beta2, (float)(1.0 - K.beta2), ss, bc,
                  (float)K.adam_eps);
         la[t] = pi; (P.m_alpha + rep * P.rsM)[t] = mi; (P.v_alpha + rep * P.rsM)[t] = vi;
       }
+      L[2] = aloss; LH[2] = aloss;     // mapped pinned memory: visible to the host once the stream has drained
     }
-    if (tid == 0) { L[2] = aloss; LH[2] = aloss; __threadfence_system(); }
   }
 }
 

@@ -192,6 +192,12 @@ int b200sac_tc_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, const fl
                          int32_t ldb, const float* bias, const float* mask, int32_t ldmask, float* C, int32_t ldc,
                          float* C2, int32_t relu, void* stream);
 
+/* The same for any GEMM engine of the step: engine 0 = 32x32-tile fp32 FFMA, 1 = tcgen05 3xTF32,
+ * 2 = thin backward kernel (modes 1/2 with N <= 16: the input-layer weight / input gradients). */
+int b200sac_gemm_test(int32_t engine, int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
+                      const float* B, int32_t ldb, const float* bias, const float* mask, int32_t ldmask, float* C,
+                      int32_t ldc, float* C2, int32_t relu, void* stream);
+
 /* Number of kernels one step launches (for bench.py's gpu_launches accounting). */
 int b200sac_launches_per_step(b200sac_t* h, int32_t* n);
 
