@@ -1047,10 +1047,10 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   h->cfg = *cfg;
   h->device = device;
   h->R = cfg->replicas;
-  // measured on B200 (LL, one learner): PDL shortens the tcgen05 step (211 -> 201 us) but lengthens the
-  // FFMA one (158 -> 171 us: early-launched CTAs take slots from the draining predecessor)
-  g_use_pdl = (cfg->precision == 1);
+  // programmatic dependent launch with the exit-time trigger only (see common.cuh::KStamp); B200SAC_PDL=0 turns it off
+  g_use_pdl = true;
   if (const char* e = getenv("B200SAC_PDL")) g_use_pdl = (e[0] != '0');
+
   build_layout(cfg, h->L);
   const Layout& L = h->L;
   const int B = cfg->batch, R = h->R, A = cfg->act_dim, obs = cfg->state_dim + cfg->num_tasks, xw = L.in_w + A;

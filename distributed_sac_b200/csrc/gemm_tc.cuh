@@ -48,7 +48,12 @@ struct TcCfg {
   static constexpr int kBBytes = BN * TC_BK * 4;                           // 8 / 16 KiB
   static constexpr int kStageBytes = 2 * (TC_A_BYTES + kBBytes);           // hi + lo of both operands: 48 / 64 KiB
   static constexpr int kStages = BN == 64 ? 4 : 3;
-  static constexpr int kNMain = BN == 64 ? 6 : 3;                          // (kNMain + 1) * BN <= 512 TMEM columns
+  // BN = 64: "paired" accumulators [main_i | cross_i] (2*BN columns each, 4 pairs) fed by ONE N=128 MMA per k step
+  // whose B operand spans the hi tile and the lo tile behind it (A_hi * [B_hi ; B_lo]) plus one N=64 MMA
+  // (A_lo * B_hi -> cross_i): 2 instead of 3 tcgen05.mma per k step, and an MMA costs ~105 cycles whatever its N <= 128
+  // (measured, scripts/micro/mma_rate.cu).  BN = 128 keeps 3 mains + 1 shared cross accumulator (an N=256 MMA costs 171).
+  static constexpr bool kPaired = BN == 64;
+  static constexpr int kNMain = BN == 64 ? 4 : 3;                          // TMEM: 4 * 128 | (3 + 1) * 128 = 512 columns
   static constexpr int kSmemBytes = kStages * kStageBytes + TC_BSUM_BYTES + 256 + 1024;   // + barriers + align slack
 };
 constexpr int TC_BN = 64;            // default tile width (descriptor-eligibility bounds, tests)
@@ -201,6 +206,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
   const int a_mn = P->a_mn, b_mn = P->b_mn;
 
   if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P->tmA) : "memory");    // descriptor fetch overlaps the barrier / TMEM setup
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P->tmB) : "memory");
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(ready_bar(s), TC_SPLIT_THREADS);
@@ -261,15 +268,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         const uint64_t dB0 = tc_smem_desc(st + 2 * TC_A_BYTES, b_mn ? 4096u : 16u, b_mn ? 512u : 1024u, b_mn ? 1u : 2u);
         const uint64_t stepA = a_mn ? (1024u >> 4) : (32u >> 4), stepB = b_mn ? (1024u >> 4) : (32u >> 4);
         const int mi = (kc * nmain) / nk;
-        const uint32_t d_main = tmem_base + (uint32_t)(TC_BN * mi), d_cross = tmem_base + (uint32_t)(TC_BN * TC_NMAIN);
         const bool new_main = (kc == 0) || (((kc - 1) * nmain) / nk != mi);
+        if (Cfg::kPaired) {
+          const uint32_t d_pair = tmem_base + (uint32_t)(2 * TC_BN * mi);       // [main_mi | cross_mi]
+          const uint32_t idesc2 = tc_instr_desc(a_mn, b_mn, 2 * TC_BN);
 #pragma unroll
-        for (int ks = 0; ks < TC_BK / 8; ++ks) {
-          const uint64_t dAh = dA0 + stepA * ks, dAl = dAh + (TC_A_BYTES >> 4);
-          const uint64_t dBh = dB0 + stepB * ks, dBl = dBh + (TC_B_BYTES >> 4);
-          tc_mma_tf32(d_cross, dAh, dBl, idesc, (kc | ks) != 0 ? 1u : 0u);
-          tc_mma_tf32(d_cross, dAl, dBh, idesc, 1u);
-          tc_mma_tf32(d_main, dAh, dBh, idesc, (new_main && ks == 0) ? 0u : 1u);
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t dAh = dA0 + stepA * ks, dAl = dAh + (TC_A_BYTES >> 4);
+            const uint64_t dBh = dB0 + stepB * ks;                              // N = 2*BN: hi rows, then the lo tile behind them
+            tc_mma_tf32(d_pair, dAh, dBh, idesc2, (new_main && ks == 0) ? 0u : 1u);   // main += Ah*Bh ; cross += Ah*Bl
+            tc_mma_tf32(d_pair + TC_BN, dAl, dBh, idesc, 1u);                          // cross += Al*Bh
+          }
+        } else {
+          const uint32_t d_main = tmem_base + (uint32_t)(TC_BN * mi), d_cross = tmem_base + (uint32_t)(TC_BN * TC_NMAIN);
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t dAh = dA0 + stepA * ks, dAl = dAh + (TC_A_BYTES >> 4);
+            const uint64_t dBh = dB0 + stepB * ks, dBl = dBh + (TC_B_BYTES >> 4);
+            tc_mma_tf32(d_cross, dAh, dBl, idesc, (kc | ks) != 0 ? 1u : 0u);
+            tc_mma_tf32(d_cross, dAl, dBh, idesc, 1u);
+            tc_mma_tf32(d_main, dAh, dBh, idesc, (new_main && ks == 0) ? 0u : 1u);
+          }
         }
         tc_commit(empty_bar(s));          // smem stage reusable once these MMAs have read it
         if (kc < 16) TC_STAMP(51 + 2 * kc);
@@ -350,15 +369,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
     }
 
     // ---- epilogue: TMEM -> registers -> global ----
-    mbar_wait(accum_bar, 0);
-    if (t == 0) TC_STAMP(82);
-    tc_fence_after();
     const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
     const int mode = P->mode, relu = P->relu, ldc = P->ldc;
     const float* __restrict__ bias = P->bias;
     const float* __restrict__ mask = P->mask;
     float* __restrict__ Cout = P->C;
     const int ldmask = P->ldmask;
+    // Output pass layout: one warp instruction covers 4 rows x 32 columns, lane = (row r0 + lane/8, column quad lane%8), so
+    // global stores and mask loads are 128-bit and a 32x32 block takes 8 of them instead of 32 (measured: ~45 cycles per
+    // store instruction in the 32-bit version = 1.5k cycles per block).
+    const int rsub = lane >> 3, c4 = (lane & 7) << 2;
+    const bool vec_c = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
+    const bool vec_m = mask && ((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+    float4 bvs[TC_BN / 32];                                   // this lane's bias quad per block, requested while the MMAs still run
+#pragma unroll
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      const int n = n0 + c * 32 + c4;
+      bvs[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mode == GEMM_FWD && bias) {
+        if (n < N) bvs[c].x = __ldg(bias + n);
+        if (n + 1 < N) bvs[c].y = __ldg(bias + n + 1);
+        if (n + 2 < N) bvs[c].z = __ldg(bias + n + 2);
+        if (n + 3 < N) bvs[c].w = __ldg(bias + n + 3);
+      }
+    }
+    mbar_wait(accum_bar, 0);
+    if (t == 0) TC_STAMP(82);
+    tc_fence_after();
     const int nmain = tc_nmain(nk, TC_NMAIN);
     // All MMAs have completed (accum barrier), so the pipeline stages are free: each warp transposes its
     // 32x32 block through a padded smem scratch so that global stores / mask loads are row-contiguous.
@@ -366,46 +403,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
 #pragma unroll
     for (int c = 0; c < TC_BN / 32; ++c) {
       uint32_t v[32], w[32];
+      float4 mkv[8];                                          // ReLU' mask quads of this lane's 8 output rows, in flight during the TMEM loads
+      if (mode == GEMM_DGRAD && mask) {
+        const int n_ = n0 + c * 32 + c4;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int m_ = m0 + q * 32 + 4 * u + rsub;
+          const float* __restrict__ mp_ = mask + (long long)m_ * ldmask + n_;
+          float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (m_ < M) {
+            if (vec_m && n_ + 3 < N) {
+              mk = __ldg(reinterpret_cast<const float4*>(mp_));
+            } else {
+              if (n_ < N) mk.x = ldg_f32(mp_);
+              if (n_ + 1 < N) mk.y = ldg_f32(mp_ + 1);
+              if (n_ + 2 < N) mk.z = ldg_f32(mp_ + 2);
+              if (n_ + 3 < N) mk.w = ldg_f32(mp_ + 3);
+            }
+          }
+          mkv[u] = mk;
+        }
+      }
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      const uint32_t acc_stride = Cfg::kPaired ? 2u * TC_BN : (uint32_t)TC_BN;
       tc_ld32(lane_addr, v);                                  // main[0]
       if (t == 0 && c == 0) TC_STAMP(85);
       for (int mi = 1; mi < nmain; ++mi) {
-        tc_ld32(lane_addr + (uint32_t)(TC_BN * mi), w);
+        tc_ld32(lane_addr + acc_stride * (uint32_t)mi, w);
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
       }
-      tc_ld32(lane_addr + (uint32_t)(TC_BN * TC_NMAIN), w);   // cross terms
+      if (Cfg::kPaired) {                                     // cross terms: one accumulator per pair, summed first (tiny values)
+        tc_ld32(lane_addr + (uint32_t)TC_BN, w);
+        for (int mi = 1; mi < nmain; ++mi) {
+          uint32_t w2[32];
+          tc_ld32(lane_addr + acc_stride * (uint32_t)mi + (uint32_t)TC_BN, w2);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) w[jj] = __float_as_uint(__uint_as_float(w[jj]) + __uint_as_float(w2[jj]));
+        }
+      } else {
+        tc_ld32(lane_addr + (uint32_t)(TC_BN * TC_NMAIN), w);   // cross terms
+      }
       if (t == 0 && c == 0) TC_STAMP(86);
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) scratch[lane * 33 + jj] = __uint_as_float(v[jj]) + __uint_as_float(w[jj]);
       __syncwarp();
       if (t == 0 && c == 0) TC_STAMP(87);
-      const int n = n0 + c * 32 + lane;                       // this lane's output column
-      const bool nin = n < N;
-      const float bv = (mode == GEMM_FWD && bias && nin) ? __ldg(bias + n) : 0.f;
+      const int n = n0 + c * 32 + c4;                         // first of this lane's four output columns
+      const float4 bv = bvs[c];
       const int mrow0 = m0 + q * 32;
-      float* __restrict__ cptr = Cout + (long long)mrow0 * ldc + n;
-      const float* __restrict__ mptr = mask ? mask + (long long)mrow0 * ldmask + n : nullptr;
 #pragma unroll
-      for (int r0 = 0; r0 < 32; r0 += 8) {
-        float x[8], mk[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = scratch[(r0 + u) * 33 + lane];
-        if (mode == GEMM_DGRAD && mptr) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) mk[u] = (nin && mrow0 + r0 + u < M) ? ldg_f32(mptr + (long long)(r0 + u) * ldmask) : 1.f;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) x[u] = mk[u] > 0.f ? x[u] : 0.f;
+      for (int u = 0; u < 8; ++u) {
+        const int row = 4 * u + rsub, m = mrow0 + row;
+        float4 x;
+        x.x = scratch[row * 33 + c4]; x.y = scratch[row * 33 + c4 + 1]; x.z = scratch[row * 33 + c4 + 2]; x.w = scratch[row * 33 + c4 + 3];
+        if (mode == GEMM_DGRAD && mask) {
+          x.x = mkv[u].x > 0.f ? x.x : 0.f; x.y = mkv[u].y > 0.f ? x.y : 0.f;
+          x.z = mkv[u].z > 0.f ? x.z : 0.f; x.w = mkv[u].w > 0.f ? x.w : 0.f;
         } else if (mode == GEMM_FWD) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            x[u] += bv;
-            if (relu) x[u] = fmaxf(x[u], 0.f);
+          x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+          if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+        }
+        if (m < M) {
+          float* __restrict__ cp = Cout + (long long)m * ldc + n;
+          if (vec_c && n + 3 < N) {
+            asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+          } else {
+            if (n < N) stg_f32(cp, x.x);
+            if (n + 1 < N) stg_f32(cp + 1, x.y);
+            if (n + 2 < N) stg_f32(cp + 2, x.z);
+            if (n + 3 < N) stg_f32(cp + 3, x.w);
           }
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (nin && mrow0 + r0 + u < M) stg_f32(cptr + (long long)(r0 + u) * ldc, x[u]);
       }
       __syncwarp();
       if (t == 0 && c == 0) TC_STAMP(88);
