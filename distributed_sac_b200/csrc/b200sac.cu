@@ -278,6 +278,9 @@ struct b200sac {
   std::vector<Launch> plan;
   IngestOut ing;
   int use_eps_buf_idx = -1;       // index of the policy launch in plan (its use_eps_buf flag varies)
+  // split-K weight gradients: slices 1..gslices-1 of the gradient arena, [slice-1][R][trainable] (slice 0 = grads)
+  float* grads_x = nullptr;
+  int gslices = 1;
   // graphs
   std::map<GraphKey, cudaGraphExec_t> graphs;
   // host staging for step_host / pinned replay
@@ -336,7 +339,7 @@ static int destroy_impl(b200sac* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
-  cudaFree(h->params); cudaFree(h->adam_m); cudaFree(h->adam_v); cudaFree(h->grads);
+  cudaFree(h->params); cudaFree(h->adam_m); cudaFree(h->adam_v); cudaFree(h->grads); cudaFree(h->grads_x);
   cudaFree(h->cnt); cudaFree(h->losses); cudaFree(h->slab); cudaFree(h->d_probs); cudaFree(h->d_tprobs);
   for (int i = 0; i < 2; ++i) {
     if (h->stage_h[i]) cudaFreeHost(h->stage_h[i]);
@@ -395,6 +398,8 @@ static bool tc_eligible(const GemmProb& p) {
   return p.M >= 32 && p.N >= 32 && p.K >= 32;
 }
 
+constexpr int kSplitK = 4, kSplitKMin = 512;     // weight gradients with K >= 512 rows are computed in 4 K slices
+
 static int make_tc_prob(const GemmProb& p, int rep, TcProb& t, int bn = 64) {
   memset(&t, 0, sizeof(t));
   const float* A = p.A + (long long)rep * p.rsA;
@@ -434,7 +439,57 @@ static int build_plan(b200sac* h) {
 
   int plan_rc = 0;
   std::function<void(std::vector<GemmProb>)> gemm_launch_ref;
-  auto gemm_launch = [&](std::vector<GemmProb> ps) {
+  auto gemm_launch = [&](std::vector<GemmProb> ps_in) {
+    // Split-K for the weight gradients: K = batch (1024 / 1280) is the long dimension and M x N = out x in gives only a
+    // handful of tiles, so one CTA would walk 32-40 k chunks alone (measured 26-32 us per launch at the 400-wide shapes).
+    // WGRAD operands are both [K][*] row-major, so a K slice is just a row offset: slice s of a problem becomes its own
+    // problem writing gradient slice s; Adam adds the slices in index order (deterministic, no atomics).
+    auto expand = [&](int Smax, std::vector<GemmProb>& out) {
+      for (auto& p : ps_in) {
+        const int S = (p.mode == GEMM_WGRAD && p.K >= kSplitKMin && h->gslices > 1) ? Smax : 1;
+        if (S == 1) { out.push_back(p); continue; }
+        const int len = (((p.K + S - 1) / S) + 31) & ~31;
+        const long long coff = p.C - h->grads, c2off = p.C2 ? p.C2 - h->grads : 0;
+        if (coff < 0 || coff >= L.trainable) { plan_rc = fail(B200SAC_ERR_INVALID, "internal: split-K output outside the gradient arena"); out.push_back(p); continue; }
+        for (int sidx = 0; sidx < S; ++sidx) {
+          const int kb = sidx * len;
+          if (kb >= p.K) break;
+          GemmProb q = p;
+          q.A = p.A + (long long)kb * p.lda; q.B = p.B + (long long)kb * p.ldb;
+          q.K = (p.K - kb < len) ? p.K - kb : len;
+          if (sidx > 0) {
+            float* base = h->grads_x + (long long)(sidx - 1) * R * L.trainable;
+            q.C = base + coff;
+            if (p.C2) q.C2 = base + c2off;
+          }
+          out.push_back(q);
+        }
+      }
+    };
+    // tcgen05 tiles hold one CTA per SM: take the finest split whose launch still fits one wave of 148 CTAs (a second
+    // wave costs more than the shorter k loop saves); the FFMA engine (several CTAs per SM) always takes the finest.
+    auto tc_ctas = [&](const std::vector<GemmProb>& v) {
+      long long c128 = 0, c64 = 0;
+      int maxN = 0;
+      for (auto& p : v) {
+        if (!tc_eligible(p)) continue;
+        c128 += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + 127) / 128);
+        c64 += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + 63) / 64);
+        maxN = p.N > maxN ? p.N : maxN;
+      }
+      return ((maxN >= 256 && c128 * R >= 96) ? c128 : c64) * R;
+    };
+    std::vector<GemmProb> ps;
+    {
+      int S = kSplitK;
+      if (c.precision == 1)
+        for (; S > 1; S >>= 1) {
+          std::vector<GemmProb> trial;
+          expand(S, trial);
+          if (tc_ctas(trial) <= 148) break;
+        }
+      expand(S, ps);
+    }
     if (c.precision == 1) {
       std::vector<GemmProb> tc, rest;
       for (auto& p : ps) (tc_eligible(p) ? tc : rest).push_back(p);
@@ -849,6 +904,7 @@ static int build_plan(b200sac* h) {
     const int64_t n = which == 0 ? L.critic_n : (which == 1 ? L.actor_n : L.cenc_n);
     P.p = h->params + beg; P.m = h->adam_m + beg; P.v = h->adam_v + beg; P.g = h->grads + beg;
     P.rsP = rsP; P.rsM = rsG; P.n = n;
+    P.gx = h->grads_x ? h->grads_x + beg : nullptr; P.xs = (long long)R * L.trainable; P.nx = h->gslices - 1;
     P.target_delta = which == 0 ? L.target_delta : 0;
     P.tau2_begin = (which == 0 && c.care) ? (L.cse_begin - L.critic_begin) : (long long)1 << 60;
     P.tau2 = (float)c.tau_se; P.one_minus_tau2 = (float)(1.0 - c.tau_se);
@@ -1092,6 +1148,11 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   CUH(cudaMemset(h->adam_m, 0, sizeof(float) * L.trainable * R));
   CUH(cudaMemset(h->adam_v, 0, sizeof(float) * L.trainable * R));
   CUH(cudaMemset(h->grads, 0, sizeof(float) * L.trainable * R));
+  h->gslices = (cfg->batch >= kSplitKMin && getenv("B200SAC_NO_SPLITK") == nullptr) ? kSplitK : 1;   // K of every weight gradient = batch
+  if (h->gslices > 1) {     // never-written entries of slices >= 1 must read as zero (Adam sums all slices)
+    CUH(cudaMalloc(&h->grads_x, sizeof(float) * L.trainable * R * (h->gslices - 1)));
+    CUH(cudaMemset(h->grads_x, 0, sizeof(float) * L.trainable * R * (h->gslices - 1)));
+  }
   {
     std::vector<Counters> c0((size_t)R);
     for (auto& c : c0) { memset(&c, 0, sizeof(c)); for (int i = 0; i < 5; ++i) c.b1p[i] = c.b2p[i] = 1.0; }
@@ -1274,6 +1335,18 @@ extern "C" int b200sac_export(b200sac_t* h, int32_t which, int32_t replica, floa
   CU(cudaSetDevice(h->device));
   CU(cudaMemcpyAsync(buf, p + (size_t)replica * n, n * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
   CU(cudaStreamSynchronize((cudaStream_t)stream));
+  if (which == B200SAC_GRADS && h->gslices > 1) {       // split-K slices: the gradient is their sum (same order as Adam's)
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, buf) != cudaSuccess || at.type == cudaMemoryTypeDevice) {
+      cudaGetLastError();
+      return fail(B200SAC_ERR_INVALID, "exporting split-K gradients needs a host buffer");
+    }
+    std::vector<float> tmp((size_t)n);
+    for (int sidx = 1; sidx < h->gslices; ++sidx) {
+      CU(cudaMemcpy(tmp.data(), h->grads_x + ((size_t)(sidx - 1) * h->R + replica) * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < n; ++i) buf[i] += tmp[(size_t)i];
+    }
+  }
   return 0;
 }
 

@@ -45,7 +45,7 @@ constexpr int GS_LDK = GS_KC + 4;      // row pitch of a K-contiguous operand ti
 constexpr int GS_LDM = GS_T + 4;       // row pitch of an MN-contiguous operand tile [64][36]
 constexpr int GS_TILE_FLOATS = (GS_T * GS_LDK > GS_KC * GS_LDM) ? GS_T * GS_LDK : GS_KC * GS_LDM;   // 2304
 constexpr int GS_THREADS = 256;
-constexpr int GS_MAXG = 12;            // problems per launch (descriptors travel as kernel parameters)
+constexpr int GS_MAXG = 24;            // problems per launch (descriptors travel as kernel parameters)
 constexpr int GS_INFLIGHT = 4;         // k chunks whose loads are issued before the first is consumed
 
 struct GemmGroup {

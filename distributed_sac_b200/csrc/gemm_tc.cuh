@@ -228,27 +228,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
+    // MN-major operands need one 32-wide box per 32 rows/columns (up to 8 boxes per stage).  A single thread issues a
+    // cp.async.bulk.tensor only every ~250 cycles (measured), which made those stages issue-bound, so the boxes of a
+    // stage are issued by different lanes of this warp in ONE warp instruction.
+    const int nA = a_mn ? TC_BM / 32 : 1, nB = b_mn ? TC_BN / 32 : 1;
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % TC_STAGES;
+      const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
+      if (lane == 0) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         if (kc < 16) TC_STAMP(2 + kc);
-        const uint32_t st = base + (uint32_t)s * TC_STAGE_BYTES;
-        const uint32_t dA = st, dB = st + 2 * TC_A_BYTES;
         mbar_expect_tx(full_bar(s), TC_A_BYTES + TC_B_BYTES);
-        const int k0 = kc * TC_BK;
-        if (!a_mn) {
-          tma_load_2d(dA, &P->tmA, k0, m0, full_bar(s));
-        } else {
-          for (int g = 0; g < TC_BM / 32; ++g) tma_load_2d(dA + g * 4096, &P->tmA, m0 + 32 * g, k0, full_bar(s));
-        }
-        if (!b_mn) {
-          tma_load_2d(dB, &P->tmB, k0, n0, full_bar(s));
-        } else {
-          for (int g = 0; g < TC_BN / 32; ++g) tma_load_2d(dB + g * 4096, &P->tmB, n0 + 32 * g, k0, full_bar(s));
-        }
       }
+      __syncwarp();
+      const uint32_t st = base + (uint32_t)s * TC_STAGE_BYTES;
+      const uint32_t dA = st, dB = st + 2 * TC_A_BYTES;
+      const int k0 = kc * TC_BK;
+      if (lane < nA) {
+        if (!a_mn) tma_load_2d(dA, &P->tmA, k0, m0, full_bar(s));
+        else tma_load_2d(dA + lane * 4096, &P->tmA, m0 + 32 * lane, k0, full_bar(s));
+      } else if (lane < nA + nB) {
+        const int g = lane - nA;
+        if (!b_mn) tma_load_2d(dB, &P->tmB, k0, n0, full_bar(s));
+        else tma_load_2d(dB + g * 4096, &P->tmB, n0 + 32 * g, k0, full_bar(s));
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================

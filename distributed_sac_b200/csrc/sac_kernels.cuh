@@ -664,6 +664,7 @@ enum { TAIL_NONE = 0, TAIL_CRITIC_LOSS = 1, TAIL_ALPHA_AND_LOSSES = 2 };
 
 struct AdamArgs {
   float* p; float* m; float* v; const float* g;     // slice bases (replica 0)
+  const float* gx; long long xs; int nx;             // nx extra gradient slices (split-K weight gradients), slice stride xs
   long long rsP, rsM;                                // replica strides: param arena / trainable arena
   long long n;
   long long target_delta;                            // p[i + target_delta] is the Polyak target (0 = none)
@@ -728,7 +729,11 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
     float4* __restrict__ t4 = P.target_delta != 0 ? reinterpret_cast<float4*>(p + P.target_delta) : nullptr;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)nb * 256) {
       float4 pv = p4[i], mv = m4[i], vv = v4[i];
-      const float4 gv = g4[i];
+      float4 gv = g4[i];
+      for (int sx = 0; sx < P.nx; ++sx) {            // split-K slices, added in index order
+        const float4 ge = reinterpret_cast<const float4*>(P.gx + rep * P.rsM + (long long)sx * P.xs)[i];
+        gv.x += ge.x; gv.y += ge.y; gv.z += ge.z; gv.w += ge.w;
+      }
       float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t4) tv = t4[i];
       adam_one(pv.x, mv.x, vv.x, gv.x, w1, b2, omb2, step_size, bc2_sqrt, eps);
