@@ -782,9 +782,16 @@ static int build_plan(b200sac* h) {
       P.log_alpha = W(L.off_alpha);
       P.dout_dbg = h->dout_dbg.p; P.dact_dbg = h->dact_dbg.p; P.rsDbg = h->dout_dbg.rs;
     }
-    l.grid = dim3((P.Kdim + kHbCols - 1) / kHbCols, P.nets, R);
+    // large batches: rows cut into slices (4x the CTAs, a quarter of the serial row loop each); slice s >= 1 leaves its
+    // partial head-weight gradient in gradient slice s, exactly like the split-K GEMM weight gradients
+    P.row_slices = h->gslices;
+    P.xs = (long long)R * L.trainable;
+    for (int net = 0; net < P.nets; ++net)
+      if (P.dW[net] && h->grads_x) { P.dWx[net] = h->grads_x + (P.dW[net] - h->grads); P.dbx[net] = h->grads_x + (P.db[net] - h->grads); }
+    const int rows_per = (B + P.row_slices - 1) / P.row_slices;
+    l.grid = dim3(((P.Kdim + kHbCols - 1) / kHbCols) * ((B + rows_per - 1) / rows_per), P.nets, R);
     l.block = dim3(256);
-    l.smem = ((size_t)B * P.NO + 256 * (size_t)P.NO) * sizeof(float);
+    l.smem = ((size_t)rows_per * P.NO + 256 * (size_t)P.NO) * sizeof(float);
     h->plan.push_back(l);
   };
   // ---- Phase C: critic backward + Adam/Polyak ----------------------------------------------

@@ -487,6 +487,8 @@ struct HeadBwdArgs {
   const float* h; long long rsHnet, rsHrep; int ldh;         // [net][M][Kdim]
   float* dh; long long rsDhNet, rsDhRep; int lddh;
   float* dW[2]; float* db[2]; long long rsG;                 // grad arena (null -> no wgrad)
+  int row_slices;                                            // rows are cut into this many slices (grid.x = col blocks x slices);
+  float* dWx[2]; float* dbx[2]; long long xs;                // slice s >= 1 writes gradient slice s (summed by Adam, like split-K)
   int policy_mode;
   const float* dx; long long rsDxNet, rsDxRep; int lddx;     // [2][B][xw] critic input grads
   const float* psave; long long rsSave;                      // rows B..2B-1 pre-offset by host
@@ -546,9 +548,15 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
   KStamp ks_;
   extern __shared__ float sm[];
   const int net = blockIdx.y, rep = blockIdx.z;
-  const int M = P.M, NO = P.NO, KD = P.Kdim;
+  const int NO = P.NO, KD = P.Kdim;
+  const int ncb = (KD + kHbCols - 1) / kHbCols;
+  const int slice = blockIdx.x / ncb, cb = blockIdx.x - slice * ncb;
+  const int rows_per = (P.M + P.row_slices - 1) / P.row_slices;
+  const int r0 = slice * rows_per, r1 = (r0 + rows_per < P.M) ? r0 + rows_per : P.M;
+  const int M = r1 - r0;                // rows of this slice (>= 1 by construction of the grid)
+  if (M <= 0) return;
   float* sd = sm;                       // [M][NO]
-  float* red = sm + (size_t)M * NO;     // [32][8][NO] partial dW / scratch (>= 256 floats)
+  float* red = sm + (size_t)rows_per * NO;     // [32][8][NO] partial dW / scratch (>= 256 floats)
   const int tid = threadIdx.x, tx = tid % kHbCols, ty = tid / kHbCols;
 
   if (P.policy_mode) {
@@ -558,38 +566,38 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
     if (tid < Teff) s_alpha[tid] = (float)exp((double)(P.log_alpha + rep * P.rsP)[tid]);
     __syncthreads();
     for (int e = tid; e < M * A; e += 256) {
-      const int m = e / A, j = e % A;
+      const int ml = e / A, j = e % A, m = r0 + ml;
       const float* __restrict__ sv = P.psave + rep * P.rsSave + ((long long)m * A + j) * kSaveW;
       const float* __restrict__ dx0 = P.dx + rep * P.rsDxRep + (long long)m * P.lddx + K.in_w + j;
       const float da = dx0[0] + dx0[P.rsDxNet];
       const int tk = (P.tid + rep * P.rsR)[m];
       float dmu, dls;
       policy_dout_point(K, sv, da, s_alpha[tk], dmu, dls);
-      sd[m * NO + j] = dmu;
-      sd[m * NO + A + j] = dls;
-      if (P.dout_dbg && blockIdx.x == 0) {
+      sd[ml * NO + j] = dmu;
+      sd[ml * NO + A + j] = dls;
+      if (P.dout_dbg && cb == 0) {
         (P.dout_dbg + rep * P.rsDbg)[(long long)m * NO + j] = dmu;
         (P.dout_dbg + rep * P.rsDbg)[(long long)m * NO + A + j] = dls;
         (P.dact_dbg + rep * P.rsDbg)[(long long)m * A + j] = da;
       }
     }
   } else {
-    const float* __restrict__ src = P.dout + rep * P.rsDoutRep + net * P.rsDoutNet;
+    const float* __restrict__ src = P.dout + rep * P.rsDoutRep + net * P.rsDoutNet + (long long)r0 * NO;
     for (int e = tid; e < M * NO; e += 256) sd[e] = src[e];
   }
-  __syncthreads();
 
-  const int kcol = blockIdx.x * kHbCols + tx;
+  const int kcol = cb * kHbCols + tx;
   const bool kin = kcol < KD;
   const float* __restrict__ W = P.W[net] + rep * P.rsP;
   float w[kMaxHeadOut], gw[kMaxHeadOut];
 #pragma unroll
-  for (int j = 0; j < kMaxHeadOut; ++j) {
+  for (int j = 0; j < kMaxHeadOut; ++j) {        // head weights requested before the staging barrier
     w[j] = (j < NO && kin) ? W[(long long)j * KD + kcol] : 0.f;
     gw[j] = 0.f;
   }
-  const float* __restrict__ h = P.h + rep * P.rsHrep + net * P.rsHnet;
-  float* __restrict__ dh = P.dh + rep * P.rsDhRep + net * P.rsDhNet;
+  __syncthreads();
+  const float* __restrict__ h = P.h + rep * P.rsHrep + net * P.rsHnet + (long long)r0 * P.ldh;
+  float* __restrict__ dh = P.dh + rep * P.rsDhRep + net * P.rsDhNet + (long long)r0 * P.lddh;
   constexpr int U = 8;                                   // rows in flight per thread
   for (int mb = ty; mb < M; mb += kHbRows * U) {
     float hv[U];
@@ -616,6 +624,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
     }
   }
   if (P.dW[net] != nullptr) {
+    float* __restrict__ dWp = (slice == 0 ? P.dW[net] : P.dWx[net] + (long long)(slice - 1) * P.xs) + rep * P.rsG;
+    float* __restrict__ dbp = (slice == 0 ? P.db[net] : P.dbx[net] + (long long)(slice - 1) * P.xs) + rep * P.rsG;
 #pragma unroll
     for (int j = 0; j < kMaxHeadOut; ++j)
       if (j < NO) red[(ty * kHbCols + tx) * NO + j] = gw[j];
@@ -623,9 +633,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
     if (ty < NO && kin) {                 // thread (ty = output j, tx = column): fixed-order sum over row groups
       float ssum = 0.f;
       for (int q = 0; q < kHbRows; ++q) ssum += red[(q * kHbCols + tx) * NO + ty];
-      (P.dW[net] + rep * P.rsG)[(long long)ty * KD + kcol] = ssum;
+      dWp[(long long)ty * KD + kcol] = ssum;
     }
-    if (blockIdx.x == 0) {             // bias gradient: per-thread row sums -> warp shuffle tree -> 8 warp partials (fixed order)
+    if (cb == 0) {                     // bias gradient: per-thread row sums -> warp shuffle tree -> 8 warp partials (fixed order)
       __syncthreads();
       float part[kMaxHeadOut];
 #pragma unroll
@@ -646,7 +656,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
         float ssum = 0.f;
 #pragma unroll
         for (int wq = 0; wq < 8; ++wq) ssum += red[wq * kMaxHeadOut + tid];
-        (P.db[net] + rep * P.rsG)[tid] = ssum;
+        dbp[tid] = ssum;
       }
     }
   }
