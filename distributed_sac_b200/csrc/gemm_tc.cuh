@@ -2,7 +2,7 @@
 // fp32-class accuracy via the 3xTF32 split:  x = hi + lo (hi = top 19 bits, lo = x - hi),
 // D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi, accumulated in fp32 in TMEM.
 //
-// One CTA = one 128 x 64 output tile of one problem (blockIdx.z = problem x replica):
+// One CTA = one 128 x 64 (or 128 x 128) output tile of one problem (blockIdx.z = problem x replica):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes (SWIZZLE_128B for K-major operands,
 //               SWIZZLE_128B_ATOM_32B for MN-major ones) of the fp32 operands,
 //               straight from the row-major activation / weight / gradient buffers; out-of-range
@@ -10,13 +10,15 @@
 //   warps 2-5   splitter: emit lo = x - trunc19(x) beside each landed tile (same swizzled offsets, so the
 //               layout is untouched); the raw fp32 tile itself serves as hi because the tensor core reads
 //               only the top 19 bits of a tf32 operand word (measured); later the epilogue warps
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M=128, N=64, K=8),
-//               12 MMAs per 32-wide k chunk; tcgen05.commit releases the smem stage / signals the
-//               epilogue
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M=128, K=8).  A tf32 MMA costs
+//               ~105 cycles whatever its shape up to N=128 (measured), so the 64-wide tile issues TWO per k step:
+//               A_hi * [B_hi ; B_lo] (N=128: the lo tile lies right behind the hi tile in shared memory) into the
+//               adjacent TMEM column blocks [main_i | cross_i], and A_lo * B_hi (N=64) into cross_i; the 128-wide
+//               tile issues three (N=128 each).  tcgen05.commit releases the smem stage / signals the epilogue
 //   accumulate  the tensor core adds into the fp32 accumulator with truncation (measured: relative
-//               bias ~ #MMAs x 2^-24), so the tiny cross terms A_hi*B_lo + A_lo*B_hi go to their own
-//               accumulator and the A_hi*B_hi sum is spread over up to six (contiguous K ranges); the
-//               epilogue adds them with round-to-nearest.  Keeps the result within ~1e-6 of fp64.
+//               bias ~ #MMAs x 2^-24), so the tiny cross terms A_hi*B_lo + A_lo*B_hi get their own
+//               accumulators and the A_hi*B_hi sum is spread over up to four (three) accumulators (contiguous
+//               K ranges); the epilogue adds them with round-to-nearest.  Keeps the result within ~1e-6 of fp64.
 //   epilogue    tcgen05.ld 32x32b (thread = accumulator row) -> bias+ReLU | ReLU' mask | plain ->
 //               global; the weight-gradient kind also emits the bias gradient (column sums of dY),
 //               accumulated by the splitter while it walks the A tiles, in a fixed order.

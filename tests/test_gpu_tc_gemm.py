@@ -37,8 +37,8 @@ def rel(a, b):
 
 
 # fp32-class accuracy: 3xTF32 drops only lo*lo (~2^-22 relative per product); the tensor core's
-# truncating fp32 accumulation adds a bias ~ (#MMAs per accumulator) * 2^-24 (rotating accumulators: up to 6 for
-# 64-wide tiles, 3 for 128-wide ones)
+# truncating fp32 accumulation adds a bias ~ (#MMAs per accumulator) * 2^-24 (rotating accumulators: up to 4 pairs for
+# 64-wide tiles, 3 mains + 1 cross for 128-wide ones)
 TOL = 5e-6
 
 SHAPES = [(256, 256, 256), (512, 256, 256), (128, 64, 32), (1024, 400, 400), (1280, 400, 400), (200, 72, 40),
