@@ -53,6 +53,7 @@ SYMBOLS = {
     "b200sac_step": (C.c_int, [_VP] + [_VP] * 7 + [_VP]),
     "b200sac_step_host": (C.c_int, [_VP] + [_VP] * 7 + [_VP, _VP]),
     "b200sac_step_sampled": (C.c_int, [_VP, _VP, C.c_int32, _VP]),
+    "b200sac_update": (C.c_int, [_VP, _VP, _VP, _VP]),
     "b200sac_read_losses": (C.c_int, [_VP, C.c_int32, _VP, _VP]),
     "b200sac_soft_update": (C.c_int, [_VP, C.c_double, _VP]),
     "b200sac_publish_begin": (C.c_int, [_VP, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _VP]),

@@ -100,7 +100,14 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """torch's current stream as a cudaStream_t (the raw-stream query skips building a torch.cuda.Stream object: ~2 us per call
+    saved on the per-update path)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -120,6 +127,7 @@ class SacCore:
         _lib.check(self.lib.b200sac_launches_per_step(self._h, C.byref(n)))
         self.launches_per_step = n.value
         self.steps_done = 0
+        self._loss_buf = (C.c_float * (4 * max(1, cfg.replicas)))()
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -266,6 +274,14 @@ class SacCore:
     def step_sampled(self, replay: "Replay", n_steps: int = 1):
         _lib.check(self.lib.b200sac_step_sampled(self._h, replay._h, int(n_steps), _stream()))
         self.steps_done += int(n_steps)
+
+    def update_sampled(self, replay: "Replay"):
+        """sample + one gradient step + that step's losses of replica 0 as python floats (critic, actor, alpha, entropy):
+        one library call, no tensor round trips -- the body of Learner.update()."""
+        buf = self._loss_buf
+        _lib.check(self.lib.b200sac_update(self._h, replay._h, buf, _stream()))
+        self.steps_done += 1
+        return buf[0], buf[1], buf[2], buf[3]
 
     def read_losses(self, n_last: int = 1) -> torch.Tensor:
         out = torch.empty(n_last, self.cfg.replicas, 4)

@@ -1849,6 +1849,14 @@ extern "C" int b200sac_graph_timeline(b200sac_t* h, b200sac_replay_t* rb, int32_
   return 0;
 }
 
+// Learner.update() in one call: sample + one gradient step + the losses of that step (LL/learner.py:246-264).
+extern "C" int b200sac_update(b200sac_t* h, b200sac_replay_t* rb, float* losses_host, void* stream) {
+  if (!h || !rb || !losses_host) return fail(B200SAC_ERR_INVALID, "null argument");
+  if (int rc = b200sac_step_sampled(h, rb, 1, stream)) return rc;
+  CU(cudaSetDevice(h->device));
+  return fetch_losses(h, (cudaStream_t)stream, 1, losses_host);
+}
+
 extern "C" int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host, void* stream) {
   if (!h || !out_host) return fail(B200SAC_ERR_INVALID, "null argument");
   CU(cudaSetDevice(h->device));

@@ -20,6 +20,8 @@ constexpr int GT_THREADS = 512;
 constexpr int GT_WARPS = GT_THREADS / 32;
 constexpr int GT_NMAX = 16;              // widest "thin" N
 constexpr int GT_KC = 512;               // k rows of B staged per pass
+constexpr int GT_LDB = 20;               // staged row pitch: lanes of the DGRAD path read rows k = lane (mod 32) as float4 --
+                                         // 20-float rows put a quarter-warp on 8 distinct 16-B bank groups (16 would 4-way conflict)
 constexpr int GT_ROWS_WGRAD = 32, GT_ROWS_DGRAD = GT_WARPS;
 
 B200_HD bool gemm_is_thin(const GemmProb& p) { return p.mode != GEMM_FWD && p.N <= GT_NMAX; }
@@ -34,9 +36,9 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_thin_kernel(const __grid_cons
   const int m0 = blockIdx.y * (wgrad ? GT_ROWS_WGRAD : GT_ROWS_DGRAD);
   if (m0 >= M) return;
 
-  // B chunk [k][16]; after the last pass the same storage holds the per-warp partial sums [16][32][17]
-  __shared__ __align__(16) float sm[GT_WARPS * 32 * (GT_NMAX + 1)];
-  static_assert(GT_KC * GT_NMAX <= GT_WARPS * 32 * (GT_NMAX + 1), "B chunk must fit the reduction buffer");
+  // B chunk [k][GT_LDB]; after the last pass the same storage holds the per-warp partial sums [16][32][17]
+  __shared__ __align__(16) float sm[GT_KC * GT_LDB];
+  static_assert(GT_KC * GT_LDB >= GT_WARPS * 32 * (GT_NMAX + 1), "the reduction buffer must fit the B chunk storage");
 
   const float* __restrict__ A = P.A + (long long)rep * P.rsA;
   const float* __restrict__ Bm = P.B + (long long)rep * P.rsB;
@@ -58,12 +60,12 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_thin_kernel(const __grid_cons
       const int q4 = ldb >> 2;
       for (int e = tid; e < kc * q4; e += GT_THREADS) {
         const int k = e / q4, c = e - k * q4;
-        *reinterpret_cast<float4*>(sm + k * GT_NMAX + 4 * c) = __ldg(reinterpret_cast<const float4*>(Bm + (long long)(k0 + k) * ldb) + c);
+        *reinterpret_cast<float4*>(sm + k * GT_LDB + 4 * c) = __ldg(reinterpret_cast<const float4*>(Bm + (long long)(k0 + k) * ldb) + c);
       }
     } else {
       for (int e = tid; e < kc * N; e += GT_THREADS) {
         const int k = e / N, n = e - k * N;
-        sm[k * GT_NMAX + n] = __ldg(Bm + (long long)(k0 + k) * ldb + n);
+        sm[k * GT_LDB + n] = __ldg(Bm + (long long)(k0 + k) * ldb + n);
       }
     }
     // ---- the long operand: issue this pass's loads before waiting for the staging barrier ----
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_thin_kernel(const __grid_cons
 #pragma unroll
           for (int c = 0; c < GT_NMAX / 4; ++c)
             if (c < n4) {
-              const float4 b = *reinterpret_cast<const float4*>(sm + k * GT_NMAX + 4 * c);
+              const float4 b = *reinterpret_cast<const float4*>(sm + k * GT_LDB + 4 * c);
               acc[4 * c + 0] = fmaf(a[j], b.x, acc[4 * c + 0]);
               acc[4 * c + 1] = fmaf(a[j], b.y, acc[4 * c + 1]);
               acc[4 * c + 2] = fmaf(a[j], b.z, acc[4 * c + 2]);
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_thin_kernel(const __grid_cons
 #pragma unroll
           for (int c = 0; c < GT_NMAX / 4; ++c)
             if (c < n4) {
-              const float4 b = *reinterpret_cast<const float4*>(sm + k * GT_NMAX + 4 * c);
+              const float4 b = *reinterpret_cast<const float4*>(sm + k * GT_LDB + 4 * c);
               acc[4 * c + 0] = fmaf(a[j], b.x, acc[4 * c + 0]);
               acc[4 * c + 1] = fmaf(a[j], b.y, acc[4 * c + 1]);
               acc[4 * c + 2] = fmaf(a[j], b.z, acc[4 * c + 2]);
@@ -142,22 +144,27 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_thin_kernel(const __grid_cons
     }
   } else {
     const int m = m0 + w;
+    // 16 columns x 32 lanes -> one column per lane pair with a halving butterfly (16 shuffles instead of 80): at offset o
+    // a lane keeps the half of its columns selected by bit o of its id and adds the partner's copy of that half; after
+    // offsets 16, 8, 4, 2 lane l holds column l >> 1, offset 1 adds the two lanes of the pair.  Fixed tree -> reproducible.
 #pragma unroll
-    for (int n = 0; n < GT_NMAX; ++n) {
-      float v = acc[n];
+    for (int o = 16, n = GT_NMAX; o >= 2; o >>= 1, n >>= 1) {
+      const bool up = (lane & o) != 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      acc[n] = v;
+      for (int i = 0; i < n / 2; ++i) {
+        const float send = up ? acc[i] : acc[i + n / 2];
+        const float keep = up ? acc[i + n / 2] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
     }
-    if (m < M && lane < N) {
-      float v = 0.f;
-#pragma unroll
-      for (int n = 0; n < GT_NMAX; ++n) v = (lane == n) ? acc[n] : v;
+    float v = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
+    const int col = lane >> 1;
+    if (m < M && col < N && (lane & 1) == 0) {
       if (P.mask != nullptr) {
         const float* __restrict__ mask = P.mask + (long long)rep * P.rsMask;
-        if (!(mask[(long long)m * P.ldmask + lane] > 0.f)) v = 0.f;
+        if (!(mask[(long long)m * P.ldmask + col] > 0.f)) v = 0.f;
       }
-      C[(long long)m * P.ldc + lane] = v;
+      C[(long long)m * P.ldc + col] = v;
     }
   }
 }

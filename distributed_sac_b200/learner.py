@@ -120,8 +120,8 @@ class _BaseLearner:
     # ---- reference method surface -------------------------------------------------------------
     def update(self):
         """Learner.update(): sample a minibatch, one SAC gradient step, return python floats."""
-        losses = self.memory.step_core(self.core)
-        return self._loss_tuple(losses)
+        l = self.memory.step_core(self.core)          # (critic, actor, alpha loss, entropy) python floats
+        return (l[0], l[1]) if self.num_tasks == 0 else (l[0], l[1], l[3])
 
     def update_SAC(self, states, actions, rewards, next_states, dones, alpha=None, retain_graph=False,
                    eps_next=None, eps_cur=None):

@@ -78,8 +78,8 @@ class ReplayBuffer(threading.Thread):
         core.step_sampled(self.ring, 1)
 
     def step_core(self, core):
-        self.enqueue_step(core)
-        return core.read_losses(1)[0]
+        """Learner.update(): sample + step + losses (critic, actor, alpha, entropy) as python floats, one library call."""
+        return core.update_sampled(self.ring)
 
     def __len__(self):
         return self.ring.size()

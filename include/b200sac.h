@@ -149,6 +149,10 @@ int b200sac_step_host(b200sac_t* h, const float* s, const float* a, const float*
  * copied on a side stream, overlapped with the previous step. */
 int b200sac_step_sampled(b200sac_t* h, b200sac_replay_t* rb, int32_t n_steps, void* stream);
 
+/* Learner.update() (learner.py:246-264) in one call: b200sac_step_sampled(h, rb, 1) followed by the losses of that
+ * step, out[replicas][4] = {critic, actor, alpha loss, entropy}.  Synchronises the stream. */
+int b200sac_update(b200sac_t* h, b200sac_replay_t* rb, float* losses_host, void* stream);
+
 /* Losses of the most recent `n_last` steps (<= 1024 kept): out[n_last][replicas][4].
  * Synchronises the stream. */
 int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host, void* stream);
