@@ -32,12 +32,17 @@ WORK = {
     "VS": dict(gflop=10.970, mbytes=30.188),
     "MS": dict(gflop=13.846, mbytes=30.728),
     "C10": dict(gflop=17.088, mbytes=37.377),
+    # CARE(O): same consumer MLPs and mixture as C10; the context path is per-task (10 rows) in both, so the per-step
+    # streaming-model work differs only by the 89.6 k trainable context-encoder parameters
+    "C10O": dict(gflop=17.088, mbytes=37.377 + 89600 * 24e-6),
 }
 WORKLOAD_DESC = {
     "LL": "LunarLanderContinuous-v2 SAC learner (obs 8, act 2, MLP 256-256, batch 256)",
     "VS": "MT1 VSAC-shape SAC learner (obs 39, act 4, MLP 400x3, batch 1024, twin-Q)",
     "MS": "MT10 MTSAC learner (mtobs 49, act 4, MLP 400x3, batch 1280, 10 tasks one-hot, weighted loss)",
     "C10": "MT10 CARE(M) learner (mtobs 49, act 4, K=6 mixture encoders 39-50-50, 768-d context, MLP 400x3 over the 100-d encoded state, batch 1280)",
+    "C10O": "MT10 CARE(O) learner (use_modified_care=false: trainable context encoder 768-100-50-50-50-50 with its own Adam, "
+            "K=6 mixture encoders, MLP 400x3, batch 1280, unweighted losses)",
 }
 
 
@@ -63,6 +68,10 @@ def core_config(workload, replicas, precision=1):
     if workload == "C10":
         return CoreConfig(state_dim=39, act_dim=4, actor_hidden=[400] * 3, critic_hidden=[400] * 3, batch=1280,
                           num_tasks=10, weighted_loss=True, replicas=replicas, precision=precision, care=True)
+    if workload == "C10O":
+        return CoreConfig(state_dim=39, act_dim=4, actor_hidden=[400] * 3, critic_hidden=[400] * 3, batch=1280,
+                          num_tasks=10, weighted_loss=False, replicas=replicas, precision=precision, care=True,
+                          care_original=True, emb_dim=50, lr_ctx=3e-4)
     raise ValueError(workload)
 
 
@@ -118,9 +127,9 @@ class ClockSampler:
 def cpu_learner(workload, n_buffer=20000, seed=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import sac_port as sp
-    if workload == "C10":
+    if workload in ("C10", "C10O"):
         import care_port as cp
-        spec = cp.CareSpec()
+        spec = cp.CareSpec() if workload == "C10" else cp.CareSpec(modified=False, weighted_loss=False)
         lrn = cp.CarePortLearner(spec, cp.init_params(spec, seed=seed))
         rspec = sp.ms_spec()                       # same replay layout as MTSAC: mtobs rows, B/T per task
         rb = sp.PortReplay(rspec, n_buffer, seed=seed)
@@ -216,7 +225,7 @@ def write_cfg(workload, tmp):
     elif workload == "VS":
         cfg = dict(base, batch_size=1024, lr_actor=3e-4, lr_critic=3e-4, update_delay=5, print_period_player=2,
                    print_period_learner=5, actor_hidden_dim=[400] * 3, critic_hidden_dim=[400] * 3)
-    elif workload == "C10":
+    elif workload in ("C10", "C10O"):
         names = [f"task-{i}" for i in range(10)]
         g = torch.Generator().manual_seed(7)
         emb = {n: (torch.randn(768, generator=g) * 0.3).tolist() for n in names}     # synthetic stand-in for the RoBERTa rows
@@ -224,7 +233,7 @@ def write_cfg(workload, tmp):
             json.dump(emb, f)
         with open(os.path.join(tmp, "names.json"), "w") as f:
             json.dump(names, f)
-        cfg = dict(base, use_modified_care=True, num_tasks=10, batch_size=1280, update_delay=6, print_period_player=2,
+        cfg = dict(base, use_modified_care=(workload == "C10"), num_tasks=10, batch_size=1280, update_delay=6, print_period_player=2,
                    print_period_learner=10, max_episode_time=500,
                    actor={"state_dim": 39, "action_dim": 4, "action_bound": [-1.0, 1.0], "lr_actor": 3e-4,
                           "actor_hidden_dim": [400] * 3},
@@ -271,7 +280,7 @@ def make_learner(workload, cfg_path, device_index, buffer_size, precision=1):
                                     precision=precision)
     if workload == "VS":
         return L.VSACLearner(cfg_path, write_mode=False, server=srv, device_index=device_index, precision=precision)
-    if workload == "C10":
+    if workload in ("C10", "C10O"):
         return L.CARELearner(None, None, cfg_path, write_mode=False, server=srv, device_index=device_index, precision=precision)
     return L.MTSACLearner(None, None, cfg_path, write_mode=False, server=srv, device_index=device_index, precision=precision)
 
@@ -282,7 +291,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="LL", choices=["LL", "VS", "MS", "C10"])
+    ap.add_argument("--workload", default="LL", choices=["LL", "VS", "MS", "C10", "C10O"])
     ap.add_argument("--replicas", type=int, default=1, help="independent learners co-scheduled per GPU")
     ap.add_argument("--ring", type=int, default=1 << 20, help="transitions in the device replay ring (per learner)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed update() calls for the e2e leg (default: min(steps, 2000))")
