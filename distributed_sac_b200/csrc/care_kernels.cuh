@@ -38,7 +38,7 @@ struct CareTabArgs {
   int original;                       // CARE(O): ctx = the shared, trainable context encoder on relu(E[t]); the trunk reads its output
 };
 
-// grid (T, n_inst, R), block 512: 16 warps, one output neuron per warp at a time, 8 independent
+// grid (T, n_inst, R), block 512: 16 warps, one output neuron per warp at a time, up to 24 independent
 // loads in flight per lane (the 768-long dot products are pure latency otherwise)
 __global__ void __launch_bounds__(512) care_tables_kernel(CareTabArgs P) {
   KStamp ks_;
@@ -71,6 +71,13 @@ __global__ void __launch_bounds__(512) care_tables_kernel(CareTabArgs P) {
         const float* __restrict__ wr = W + (long long)o * nin;
         float a = 0.f;
         int i = lane;
+        for (; i + 23 * 32 < nin; i += 24 * 32) {        // 768-wide rows: the whole row in flight (one round trip, not three)
+          float wv[24];
+#pragma unroll
+          for (int u = 0; u < 24; ++u) wv[u] = __ldg(wr + i + u * 32);
+#pragma unroll
+          for (int u = 0; u < 24; ++u) a = fmaf(cur[i + u * 32], wv[u], a);
+        }
         for (; i + 7 * 32 < nin; i += 8 * 32) {
           float wv[8];
 #pragma unroll
