@@ -128,6 +128,19 @@ B200_D void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+B200_D void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+B200_D void tc_ld32_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
 B200_D void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -432,23 +445,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
       }
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
       const uint32_t acc_stride = Cfg::kPaired ? 2u * TC_BN : (uint32_t)TC_BN;
-      tc_ld32(lane_addr, v);                                  // main[0]
-      if (t == 0 && c == 0) TC_STAMP(85);
-      for (int mi = 1; mi < nmain; ++mi) {
-        tc_ld32(lane_addr + acc_stride * (uint32_t)mi, w);
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
-      }
-      if (Cfg::kPaired) {                                     // cross terms: one accumulator per pair, summed first (tiny values)
-        tc_ld32(lane_addr + (uint32_t)TC_BN, w);
+      if (Cfg::kPaired) {                                     // [main_i | cross_i]: both halves of a pair per wait
+        tc_ld32_nowait(lane_addr, v);
+        tc_ld32_nowait(lane_addr + (uint32_t)TC_BN, w);
+        tc_ld_wait();
+        if (t == 0 && c == 0) TC_STAMP(85);
         for (int mi = 1; mi < nmain; ++mi) {
-          uint32_t w2[32];
-          tc_ld32(lane_addr + acc_stride * (uint32_t)mi + (uint32_t)TC_BN, w2);
+          uint32_t v2[32], w2[32];
+          tc_ld32_nowait(lane_addr + acc_stride * (uint32_t)mi, v2);
+          tc_ld32_nowait(lane_addr + acc_stride * (uint32_t)mi + (uint32_t)TC_BN, w2);
+          tc_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) w[jj] = __float_as_uint(__uint_as_float(w[jj]) + __uint_as_float(w2[jj]));
+          for (int jj = 0; jj < 32; ++jj) {
+            v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
+            w[jj] = __float_as_uint(__uint_as_float(w[jj]) + __uint_as_float(w2[jj]));     // cross terms summed apart (tiny values)
+          }
         }
       } else {
-        tc_ld32(lane_addr + (uint32_t)(TC_BN * TC_NMAIN), w);   // cross terms
+        tc_ld32_nowait(lane_addr, v);                         // main[0]
+        tc_ld32_nowait(lane_addr + (uint32_t)(TC_BN * TC_NMAIN), w);   // cross terms
+        tc_ld_wait();
+        if (t == 0 && c == 0) TC_STAMP(85);
+        for (int mi = 1; mi < nmain; ++mi) {
+          uint32_t v2[32];
+          tc_ld32(lane_addr + acc_stride * (uint32_t)mi, v2);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
+        }
       }
       if (t == 0 && c == 0) TC_STAMP(86);
 #pragma unroll
@@ -458,11 +481,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
       const int n = n0 + c * 32 + c4;                         // first of this lane's four output columns
       const float4 bv = bvs[c];
       const int mrow0 = m0 + q * 32;
+      float4 xo[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int row = 4 * u + rsub, m = mrow0 + row;
-        float4 x;
-        x.x = scratch[row * 33 + c4]; x.y = scratch[row * 33 + c4 + 1]; x.z = scratch[row * 33 + c4 + 2]; x.w = scratch[row * 33 + c4 + 3];
+      for (int u = 0; u < 8; ++u) {                           // all shared-memory reads of the block first ...
+        const int row = 4 * u + rsub;
+        xo[u].x = scratch[row * 33 + c4]; xo[u].y = scratch[row * 33 + c4 + 1];
+        xo[u].z = scratch[row * 33 + c4 + 2]; xo[u].w = scratch[row * 33 + c4 + 3];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {                           // ... then the fused epilogue math ...
+        float4 x = xo[u];
         if (mode == GEMM_DGRAD && mask) {
           x.x = mkv[u].x > 0.f ? x.x : 0.f; x.y = mkv[u].y > 0.f ? x.y : 0.f;
           x.z = mkv[u].z > 0.f ? x.z : 0.f; x.w = mkv[u].w > 0.f ? x.w : 0.f;
@@ -470,6 +498,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
           x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
           if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
         }
+        xo[u] = x;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {                           // ... then eight back-to-back 128-bit row stores
+        const int m = mrow0 + 4 * u + rsub;
+        const float4 x = xo[u];
         if (m < M) {
           float* __restrict__ cp = Cout + (long long)m * ldc + n;
           if (vec_c && n + 3 < N) {
