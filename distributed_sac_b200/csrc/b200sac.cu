@@ -1524,10 +1524,14 @@ static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* co
   return run_plan(h, st, use_eps, evs ? evs + 1 : nullptr);
 }
 
-static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* const* p, int np, b200sac_replay* rb) {
+// nsteps > 1 (device-ring sampling only): that many consecutive gradient steps captured in ONE graph, so a pipelined
+// run pays the graph-launch gap (~3-4 us between two graph launches on B200) once per kGraphSteps steps.
+constexpr int kGraphSteps = 8;
+static bool g_stamp_host_off = true;           // false while b200sac_graph_timeline runs
+static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* const* p, int np, b200sac_replay* rb, int nsteps = 1) {
   GraphKey key;
   memset(&key, 0, sizeof(key));
-  key.variant = variant;
+  key.variant = variant + 16 * (nsteps - 1);
   for (int i = 0; i < np && i < 9; ++i) key.p[i] = p[i];
   if (rb) key.p[8] = rb;
   auto it = h->graphs.find(key);
@@ -1538,7 +1542,8 @@ static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* con
     }
     cudaGraph_t g = nullptr;
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_body(h, st, variant, p, rb);
+    int rc = 0;
+    for (int k = 0; k < nsteps && rc == 0; ++k) rc = enqueue_body(h, st, variant, p, rb);
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(B200SAC_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -1549,7 +1554,7 @@ static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* con
     it = h->graphs.emplace(key, ge).first;
   }
   CU(cudaGraphLaunch(it->second, st));
-  h->host_steps += 1;
+  h->host_steps += nsteps;
   return 0;
 }
 
@@ -1834,7 +1839,9 @@ extern "C" int b200sac_graph_timeline(b200sac_t* h, b200sac_replay_t* rb, int32_
   if (int rc = b200sac_step_sampled(h, rb, 5, stream)) return rc;     // warm (graph instantiated)
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpyToSymbol(g_stamp, &sb_on, sizeof(StampBuf)));
+  g_stamp_host_off = false;
   int rc = b200sac_step_sampled(h, rb, iters + 1, stream);
+  g_stamp_host_off = true;
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpyToSymbol(g_stamp, &sb_off, sizeof(StampBuf)));
   if (rc) return rc;
@@ -2108,7 +2115,11 @@ extern "C" int b200sac_step_sampled(b200sac_t* h, b200sac_replay_t* rb, int32_t 
   }
   if (rb->where == 0) {
     const void* p[1] = {rb->rows};
-    for (int i = 0; i < n_steps; ++i)
+    int i = 0;
+    if (g_stamp_host_off)                       // (the in-graph timeline wants one step per graph)
+      for (; i + kGraphSteps <= n_steps; i += kGraphSteps)
+        if (int rc = launch_step(h, st, 2, p, 1, rb, kGraphSteps)) return rc;
+    for (; i < n_steps; ++i)
       if (int rc = launch_step(h, st, 2, p, 1, rb)) return rc;
     return sb.end();
   }
