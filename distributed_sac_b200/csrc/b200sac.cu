@@ -289,6 +289,8 @@ struct b200sac {
   size_t stage_floats = 0;
   int row_w = 0, row_stride = 0;
   cudaStream_t side = nullptr;
+  cudaStream_t fork = nullptr;    // capture-time fork for the next step's index sampling (multi-step graphs)
+  cudaEvent_t ev_ingested = nullptr, ev_sampled = nullptr;
   cudaStream_t own = nullptr;     // used when the caller hands us the legacy default stream (not capturable)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -354,6 +356,9 @@ static int destroy_impl(b200sac* h) {
   cudaFree(h->pub_d);
   if (h->pub_h) cudaFreeHost(h->pub_h);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->fork) cudaStreamDestroy(h->fork);
+  if (h->ev_ingested) cudaEventDestroy(h->ev_ingested);
+  if (h->ev_sampled) cudaEventDestroy(h->ev_sampled);
   if (h->own) cudaStreamDestroy(h->own);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
@@ -1304,6 +1309,9 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   CUH(cudaHostGetDevicePointer((void**)&h->loss_h_dev, h->loss_h, 0));
   CUH(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CUH(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
+  CUH(cudaStreamCreateWithFlags(&h->fork, cudaStreamNonBlocking));
+  CUH(cudaEventCreateWithFlags(&h->ev_ingested, cudaEventDisableTiming));
+  CUH(cudaEventCreateWithFlags(&h->ev_sampled, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
 
@@ -1485,8 +1493,13 @@ extern "C" int b200sac_publish_wait(b200sac_t* h, const float** host_ptr, int64_
 // ------------------------------------------------------------------------------------------
 // step variants.  variant 0: split device arrays; 1: packed rows (dense, staged); 2: replay gather
 // ------------------------------------------------------------------------------------------
+// variant 2 sampling modes (multi-step graphs): SAMPLE_INLINE = sample on `st` right before the gather (one step per graph);
+// SAMPLE_DONE = the indices of this step were already drawn on the fork stream (wait for them); `fork_next` = once this
+// step's gather has consumed the index buffer and bumped the step counter, draw the NEXT step's indices on the fork stream
+// -- that kernel then overlaps the whole step instead of heading its critical path.
+enum { SAMPLE_INLINE = 0, SAMPLE_DONE = 1 };
 static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* const* p, b200sac_replay* rb,
-                        cudaEvent_t* evs = nullptr) {
+                        cudaEvent_t* evs = nullptr, int sample_mode = SAMPLE_INLINE, bool fork_next = false) {
   if (evs) CU(cudaEventRecord(evs[0], st));
   const int B = h->cfg.batch, R = h->R;
   dim3 grid((B + 7) / 8, R), block(256);
@@ -1515,10 +1528,20 @@ static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* co
       }
     }
   } else {
-    launch_k(sample_indices_kernel, dim3(R), dim3(256), 0, st, h->K, (const Counters*)h->cnt, (const long long*)rb->d_fill,
-             rb->cap_per_task, rb->d_idx, (long long)B, rb->seed);
+    auto sample_on = [&](cudaStream_t s2) {
+      return launch_k(sample_indices_kernel, dim3(R), dim3(B > 256 ? 512 : 256), 0, s2, h->K,   // 98 regs/thread: 512 threads fit
+                      (const Counters*)h->cnt, (const long long*)rb->d_fill, rb->cap_per_task, rb->d_idx, (long long)B, rb->seed);
+    };
+    if (sample_mode == SAMPLE_INLINE) sample_on(st);
+    else CU(cudaStreamWaitEvent(st, h->ev_sampled, 0));
     launch_k(ingest_rows_kernel, grid, block, 0, st, h->K, h->ing, (const float*)rb->rows, rb->rs_rows, h->row_stride,
              (const int*)rb->d_idx, (long long)B);
+    if (fork_next) {
+      CU(cudaEventRecord(h->ev_ingested, st));
+      CU(cudaStreamWaitEvent(h->fork, h->ev_ingested, 0));
+      sample_on(h->fork);
+      CU(cudaEventRecord(h->ev_sampled, h->fork));
+    }
   }
   CU(cudaGetLastError());
   return run_plan(h, st, use_eps, evs ? evs + 1 : nullptr);
@@ -1543,7 +1566,8 @@ static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* con
     cudaGraph_t g = nullptr;
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
-    for (int k = 0; k < nsteps && rc == 0; ++k) rc = enqueue_body(h, st, variant, p, rb);
+    for (int k = 0; k < nsteps && rc == 0; ++k)
+      rc = enqueue_body(h, st, variant, p, rb, nullptr, (nsteps > 1 && k > 0) ? SAMPLE_DONE : SAMPLE_INLINE, nsteps > 1 && k + 1 < nsteps);
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(B200SAC_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
