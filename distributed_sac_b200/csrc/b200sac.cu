@@ -219,6 +219,8 @@ struct Launch {
   LaunchKind kind;
   dim3 grid, block;
   size_t smem = 0;
+  int branch = 0;        // 1: may run on the fork stream, concurrently with the launches that follow it on the main stream
+  bool join = false;     // the main stream waits for the fork stream before this launch
   // payloads (only the one matching `kind` is used)
   const GemmProb* probs = nullptr; int G = 0;
   GemmGroup grp;
@@ -290,7 +292,7 @@ struct b200sac {
   int row_w = 0, row_stride = 0;
   cudaStream_t side = nullptr;
   cudaStream_t fork = nullptr;    // capture-time fork for the next step's index sampling (multi-step graphs)
-  cudaEvent_t ev_ingested = nullptr, ev_sampled = nullptr;
+  cudaEvent_t ev_ingested = nullptr, ev_sampled = nullptr, ev_fork_src = nullptr, ev_fork_done = nullptr;
   cudaStream_t own = nullptr;     // used when the caller hands us the legacy default stream (not capturable)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -359,6 +361,8 @@ static int destroy_impl(b200sac* h) {
   if (h->fork) cudaStreamDestroy(h->fork);
   if (h->ev_ingested) cudaEventDestroy(h->ev_ingested);
   if (h->ev_sampled) cudaEventDestroy(h->ev_sampled);
+  if (h->ev_fork_src) cudaEventDestroy(h->ev_fork_src);
+  if (h->ev_fork_done) cudaEventDestroy(h->ev_fork_done);
   if (h->own) cudaStreamDestroy(h->own);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
@@ -443,6 +447,11 @@ static int build_plan(b200sac* h) {
   auto Gp = [&](int64_t off) { return h->grads + off; };
 
   int plan_rc = 0;
+  int cur_branch = 0;            // branch tag given to the launches gemm_launch creates
+  // FFMA back-end, plain SAC nets: a layer's weight gradient only feeds Adam, while its input gradient heads the rest of the
+  // backward chain.  The weight-gradient launch goes to the fork stream and the chain continues at once (the kernels hold
+  // <= 2 CTAs per SM, so both fit); Adam joins.  (tcgen05 tiles own a whole SM each: grouping is better there.)
+  const bool use_fork = (c.precision == 0) && !c.care && getenv("B200SAC_NO_FORK") == nullptr;
   std::function<void(std::vector<GemmProb>)> gemm_launch_ref;
   auto gemm_launch = [&](std::vector<GemmProb> ps_in) {
     // Split-K for the weight gradients: K = batch (1024 / 1280) is the long dimension and M x N = out x in gives only a
@@ -508,6 +517,7 @@ static int build_plan(b200sac* h) {
         int bn = (maxN >= 256 && ctas128 * R >= 96) ? 128 : 64;
         if (const char* e = getenv("B200SAC_TC_BN")) bn = atoi(e) == 128 ? 128 : 64;
         l.kind = L_GEMM_TC;
+        l.branch = cur_branch;
         l.bn = bn;
         l.grid = dim3((maxN + bn - 1) / bn, (maxM + TC_BM - 1) / TC_BM, (unsigned)(tc.size() * R));
         l.block = dim3(TC_THREADS);
@@ -538,6 +548,7 @@ static int build_plan(b200sac* h) {
     bool thin = getenv("B200SAC_NO_THIN") == nullptr;
     for (auto& p : ps) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; thin = thin && gemm_is_thin(p); }
     l.kind = L_GEMM_SMALL;
+    l.branch = cur_branch;
     l.grid = dim3((maxN + GS_T - 1) / GS_T, (maxM + GS_T - 1) / GS_T, (unsigned)(ps.size() * R));
     l.block = dim3(GS_THREADS);
     if (thin) {        // input-layer weight / input gradients (N = obs+act <= 16): gemm_thin.cuh
@@ -821,7 +832,12 @@ static int build_plan(b200sac* h) {
         ps.push_back(dgrad(netp(h->dhQ[0], net, lo.out), h->dhQ[0].rs, lo, nullptr, 0,
                            h->dxP.p + (long long)net * B * h->K.ldx, h->dxP.rs));
       }
-    gemm_launch(ps);
+    if (use_fork && l > 0) {        // ps = {wgrad q1, wgrad q2, dgrad q1, dgrad q2}
+      cur_branch = 1; gemm_launch(std::vector<GemmProb>(ps.begin(), ps.begin() + 2)); cur_branch = 0;
+      gemm_launch(std::vector<GemmProb>(ps.begin() + 2, ps.end()));
+    } else {
+      gemm_launch(ps);
+    }
   }
   if (c.care) {
     {  // backward of the attention mix: dZk, d(att)
@@ -935,6 +951,7 @@ static int build_plan(b200sac* h) {
     if (nb > 592) nb = 592;
     l.grid = dim3(nb + (P.tail != TAIL_NONE ? 1 : 0), R);
     l.block = dim3(256);
+    l.join = true;                 // every gradient of the slice must have landed, including the forked weight gradients
     h->plan.push_back(l);
   };
   adam(0);
@@ -994,7 +1011,12 @@ static int build_plan(b200sac* h) {
     if (l > 0)
       ps.push_back(dgrad(h->dhA[l].p, h->dhA[l].rs, lo, h->hA[l - 1].p + (long long)B * lo.ld, h->hA[l - 1].rs,
                          h->dhA[l - 1].p, h->dhA[l - 1].rs));
-    gemm_launch(ps);
+    if (use_fork && l > 0) {
+      cur_branch = 1; gemm_launch(std::vector<GemmProb>(ps.begin(), ps.begin() + 1)); cur_branch = 0;
+      gemm_launch(std::vector<GemmProb>(ps.begin() + 1, ps.end()));
+    } else {
+      gemm_launch(ps);
+    }
   }
   adam(1);
   if (c.care == 2) adam(2);        // update(): context_encoder_optimizer.step() (learner.py:399), gradients from the critic loss
@@ -1024,6 +1046,7 @@ static int build_plan(b200sac* h) {
 // Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor
 // drains; every kernel begins with griddepcontrol.wait (common.cuh::kstamp), so data dependencies hold.
 static bool g_use_pdl = true;
+static bool g_stamp_host_off = true;           // false while b200sac_graph_timeline runs (one unforked step per graph)
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg;
@@ -1037,60 +1060,77 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* evs = nullptr) {
+static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* evs = nullptr, bool allow_fork = false) {
+  bool fork_pending = false;
   for (size_t i = 0; i < h->plan.size(); ++i) {
     Launch& l = h->plan[i];
     if (evs) CU(cudaEventRecord(evs[i], st));
+    cudaStream_t s = st;
+    if (l.join && fork_pending) {                       // e.g. Adam: wait for the forked weight gradients
+      CU(cudaStreamWaitEvent(st, h->ev_fork_done, 0));
+      fork_pending = false;
+    }
+    const bool forked = allow_fork && l.branch == 1;
+    if (forked) {                                       // runs beside the launches that follow on `st`
+      CU(cudaEventRecord(h->ev_fork_src, st));
+      CU(cudaStreamWaitEvent(h->fork, h->ev_fork_src, 0));
+      s = h->fork;
+    }
     switch (l.kind) {
       case L_POLICY_DOUT:
-        launch_k(policy_dout_kernel, l.grid, l.block, 0, st, h->K, l.pdo);
+        launch_k(policy_dout_kernel, l.grid, l.block, 0, s, h->K, l.pdo);
         break;
       case L_CARE_TAB:
-        launch_k(care_tables_kernel, l.grid, l.block, 0, st, l.ctab);
+        launch_k(care_tables_kernel, l.grid, l.block, 0, s, l.ctab);
         break;
       case L_CARE_MIX:
-        launch_k(care_mix_kernel, l.grid, l.block, 0, st, l.cmix);
+        launch_k(care_mix_kernel, l.grid, l.block, 0, s, l.cmix);
         break;
       case L_CARE_MIXBWD:
-        launch_k(care_mix_bwd_kernel, l.grid, l.block, 0, st, l.cmixb);
+        launch_k(care_mix_bwd_kernel, l.grid, l.block, 0, s, l.cmixb);
         break;
       case L_CARE_TABRED:
-        launch_k(care_tab_reduce_kernel, l.grid, l.block, 0, st, l.ctred);
+        launch_k(care_tab_reduce_kernel, l.grid, l.block, 0, s, l.ctred);
         break;
       case L_CARE_TABWG:
-        launch_k(care_tab_wgrad_kernel, l.grid, l.block, l.smem, st, l.ctwg);
+        launch_k(care_tab_wgrad_kernel, l.grid, l.block, l.smem, s, l.ctwg);
         break;
       case L_GEMM_BIG:
       case L_GEMM_SMALL:
-        launch_k(gemm_simt_kernel, l.grid, l.block, 0, st, l.grp);
+        launch_k(gemm_simt_kernel, l.grid, l.block, 0, s, l.grp);
         break;
       case L_GEMM_THIN:
-        launch_k(gemm_thin_kernel, l.grid, l.block, 0, st, l.grp);
+        launch_k(gemm_thin_kernel, l.grid, l.block, 0, s, l.grp);
         break;
       case L_GEMM_TC:
-        if (l.bn == 128) launch_k(gemm_tc_kernel<128>, l.grid, l.block, l.smem, st, l.tprobs);
-        else launch_k(gemm_tc_kernel<64>, l.grid, l.block, l.smem, st, l.tprobs);
+        if (l.bn == 128) launch_k(gemm_tc_kernel<128>, l.grid, l.block, l.smem, s, l.tprobs);
+        else launch_k(gemm_tc_kernel<64>, l.grid, l.block, l.smem, s, l.tprobs);
         break;
       case L_POLICY: {
         PolicyHeadArgs P = l.pol;
         P.use_eps_buf = use_eps_buf ? 1 : 0;
-        launch_k(policy_head_kernel, l.grid, l.block, 0, st, h->K, P);
+        launch_k(policy_head_kernel, l.grid, l.block, 0, s, h->K, P);
         break;
       }
       case L_CHEADS:
-        launch_k(critic_heads_kernel, l.grid, l.block, 0, st, h->K, l.ch);
+        launch_k(critic_heads_kernel, l.grid, l.block, 0, s, h->K, l.ch);
         break;
       case L_AQHEADS:
-        launch_k(actor_q_heads_kernel, l.grid, l.block, 0, st, h->K, l.aq);
+        launch_k(actor_q_heads_kernel, l.grid, l.block, 0, s, h->K, l.aq);
         break;
       case L_HEADBWD:
-        launch_k(head_bwd_kernel, l.grid, l.block, l.smem, st, h->K, l.hb);
+        launch_k(head_bwd_kernel, l.grid, l.block, l.smem, s, h->K, l.hb);
         break;
       case L_ADAM:
-        launch_k(adam_kernel, l.grid, l.block, 0, st, h->K, l.ad);
+        launch_k(adam_kernel, l.grid, l.block, 0, s, h->K, l.ad);
         break;
     }
+    if (forked) {
+      CU(cudaEventRecord(h->ev_fork_done, h->fork));
+      fork_pending = true;
+    }
   }
+  if (fork_pending) CU(cudaStreamWaitEvent(st, h->ev_fork_done, 0));
   if (evs) CU(cudaEventRecord(evs[h->plan.size()], st));
   CU(cudaGetLastError());
   return 0;
@@ -1312,6 +1352,8 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   CUH(cudaStreamCreateWithFlags(&h->fork, cudaStreamNonBlocking));
   CUH(cudaEventCreateWithFlags(&h->ev_ingested, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_sampled, cudaEventDisableTiming));
+  CUH(cudaEventCreateWithFlags(&h->ev_fork_src, cudaEventDisableTiming));
+  CUH(cudaEventCreateWithFlags(&h->ev_fork_done, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
 
@@ -1544,17 +1586,16 @@ static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* co
     }
   }
   CU(cudaGetLastError());
-  return run_plan(h, st, use_eps, evs ? evs + 1 : nullptr);
+  return run_plan(h, st, use_eps, evs ? evs + 1 : nullptr, evs == nullptr && g_stamp_host_off);
 }
 
 // nsteps > 1 (device-ring sampling only): that many consecutive gradient steps captured in ONE graph, so a pipelined
 // run pays the graph-launch gap (~3-4 us between two graph launches on B200) once per kGraphSteps steps.
 constexpr int kGraphSteps = 8;
-static bool g_stamp_host_off = true;           // false while b200sac_graph_timeline runs
 static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* const* p, int np, b200sac_replay* rb, int nsteps = 1) {
   GraphKey key;
   memset(&key, 0, sizeof(key));
-  key.variant = variant + 16 * (nsteps - 1);
+  key.variant = variant + 4 * (g_stamp_host_off ? 0 : 1) + 16 * (nsteps - 1);      // the timeline run captures unforked graphs
   for (int i = 0; i < np && i < 9; ++i) key.p[i] = p[i];
   if (rb) key.p[8] = rb;
   auto it = h->graphs.find(key);
