@@ -697,7 +697,14 @@ static int build_plan(b200sac* h) {
         ps.push_back(fwd(l == 0 ? h->XQ.p : netp(h->hQ[l - 1], net, lo.in), l == 0 ? h->XQ.rs : h->hQ[l - 1].rs, B, lo,
                          true, netp(h->hQ[l], net, lo.out), h->hQ[l].rs));
       }
-    gemm_launch(ps);
+    if (use_fork && La == Lc) {
+      // Q1,Q2 on (s,a) are not needed before critic_heads, while the actor's output heads the policy_head -> target-critic
+      // chain: the critics' layer goes to the fork stream (joined at critic_heads), the actor's stays on the main stream.
+      cur_branch = 1; gemm_launch(std::vector<GemmProb>(ps.begin() + 1, ps.end())); cur_branch = 0;
+      gemm_launch(std::vector<GemmProb>(ps.begin(), ps.begin() + 1));
+    } else {
+      gemm_launch(ps);
+    }
   }
   {  // policy head
     Launch l;
@@ -734,6 +741,7 @@ static int build_plan(b200sac* h) {
   {  // critic heads: y, Q1, Q2, dQ
     Launch l;
     l.kind = L_CHEADS;
+    l.join = true;                 // needs Q1,Q2 on (s,a), which may have run on the fork stream
     l.grid = dim3((B + 7) / 8, R);
     l.block = dim3(256);
     CriticHeadArgs& P = l.ch;
