@@ -404,13 +404,13 @@ def main():
     # DRAM traffic of one step from the committed ncu capture of this workload / back-end (cold caches under ncu: an upper
     # bound -- in the running step parameters, Adam state and activations stay in the 126 MB L2); null when not captured
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
     if os.path.exists(tpath) and R == 1 and (args.workload, args.precision) in (("LL", 0), ("VS", 1)):
         with open(tpath) as f:
             tj = json.load(f).get(args.workload)
         if tj:
             traffic = tj["dram_read_bytes_per_step"] + tj["dram_write_bytes_per_step"]
-            traffic_src = "profiles/r1b_traffic.json: " + tj["source"]
+            traffic_src = "profiles/r1c_traffic.json: " + tj["source"]
     roofline = {
         "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": ach_gbs / pk["hbm"],
         "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per step (= per graph launch)", "traffic_source": traffic_src,

@@ -7,7 +7,7 @@ TAG=${1:-r1b}
 OUT=gpurun_out
 mkdir -p $OUT
 B="python bench.py --no-cpu --ring 65536 --e2e-steps 2"
-ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 66 --csv --log-file $OUT/${TAG}_launches_LL_ffma.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 78 --csv --log-file $OUT/${TAG}_launches_LL_ffma.csv \
     $B --workload LL --precision 0 --steps 20 --warmup 5 > $OUT/ncu_ll.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 87 --csv --log-file $OUT/${TAG}_launches_VS_tc.csv \
     $B --workload VS --precision 1 --steps 20 --warmup 5 > $OUT/ncu_vs.log 2>&1
