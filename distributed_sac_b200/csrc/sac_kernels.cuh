@@ -213,6 +213,9 @@ __global__ void sample_indices_kernel(StepConst K, const Counters* __restrict__ 
       }
     }
     __syncthreads();
+    // read the round's verdict NOW: thread 0 resets the counter at the top of the next round, and the only barrier between
+    // here and there is the one below -- reading it after that barrier raced with the reset (compute-sanitizer racecheck)
+    const int pending = unresolved;
     // winners lock their table entry so that a lower slot redrawing later cannot steal it
 #pragma unroll
     for (int j = 0; j < kMaxPer; ++j) {
@@ -220,7 +223,7 @@ __global__ void sample_indices_kernel(StepConst K, const Counters* __restrict__ 
       if (i < B && done[j] && pos[j] >= 0 && owner[pos[j]] == i) owner[pos[j]] = -1;
     }
     __syncthreads();
-    if (unresolved == 0) break;
+    if (pending == 0) break;
   }
 }
 
