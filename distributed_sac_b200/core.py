@@ -178,14 +178,13 @@ class SacCore:
         """Enqueue a consistent snapshot of the named parameter tensors and start its async copy to pinned host
         memory (b200sac_publish_begin); steps enqueued afterwards overlap it.  Collect with publish_wait()."""
         ents = sorted((self.table[n][0], self.table[n][1] * self.table[n][5], n) for n in tensor_names)
-        ranges, where, at = [], {}, 0            # merge adjacent tensors into as few copies as possible
+        ranges, where = [], {}                   # merge neighbouring tensors (16-B alignment gaps of <= 3 floats are copied along)
         for off, cnt, n in ents:
-            if ranges and ranges[-1][0] + ranges[-1][1] == off:
-                ranges[-1][1] += cnt
+            if ranges and 0 <= off - (ranges[-1][0] + ranges[-1][1]) <= 3:
+                ranges[-1][1] = off + cnt - ranges[-1][0]
             else:
                 ranges.append([off, cnt])
-            where[n] = at
-            at += cnt
+            where[n] = sum(r[1] for r in ranges[:-1]) + (off - ranges[-1][0])
         offs = (C.c_int64 * len(ranges))(*[r[0] for r in ranges])
         cnts = (C.c_int64 * len(ranges))(*[r[1] for r in ranges])
         _lib.check(self.lib.b200sac_publish_begin(self._h, replica, len(ranges), offs, cnts, _stream()))
