@@ -283,6 +283,7 @@ struct b200sac {
   // split-K weight gradients: slices 1..gslices-1 of the gradient arena, [slice-1][R][trainable] (slice 0 = grads)
   float* grads_x = nullptr;
   int gslices = 1;
+  unsigned long long act_calls = 0;     // b200sac_act invocations (noise stream selector)
   // graphs
   std::map<GraphKey, cudaGraphExec_t> graphs;
   // host staging for step_host / pinned replay
@@ -1941,6 +1942,67 @@ extern "C" int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host
   if (!h || !out_host) return fail(B200SAC_ERR_INVALID, "null argument");
   CU(cudaSetDevice(h->device));
   return fetch_losses(h, (cudaStream_t)stream, n_last, out_host);
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched policy inference: the actor forward + tanh-Gaussian head the step uses, on n <= 2B
+// caller-provided observation rows -- Actor.get_action (LunarLander_Distributed_SAC/src/model.py:67-82; MT: mtobs rows,
+// MT10_Distributed_MTSAC/src/model.py:58-73) for many environments at once.  stochastic = 0 gives k*tanh(mu).
+// Uses the actor's own work buffers, so it is ordered with the steps on `stream` like any other call of the handle.
+// ------------------------------------------------------------------------------------------
+extern "C" int b200sac_act(b200sac_t* h, int32_t replica, int32_t n, const float* obs, const float* eps, int32_t stochastic,
+                           float* actions_out, void* stream) {
+  if (!h || !obs || !actions_out) return fail(B200SAC_ERR_INVALID, "null argument");
+  if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica %d out of range", replica);
+  const b200sac_cfg& c = h->cfg;
+  const int B = c.batch, A = c.act_dim, La = c.n_actor_hidden;
+  if (n < 1 || n > 2 * B) return fail(B200SAC_ERR_INVALID, "n must be in [1, 2*batch = %d], got %d", 2 * B, n);
+  if (c.care) return fail(B200SAC_ERR_INVALID, "b200sac_act: CARE actors need the state encoder path (not built)");
+  CU(cudaSetDevice(h->device));
+  StreamBridge sb(h, stream);
+  if (int rc = sb.begin()) return rc;
+  cudaStream_t st = sb.run;
+  const Layout& L = h->L;
+  const int obs_w = h->K.obs;
+  float* XA = h->XA.p + (long long)replica * h->XA.rs;
+  CU(cudaMemcpy2DAsync(XA, (size_t)h->K.ldxa * sizeof(float), obs, (size_t)obs_w * sizeof(float), (size_t)obs_w * sizeof(float),
+                       (size_t)n, cudaMemcpyDefault, st));
+  for (int l = 0; l < La; ++l) {
+    const LayerOff& lo = L.actor[l];
+    GemmGroup grp;
+    memset(&grp, 0, sizeof(grp));
+    grp.G = 1;
+    GemmProb& p = grp.p[0];
+    p.A = (l == 0 ? XA : h->hA[l - 1].p + (long long)replica * h->hA[l - 1].rs); p.lda = lo.ld;
+    p.B = h->params + (long long)replica * L.arena + lo.w; p.ldb = lo.ld;
+    p.bias = h->params + (long long)replica * L.arena + lo.b;
+    p.C = h->hA[l].p + (long long)replica * h->hA[l].rs; p.ldc = lo.out;
+    p.M = n; p.N = lo.out; p.K = lo.in; p.mode = GEMM_FWD; p.relu = 1;
+    gemm_simt_kernel<<<dim3((p.N + GS_T - 1) / GS_T, (p.M + GS_T - 1) / GS_T, 1), GS_THREADS, 0, st>>>(grp);
+  }
+  PolicyHeadArgs P = h->plan[(size_t)h->use_eps_buf_idx].pol;
+  P.h += replica * P.rsH; P.W += replica * P.rsP; P.b += replica * P.rsP; P.eps += replica * P.rsEps;
+  P.pout += replica * P.rsPout; P.psave += replica * P.rsSave; P.XT += replica * P.rsX; P.XP += replica * P.rsX;
+  P.act_out += replica * P.rsAct; P.logp += replica * P.rsLogp; P.logstd_sum += replica * P.rsLogp; P.cnt += replica;
+  P.rows = n;
+  float* epsb = h->eps.p + (long long)replica * h->eps.rs;
+  if (eps != nullptr) {
+    CU(cudaMemcpyAsync(epsb, eps, (size_t)n * A * sizeof(float), cudaMemcpyDefault, st));
+    P.use_eps_buf = 1;
+  } else if (!stochastic) {
+    CU(cudaMemsetAsync(epsb, 0, (size_t)n * A * sizeof(float), st));       // u = mu: Actor.get_action(stochastic=False)
+    P.use_eps_buf = 1;
+  } else {
+    P.use_eps_buf = 0;
+  }
+  StepConst K = h->K;
+  K.seed ^= 0x5851F42D4C957F2Dull * (unsigned long long)(++h->act_calls);    // fresh noise per call, not per training step
+  policy_head_kernel<<<dim3((n + 7) / 8, 1), 256, 0, st>>>(K, P);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(actions_out, h->act_out.p + (long long)replica * h->act_out.rs, (size_t)n * A * sizeof(float), cudaMemcpyDefault, st));
+  if (int rc = sb.end()) return rc;
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
 }
 
 extern "C" int b200sac_soft_update(b200sac_t* h, double tau, void* stream) {

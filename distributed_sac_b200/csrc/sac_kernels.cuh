@@ -245,6 +245,7 @@ struct PolicyHeadArgs {
   float* logp; long long rsLogp;              // [2B]
   float* logstd_sum;                          // [2B] sum_j log(std) (entropy statistic, MS/learner.py:310)
   const Counters* cnt;
+  int rows;                                   // 0: all 2B rows (a training step); n: only rows [0, n) (b200sac_act)
 };
 
 struct PolicyPoint {   // everything the backward needs for one (row, action)
@@ -276,7 +277,7 @@ __global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int row = blockIdx.x * (blockDim.x / 32) + warp;
   const int B = K.B, A = K.act, NO = 2 * K.act, H = K.Ha;
-  if (row >= 2 * B) return;
+  if (row >= (P.rows > 0 ? P.rows : 2 * B)) return;
   const float* hr = P.h + rep * P.rsH + (long long)row * P.ldh;
   const float* W = P.W + rep * P.rsP;
   const float* bias = P.b + rep * P.rsP;

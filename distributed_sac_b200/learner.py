@@ -162,6 +162,11 @@ class _BaseLearner:
         while len(self.memory) <= self.start_memory_len:
             time.sleep(0.1)
 
+    def act_batch(self, states, stochastic=True):
+        """Actor.get_action (LL/model.py:67-82) for a batch of environments at once with the learner's current actor:
+        states [n][obs_dim] (n <= 2*batch_size) -> actions [n][action_dim] on the CPU."""
+        return self.core.act(torch.as_tensor(states), stochastic=stochastic)
+
     # ---- parameter publication (LL/learner.py:272-276; consumed by Player.pull_parameters, player.py:75-85) ----
     _published = ("actor",)
 

@@ -161,6 +161,14 @@ int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host, void* str
  * the hard copy Learner.run() does before training, learner.py:287-288). */
 int b200sac_soft_update(b200sac_t* h, double tau, void* stream);
 
+/* Batched policy inference for n <= 2*batch observation rows obs[n][obs_dim] (obs_dim = state_dim + num_tasks), host or
+ * device memory: actions[n][act_dim] = k * tanh(mu + std * eps) -- Actor.get_action
+ * (LunarLander_Distributed_SAC/src/model.py:67-82, MT10_Distributed_MTSAC/src/model.py:58-73) vectorised over environments.
+ * eps (nullable, [n][act_dim]) injects the noise; eps == NULL: stochastic != 0 draws fresh Philox noise, stochastic == 0
+ * returns the deterministic action k * tanh(mu).  Not available for CARE handles.  Synchronises the stream. */
+int b200sac_act(b200sac_t* h, int32_t replica, int32_t n, const float* obs, const float* eps, int32_t stochastic,
+                float* actions_out, void* stream);
+
 /* Publication path = Learner.get_parameters() (LunarLander_Distributed_SAC/src/learner.py:272-276,298-299;
  * MT10_Distributed_CARE/src/learner.py:412-417,442-443), which the reference runs after every update.
  * publish_begin enqueues, in stream order, a consistent device snapshot of `n_ranges` ranges
