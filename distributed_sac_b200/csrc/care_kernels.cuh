@@ -67,8 +67,42 @@ __global__ void __launch_bounds__(512) care_tables_kernel(CareTabArgs P) {
       const int nin = N.dims[j], nout = N.dims[j + 1];
       const float* __restrict__ W = par + delta + N.w[j];
       const float* __restrict__ bb = par + delta + N.b[j];
+      if (nin <= 64) {
+        // narrow layer: a warp's (up to four) output neurons are evaluated together -- all their weights and biases are
+        // requested before the first FMA, so the layer costs one memory round trip instead of one per neuron
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f}, w0[4], w1[4];
+        const float x0 = lane < nin ? cur[lane] : 0.f, x1 = lane + 32 < nin ? cur[lane + 32] : 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int o = warp + 16 * g;
+          const float* __restrict__ wr = W + (long long)o * nin;
+          w0[g] = (o < nout && lane < nin) ? __ldg(wr + lane) : 0.f;
+          w1[g] = (o < nout && lane + 32 < nin) ? __ldg(wr + lane + 32) : 0.f;
+          bv[g] = o < nout ? __ldg(bb + o) : 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int o = warp + 16 * g;
+          if (o < nout) {                                  // warp-uniform
+            a[g] = fmaf(x0, w0[g], a[g]);
+            a[g] = fmaf(x1, w1[g], a[g]);
+            float v = warp_sum(a[g]) + bv[g];
+            if (j < N.n - 1) v = fmaxf(v, 0.f);
+            if (lane == 0) { nxt[o] = v; row[N.act_off[j] + o] = v; }
+          }
+        }
+        for (int o = warp + 64; o < nout; o += 16) {     // wider-than-64-output layers: remaining neurons one at a time
+          const float* __restrict__ wr = W + (long long)o * nin;
+          float acc = fmaf(x0, lane < nin ? __ldg(wr + lane) : 0.f, 0.f);
+          acc = fmaf(x1, lane + 32 < nin ? __ldg(wr + lane + 32) : 0.f, acc);
+          float v = warp_sum(acc) + bb[o];
+          if (j < N.n - 1) v = fmaxf(v, 0.f);
+          if (lane == 0) { nxt[o] = v; row[N.act_off[j] + o] = v; }
+        }
+      } else
       for (int o = warp; o < nout; o += 16) {
         const float* __restrict__ wr = W + (long long)o * nin;
+        const float bo = __ldg(bb + o);                    // bias requested with the weights, not after the reduction
         float a = 0.f;
         int i = lane;
         for (; i + 23 * 32 < nin; i += 24 * 32) {        // 768-wide rows: the whole row in flight (one round trip, not three)
@@ -86,7 +120,7 @@ __global__ void __launch_bounds__(512) care_tables_kernel(CareTabArgs P) {
           for (int u = 0; u < 8; ++u) a = fmaf(cur[i + u * 32], wv[u], a);
         }
         for (; i < nin; i += 32) a = fmaf(cur[i], __ldg(wr + i), a);
-        a = warp_sum(a) + bb[o];
+        a = warp_sum(a) + bo;
         if (j < N.n - 1) a = fmaxf(a, 0.f);
         if (lane == 0) { nxt[o] = a; row[N.act_off[j] + o] = a; }
       }
