@@ -6,10 +6,12 @@
  * `ReplayBuffer`.  Each entry point below names the reference code it replaces
  * (paths relative to the reference checkout):
  *
- *   b200sac_step*            Learner.update() -> update_SAC()
+ *   b200sac_step*, b200sac_update
+ *                            Learner.update() -> update_SAC()
  *                            LunarLander_Distributed_SAC/src/learner.py:246-264,203-239
  *                            MT1_Distributed_VSAC/src/learner.py:205-244,251-269
  *                            MT10_Distributed_MTSAC/src/learner.py:253-325,332-352
+ *                            MT10_Distributed_CARE/src/learner.py:281-404 (care = 1 | 2), MT1_Distributed_CARE/src/learner.py:247-348
  *   b200sac_replay_*         ReplayBuffer.sample()/__len__ and the append in run()
  *                            LunarLander_Distributed_SAC/src/replay_buffer.py:43-77
  *                            MT10_Distributed_MTSAC/src/replay_buffers.py:47-107
@@ -18,6 +20,8 @@
  *                            LunarLander_Distributed_SAC/src/learner.py:100-124,144-163,272-276
  *   b200sac_soft_update      Learner.soft_update()            learner.py:126-137
  *   b200sac_publish_*        Learner.get_parameters()         learner.py:272-276 (called at :298-299)
+ *   b200sac_act              Actor.get_action() for a batch of environments
+ *                            LunarLander_Distributed_SAC/src/model.py:67-82
  *
  * Conventions: plain pointers and sizes only (no torch types).  Every function
  * returns 0 on success or a negative b200sac_status; a message for the calling
