@@ -47,6 +47,7 @@ SYMBOLS = {
     "b200sac_destroy": (C.c_int, [_VP]),
     "b200sac_export": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64, _VP]),
     "b200sac_import": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64, _VP]),
+    "b200sac_read_range": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _VP, _VP]),
     "b200sac_arena_ptr": (C.c_int, [_VP, C.c_int32, C.POINTER(_VP), C.POINTER(C.c_int64)]),
     "b200sac_get_steps": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_int64)]),
     "b200sac_set_steps": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_int64)]),
@@ -54,6 +55,7 @@ SYMBOLS = {
     "b200sac_step_host": (C.c_int, [_VP] + [_VP] * 7 + [_VP, _VP]),
     "b200sac_step_sampled": (C.c_int, [_VP, _VP, C.c_int32, _VP]),
     "b200sac_update": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "b200sac_prepare": (C.c_int, [_VP, _VP, _VP]),
     "b200sac_read_losses": (C.c_int, [_VP, C.c_int32, _VP, _VP]),
     "b200sac_soft_update": (C.c_int, [_VP, C.c_double, _VP]),
     "b200sac_act": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, _VP, C.c_int32, _VP, _VP]),

@@ -164,6 +164,10 @@ class SacCore:
         """One layout-table entry read out of `flat` (float32 numpy array) at float offset `off`, as a fresh CPU tensor in
         the reference's shape.  numpy copies on purpose: a 256x256 torch .clone() fans out to the intra-op thread pool,
         which costs milliseconds on a busy host -- this runs after every update (publication path)."""
+        return torch.from_numpy(np.array(self._view(name, flat, off), dtype=np.float32, order="C", copy=True))
+
+    def _view(self, name, flat, off):
+        """numpy view (no copy) of one layout-table entry inside `flat`, in the reference's shape."""
         _, rows, cols, _t, _o, pitch = self.table[name]
         a = flat[off:off + rows * pitch].reshape(rows, pitch)[:, :cols]
         if ".mix." in name:            # stored as [K][out][in] | [K][out]; the reference holds (K,in,out) | (K,1,out)
@@ -171,7 +175,7 @@ class SacCore:
             a = (a.reshape(K, rows // K, cols).transpose(0, 2, 1) if name.endswith(".W") else a.reshape(K, 1, rows // K))
         elif not (name.endswith(".weight") or name == "embedding"):
             a = a.reshape(-1)
-        return torch.from_numpy(np.array(a, dtype=np.float32, order="C", copy=True))
+        return a
 
     def act(self, obs, stochastic=True, eps=None, replica=0) -> torch.Tensor:
         """Batched Actor.get_action for n <= 2*batch observation rows (CPU or CUDA tensor [n][obs_dim]); returns a CPU tensor
@@ -199,6 +203,21 @@ class SacCore:
         cnts = (C.c_int64 * len(ranges))(*[r[1] for r in ranges])
         _lib.check(self.lib.b200sac_publish_begin(self._h, replica, len(ranges), offs, cnts, _stream()))
         self._pub_where = where
+
+    def read_named(self, name, which=_lib.PARAMS, replica=0) -> torch.Tensor:
+        """One small tensor (e.g. log_alpha) straight from the device: a few floats cross PCIe, not the arena."""
+        off, rows, cols, _t, _o, pitch = self.table[name]
+        out = torch.empty(rows * pitch)
+        _lib.check(self.lib.b200sac_read_range(self._h, which, replica, off, rows * pitch, _ptr(out), _stream()))
+        return self._unpack(name, out.numpy(), 0)
+
+    def publish_views(self) -> Dict[str, np.ndarray]:
+        """Like publish_wait(), but returns numpy VIEWS of the pinned snapshot in the reference's shapes (no copy); valid
+        until the next publish_begin()."""
+        ptr, n = C.POINTER(C.c_float)(), C.c_int64()
+        _lib.check(self.lib.b200sac_publish_wait(self._h, C.byref(ptr), C.byref(n)))
+        flat = np.ctypeslib.as_array(ptr, shape=(n.value,))
+        return {name: self._view(name, flat, at) for name, at in self._pub_where.items()}
 
     def publish_wait(self) -> Dict[str, torch.Tensor]:
         ptr, n = C.POINTER(C.c_float)(), C.c_int64()
@@ -284,6 +303,10 @@ class SacCore:
         _lib.check(self.lib.b200sac_step_sampled(self._h, replay._h, int(n_steps), _stream()))
         self.steps_done += int(n_steps)
 
+    def prepare(self, replay: "Replay"):
+        """Instantiate every CUDA graph the sampled path can launch for this ring (no step is run)."""
+        _lib.check(self.lib.b200sac_prepare(self._h, replay._h, _stream()))
+
     def update_sampled(self, replay: "Replay"):
         """sample + one gradient step + that step's losses of replica 0 as python floats (critic, actor, alpha, entropy):
         one library call, no tensor round trips -- the body of Learner.update()."""
@@ -318,7 +341,13 @@ class SacCore:
         return [float(out[i]) for i in range(n.value)]
 
     def debug(self, name: str, replica=0) -> torch.Tensor:
+        """Per-step intermediates (b200sac_debug_read): y, q1, ..., and the hidden activations "hA.<l>", "hQ.<l>", "hP.<l>",
+        "hT.<l>", "mixH.<inst>.<l>" whose sign patterns are the ReLU masks the step used."""
         cap = self.cfg.batch * max(2 * self.cfg.act_dim, 1)
+        if name[0] == "h" or name.startswith("mixH"):
+            widest = max(list(self.cfg.actor_hidden) + list(self.cfg.critic_hidden) + [4 * ((w + 3) // 4) * self.cfg.num_encoders
+                                                                                        for w in self.cfg.mix_hidden])
+            cap = 2 * self.cfg.batch * widest
         out = torch.empty(cap)
         n = C.c_int64(0)
         _lib.check(self.lib.b200sac_debug_read(self._h, name.encode(), replica, _ptr(out), cap, C.byref(n), _stream()))

@@ -25,6 +25,7 @@
 #include "gemm_tc.cuh"
 #include "sac_kernels.cuh"
 #include "care_kernels.cuh"
+#include "chain.cuh"
 
 using namespace bsac;
 
@@ -213,7 +214,7 @@ struct Buf {           // [R][n] fp32 (or int32) slab slice
   long long rs = 0;    // replica stride in floats
 };
 
-enum LaunchKind { L_POLICY_DOUT, L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_THIN, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM };
+enum LaunchKind { L_POLICY_DOUT, L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_THIN, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM, L_CHAIN, L_WGRAD };
 
 struct Launch {
   LaunchKind kind;
@@ -237,6 +238,9 @@ struct Launch {
   ActorQHeadArgs aq;
   HeadBwdArgs hb;
   AdamArgs ad;
+  ChainArgs chain;
+  WgradArgs wg;
+  const char* label = nullptr;
 };
 
 struct GraphKey {
@@ -265,7 +269,10 @@ struct b200sac {
   float* slab = nullptr;
   size_t slab_floats = 0;
   Buf XA, XQ, XT, XP, r, d, tid, eps, pout, psave, act_out, logp, logstd, y, q, dq, lq, dqa, la, qmin, dxP,
-      dout_dbg, dact_dbg;
+      dout_dbg, dact_dbg, qt, qp;
+  bool stamping = false;          // true while b200sac_graph_timeline runs on this handle (one unforked step per graph)
+  bool fused = false;             // layer-chained plan (chain.cuh): every hidden width <= 256, exact-fp32 mode, no CARE
+  PolicyHeadArgs pol;             // the policy head's arguments (also used by b200sac_act)
   // CARE
   Buf XS, careTab[3], careDtab, careDatt, mixZ[3], mixDZ;     // instances: 0 = critic's (old) on [s';s], 1 = target's on s', 2 = critic's (new) on s
   std::vector<Buf> mixH[3], mixDH;                             // per mixture hidden layer: [K][rows][pitch]
@@ -308,6 +315,7 @@ struct b200sac {
   float* pub_h = nullptr;         // pinned host copy handed to the caller
   int64_t pub_cap = 0, pub_n = 0;
   bool pub_pending = false;
+  float* split_d = nullptr;       // b200sac_step: handle-owned copy of the caller's minibatch arrays (stable graph pointers)
   float* loss_h = nullptr;        // mapped pinned loss ring [kLossSlots][R][4], written by the tail kernels
   float* loss_h_dev = nullptr;    // its device-side address
 };
@@ -325,6 +333,8 @@ struct b200sac_replay {
   unsigned long long seed = 0;
   std::mt19937_64 rng;
   std::mutex mu;
+  cudaEvent_t ev_gather = nullptr;   // device ring: recorded after the last enqueued gather (pushes wait for it under `mu`)
+  bool gather_pending = false;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -357,6 +367,7 @@ static int destroy_impl(b200sac* h) {
   if (h->ev_pub_snap) cudaEventDestroy(h->ev_pub_snap);
   if (h->ev_pub_done) cudaEventDestroy(h->ev_pub_done);
   cudaFree(h->pub_d);
+  cudaFree(h->split_d);
   if (h->pub_h) cudaFreeHost(h->pub_h);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->fork) cudaStreamDestroy(h->fork);
@@ -432,6 +443,225 @@ static int make_tc_prob(const GemmProb& p, int rep, TcProb& t, int bn = 64) {
     if (int rc = make_map(&t.tmA, A, p.M, p.K, p.lda, TC_BK, true)) return rc;
     if (int rc = make_map(&t.tmB, B, p.N, p.K, p.ldb, TC_BK, true)) return rc;
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Layer-chained plan (chain.cuh): 10 launches per step instead of one per layer.
+//   A   forward  {actor on [s';s], Q1, Q2 on (s,a)}  -> policy head / scalar heads
+//   B   forward  {Qt1, Qt2 on (s',a')}               -> scalar heads
+//   C   backward {Q1, Q2}: y, dQ from the per-row scalars, input-gradient chain   -> wgrad -> adam_critic+polyak
+//   D1  forward  {Q1, Q2 on (s,a~)} with the updated critics
+//   D2  backward {Q1, Q2}: min routing, input-gradient chain down to d(action)
+//   E   backward {actor}: d(mu|log_std), input-gradient chain                     -> wgrad -> adam_actor+alpha
+// Eligible: exact-fp32 mode, no CARE, every hidden width a multiple of 4 and <= 256, obs+act <= 252.
+// ------------------------------------------------------------------------------------------
+static bool fused_eligible(const b200sac_cfg& c) {
+  if (c.precision != 0 || c.care) return false;
+  if (const char* e = getenv("B200SAC_FUSE")) if (e[0] == '0') return false;
+  for (int i = 0; i < c.n_actor_hidden; ++i) if (c.actor_hidden[i] % 4 || c.actor_hidden[i] > CH_MAXW) return false;
+  for (int i = 0; i < c.n_critic_hidden; ++i) if (c.critic_hidden[i] % 4 || c.critic_hidden[i] > CH_MAXW) return false;
+  if (c.state_dim + c.num_tasks + c.act_dim > CH_MAXW - 4) return false;
+  return true;
+}
+
+static int build_plan_fused(b200sac* h, const std::function<void(int)>& adam) {
+  const b200sac_cfg& c = h->cfg;
+  const Layout& L = h->L;
+  const int B = c.batch, R = h->R, A = c.act_dim;
+  const int La = c.n_actor_hidden, Lc = c.n_critic_hidden;
+  const long long rsP = L.arena, rsG = L.trainable;
+  auto W = [&](int64_t off) { return h->params + off; };
+  auto Gp = [&](int64_t off) { return h->grads + off; };
+  const int Hc = c.critic_hidden[Lc - 1], Ha = c.actor_hidden[La - 1];
+
+  ChainRows rw;
+  memset(&rw, 0, sizeof(rw));
+  rw.r = h->r.p; rw.d = h->d.p; rw.tid = (const int*)h->tid.p; rw.rsR = h->r.rs;
+  rw.logp = h->logp.p; rw.rsLogp = h->logp.rs;
+  rw.log_alpha = W(L.off_alpha);
+  rw.qt = h->qt.p; rw.q = h->q.p; rw.qp = h->qp.p;
+  rw.y = h->y.p; rw.dq = h->dq.p; rw.lq = h->lq.p; rw.dqa = h->dqa.p; rw.la = h->la.p; rw.qmin = h->qmin.p; rw.rsY = h->y.rs;
+  rw.dxP = h->dxP.p; rw.rsDxNet = (long long)B * h->K.ldx; rw.rsDxRep = h->dxP.rs; rw.lddx = h->K.ldx;
+  rw.psave = h->psave.p + (long long)B * A * kSaveW; rw.rsSave = h->psave.rs;
+  rw.dout_dbg = h->dout_dbg.p; rw.dact_dbg = h->dact_dbg.p; rw.rsDbg = h->dout_dbg.rs;
+
+  auto new_chain = [&](const char* label) {
+    Launch l;
+    l.kind = L_CHAIN;
+    l.label = label;
+    memset(&l.chain, 0, sizeof(l.chain));
+    l.chain.rsP = rsP;
+    l.chain.pol = h->pol;
+    l.chain.rw = rw;
+    l.block = dim3(CH_THREADS);
+    l.smem = CH_SMEM_BYTES;
+    return l;
+  };
+  auto finish_chain = [&](Launch& l) {
+    int maxb = 1;
+    for (int j = 0; j < l.chain.njobs; ++j) {
+      const int nb = (l.chain.job[j].rows + CH_ROWS - 1) / CH_ROWS;
+      maxb = nb > maxb ? nb : maxb;
+    }
+    l.grid = dim3(maxb, l.chain.njobs, R);
+    h->plan.push_back(l);
+  };
+  // forward job of one MLP: input rows X, per-layer stores `store[l]` (+ net offset), head
+  auto fwd_job = [&](ChainJob& J, const std::vector<LayerOff>& net, int nh, const float* X, long long rsX, int ldx, int K0, int rows,
+                     const std::vector<Buf>* store, int net_idx, int rows_per_net) {
+    memset(&J, 0, sizeof(J));
+    J.kind = CJ_FWD; J.rows = rows; J.nstages = nh; J.net = net_idx;
+    J.X = X; J.rsX = rsX; J.ldx = ldx; J.K0 = K0;
+    for (int l = 0; l < nh; ++l) {
+      const LayerOff& lo = net[l];
+      ChainStage& S = J.st[l];
+      S.W = W(lo.w); S.bias = W(lo.b); S.ldw = lo.ld; S.K = lo.in; S.N = lo.out;
+      if (store) { S.out = (*store)[l].p + (long long)net_idx * rows_per_net * lo.out; S.rsOut = (*store)[l].rs; S.ldo = lo.out; }
+    }
+    const LayerOff& hd = net[nh];
+    J.Wh = W(hd.w); J.bh = W(hd.b); J.NO = hd.out; J.Hh = hd.in;
+  };
+  // backward job of one MLP (input-gradient chain): gate activations acts[l], stores dstore[l] (nullable)
+  auto bwd_job = [&](ChainJob& J, int kind, const std::vector<LayerOff>& net, int nh, int rows, const std::vector<Buf>& acts,
+                     long long act_row_off /* rows to skip in acts */, const std::vector<Buf>* dstore, int net_idx) {
+    memset(&J, 0, sizeof(J));
+    J.kind = kind; J.rows = rows; J.nstages = nh - 1; J.net = net_idx;
+    const LayerOff& hd = net[nh];
+    J.Wh = W(hd.w); J.bh = W(hd.b); J.NO = hd.out; J.Hh = hd.in;
+    const int Hl = net[nh - 1].out;
+    J.hlast = acts[nh - 1].p + ((long long)net_idx * rows + act_row_off) * Hl; J.rsHlast = acts[nh - 1].rs; J.ldh = Hl;
+    if (dstore) { J.dylast = (*dstore)[nh - 1].p + (long long)net_idx * rows * Hl; J.rsDy = (*dstore)[nh - 1].rs; J.lddy = Hl; }
+    for (int s = 0; s + 1 < nh; ++s) {
+      const int l = nh - 1 - s;                    // dh_{l-1} = (dh_l W_l) * [h_{l-1} > 0]
+      const LayerOff& lo = net[l];
+      ChainStage& S = J.st[s];
+      S.W = W(lo.w); S.ldw = lo.ld; S.K = lo.out; S.N = lo.in;
+      S.mask = acts[l - 1].p + ((long long)net_idx * rows + act_row_off) * lo.in; S.rsMask = acts[l - 1].rs; S.ldmask = lo.in;
+      if (dstore) { S.out = (*dstore)[l - 1].p + (long long)net_idx * rows * lo.in; S.rsOut = (*dstore)[l - 1].rs; S.ldo = lo.in; }
+    }
+  };
+  // weight-gradient launch of a group of networks
+  struct WNet { const std::vector<LayerOff>* net; int nh; const std::vector<Buf>* dstore; const std::vector<Buf>* acts; long long act_row_off;
+                const float* X; long long rsX; int ldx; const float* dout; long long rsDout; int lddout; int net_idx; };
+  auto wgrad_launch = [&](const std::vector<WNet>& nets, const char* label) -> int {
+    Launch l;
+    l.kind = L_WGRAD;
+    l.label = label;
+    memset(&l.wg, 0, sizeof(l.wg));
+    l.wg.M = B; l.wg.rsG = rsG;
+    int tiles = 0;
+    auto add = [&](const float* Ap, long long rsA, int lda, const float* Bp, long long rsB, int ldb, int64_t offW, int ldc, int64_t offB,
+                   int Kout, int Nin) -> int {
+      if (l.wg.njobs >= WG_MAXJOBS) return fail(B200SAC_ERR_INVALID, "too many weight-gradient jobs in one launch");
+      WgradJob& J = l.wg.job[l.wg.njobs++];
+      J.A = Ap; J.rsA = rsA; J.lda = lda; J.B = Bp; J.rsB = rsB; J.ldb = ldb;
+      J.C = Gp(offW); J.C2 = Gp(offB); J.ldc = ldc; J.Kout = Kout; J.Nin = Nin;
+      J.tile0 = tiles; J.tn = (Nin + WG_T - 1) / WG_T;
+      tiles += J.tn * ((Kout + WG_T - 1) / WG_T);
+      return 0;
+    };
+    for (const WNet& n : nets) {
+      const std::vector<LayerOff>& net = *n.net;
+      for (int lyr = n.nh - 1; lyr >= 0; --lyr) {      // biggest layers first
+        const LayerOff& lo = net[lyr];
+        const Buf& db = (*n.dstore)[lyr];
+        const float* Ap = db.p + (long long)n.net_idx * B * lo.out;
+        const float* Bp; long long rsB; int ldb;
+        if (lyr == 0) { Bp = n.X; rsB = n.rsX; ldb = n.ldx; }
+        else {
+          const Buf& ab = (*n.acts)[lyr - 1];
+          Bp = ab.p + ((long long)n.net_idx * B + n.act_row_off) * lo.in; rsB = ab.rs; ldb = lo.in;   // (actor: [s';s], skip the s' half)
+        }
+        if (int rc = add(Ap, db.rs, lo.out, Bp, rsB, ldb, lo.w, lo.ld, lo.b, lo.out, lo.in)) return rc;
+      }
+      const LayerOff& hd = net[n.nh];
+      const Buf& ab = (*n.acts)[n.nh - 1];
+      const float* Bp = ab.p + ((long long)n.net_idx * B + n.act_row_off) * hd.in;
+      if (int rc = add(n.dout, n.rsDout, n.lddout, Bp, ab.rs, hd.in, hd.w, hd.in, hd.b, hd.out, hd.in)) return rc;
+    }
+    l.grid = dim3(tiles, R);
+    l.block = dim3(WG_THREADS);
+    l.smem = WG_SMEM_BYTES;
+    h->plan.push_back(l);
+    return 0;
+  };
+
+  // ---- A: actor over [s';s], Q1/Q2 over (s,a) ----------------------------------------------------------------------
+  {
+    Launch l = new_chain("chain_fwd{actor,q1,q2}");
+    l.chain.njobs = 3;
+    fwd_job(l.chain.job[0], L.actor, La, h->XA.p, h->XA.rs, h->K.ldxa, h->K.in_w, 2 * B, &h->hA, 0, 0);
+    l.chain.job[0].head = CH_HEAD_POLICY;
+    for (int net = 0; net < 2; ++net) {
+      ChainJob& J = l.chain.job[1 + net];
+      fwd_job(J, L.q[net], Lc, h->XQ.p, h->XQ.rs, h->K.ldx, h->K.xw, B, &h->hQ, net, B);
+      J.head = CH_HEAD_SCALAR; J.qout = h->q.p + (long long)net * B; J.rsQ = h->q.rs;
+    }
+    h->use_eps_buf_idx = (int)h->plan.size();
+    finish_chain(l);
+  }
+  // ---- B: target critics over (s', a') -------------------------------------------------------------------------------
+  {
+    Launch l = new_chain("chain_fwd{qt1,qt2}");
+    l.chain.njobs = 2;
+    for (int net = 0; net < 2; ++net) {
+      ChainJob& J = l.chain.job[net];
+      fwd_job(J, L.qt[net], Lc, h->XT.p, h->XT.rs, h->K.ldx, h->K.xw, B, nullptr, net, B);
+      J.head = CH_HEAD_SCALAR; J.qout = h->qt.p + (long long)net * B; J.rsQ = h->qt.rs;
+    }
+    finish_chain(l);
+  }
+  // ---- C: critic backward, weight gradients, Adam + Polyak -------------------------------------------------------------
+  {
+    Launch l = new_chain("chain_bwd{q1,q2}");
+    l.chain.njobs = 2;
+    for (int net = 0; net < 2; ++net) bwd_job(l.chain.job[net], CJ_BWD_CRITIC, L.q[net], Lc, B, h->hQ, 0, &h->dhQ, net);
+    finish_chain(l);
+    std::vector<WNet> nets;
+    for (int net = 0; net < 2; ++net)
+      nets.push_back(WNet{&L.q[net], Lc, &h->dhQ, &h->hQ, 0, h->XQ.p, h->XQ.rs, h->K.ldx, h->dq.p + (long long)net * B, h->dq.rs, 1, net});
+    if (int rc = wgrad_launch(nets, "wgrad{q1,q2}")) return rc;
+    adam(0);
+  }
+  // ---- D: actor pass through the updated critics ------------------------------------------------------------------------
+  {
+    Launch l = new_chain("chain_fwd{q1,q2}(s,a~)");
+    l.chain.njobs = 2;
+    for (int net = 0; net < 2; ++net) {
+      ChainJob& J = l.chain.job[net];
+      fwd_job(J, L.q[net], Lc, h->XP.p, h->XP.rs, h->K.ldx, h->K.xw, B, &h->hP, net, B);
+      J.head = CH_HEAD_SCALAR; J.qout = h->qp.p + (long long)net * B; J.rsQ = h->qp.rs;
+    }
+    finish_chain(l);
+    Launch l2 = new_chain("chain_bwd{q1,q2}->d(action)");
+    l2.chain.njobs = 2;
+    for (int net = 0; net < 2; ++net) {
+      ChainJob& J = l2.chain.job[net];
+      bwd_job(J, CJ_BWD_ACTORQ, L.q[net], Lc, B, h->hP, 0, nullptr, net);
+      const LayerOff& lo = L.q[net][0];
+      J.head = CH_TAIL_DACTION;
+      J.W0 = W(lo.w); J.ldw0 = lo.ld; J.col0 = h->K.in_w; J.nact = A; J.H0 = lo.out;
+      J.dx = h->dxP.p + (long long)net * B * h->K.ldx; J.rsDx = h->dxP.rs; J.lddx = h->K.ldx;
+    }
+    finish_chain(l2);
+  }
+  // ---- E: policy backward, weight gradients, Adam + temperature ------------------------------------------------------------
+  {
+    Launch l = new_chain("chain_bwd{actor}");
+    l.chain.njobs = 1;
+    bwd_job(l.chain.job[0], CJ_BWD_POLICY, L.actor, La, B, h->hA, B, &h->dhA, 0);
+    finish_chain(l);
+    std::vector<WNet> nets;
+    nets.push_back(WNet{&L.actor, La, &h->dhA, &h->hA, (long long)B, h->XA.p + (long long)B * h->K.ldxa, h->XA.rs, h->K.ldxa,
+                        h->dout_dbg.p, h->dout_dbg.rs, 2 * A, 0});
+    if (int rc = wgrad_launch(nets, "wgrad{actor}")) return rc;
+    adam(1);
+  }
+  (void)Hc; (void)Ha;
+  CU(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES));
   return 0;
 }
 
@@ -684,6 +914,55 @@ static int build_plan(b200sac* h) {
   };
   auto netp = [&](const Buf& b, int net, int H) { return b.p + (long long)net * B * H; };
 
+  {  // policy head arguments (the generic plan's policy_head launch, the chained forward kernel and b200sac_act share them)
+    PolicyHeadArgs& P = h->pol;
+    memset(&P, 0, sizeof(P));
+    const LayerOff& lo = L.actor[La];
+    P.h = h->hA[La - 1].p; P.rsH = h->hA[La - 1].rs; P.ldh = lo.in;
+    P.W = W(lo.w); P.b = W(lo.b); P.rsP = rsP;
+    P.eps = h->eps.p; P.rsEps = h->eps.rs; P.use_eps_buf = 0;
+    P.pout = h->pout.p; P.rsPout = h->pout.rs;
+    P.psave = h->psave.p; P.rsSave = h->psave.rs;
+    P.XT = h->XT.p; P.XP = h->XP.p; P.rsX = h->XT.rs;
+    P.act_out = h->act_out.p; P.rsAct = h->act_out.rs;
+    P.logp = h->logp.p; P.rsLogp = h->logp.rs;
+    P.logstd_sum = h->logstd.p;
+    P.cnt = h->cnt;
+  }
+  auto adam = [&](int which) {
+    Launch l;
+    l.kind = L_ADAM;
+    AdamArgs& P = l.ad;
+    memset(&P, 0, sizeof(P));
+    const int64_t beg = which == 0 ? L.critic_begin : (which == 1 ? L.actor_begin : L.cenc_begin);
+    const int64_t n = which == 0 ? L.critic_n : (which == 1 ? L.actor_n : L.cenc_n);
+    P.p = h->params + beg; P.m = h->adam_m + beg; P.v = h->adam_v + beg; P.g = h->grads + beg;
+    P.rsP = rsP; P.rsM = rsG; P.n = n;
+    P.gx = h->grads_x ? h->grads_x + beg : nullptr; P.xs = (long long)R * L.trainable; P.nx = h->gslices - 1;
+    P.target_delta = which == 0 ? L.target_delta : 0;
+    P.tau2_begin = (which == 0 && c.care) ? (L.cse_begin - L.critic_begin) : (long long)1 << 60;
+    P.tau2 = (float)c.tau_se; P.one_minus_tau2 = (float)(1.0 - c.tau_se);
+    P.which = which == 2 ? 4 : which;                    // counter slot: 0 critic, 1 actor, 4 context encoder
+    P.lr = which == 0 ? c.lr_critic : (which == 1 ? c.lr_actor : c.lr_ctx);
+    P.cnt = h->cnt;
+    P.tail = which == 0 ? TAIL_CRITIC_LOSS : (which == 1 ? TAIL_ALPHA_AND_LOSSES : TAIL_NONE);
+    P.lq = h->lq.p; P.la = h->la.p; P.rsY = h->y.rs;
+    P.logp_cur = h->logp.p + B; P.logstd_sum = h->logstd.p + B; P.rsLogp = h->logp.rs;
+    P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
+    P.log_alpha = h->params + L.off_alpha;
+    P.m_alpha = h->adam_m + L.off_alpha; P.v_alpha = h->adam_v + L.off_alpha; P.g_alpha = h->grads + L.off_alpha;
+    P.losses = h->losses; P.losses_host = h->loss_h_dev; P.R = R;
+    int nb = (int)((n + 256 * 4 - 1) / (256 * 4));
+    if (nb < 1) nb = 1;
+    if (nb > 592) nb = 592;
+    l.grid = dim3(nb + (P.tail != TAIL_NONE ? 1 : 0), R);
+    l.block = dim3(256);
+    l.join = true;                 // every gradient of the slice must have landed, including the forked weight gradients
+    h->plan.push_back(l);
+  };
+  if (h->fused) {
+    if (int rc = build_plan_fused(h, adam)) return rc;
+  } else {
   // ---- Phase A: actor over [s2; s] and Q1,Q2 over (s,a), layer by layer -----------------
   for (int l = 0; l < (La > Lc ? La : Lc); ++l) {
     std::vector<GemmProb> ps;
@@ -712,19 +991,7 @@ static int build_plan(b200sac* h) {
     l.kind = L_POLICY;
     l.grid = dim3((2 * B + 7) / 8, R);
     l.block = dim3(256);
-    PolicyHeadArgs& P = l.pol;
-    memset(&P, 0, sizeof(P));
-    const LayerOff& lo = L.actor[La];
-    P.h = h->hA[La - 1].p; P.rsH = h->hA[La - 1].rs; P.ldh = lo.in;
-    P.W = W(lo.w); P.b = W(lo.b); P.rsP = rsP;
-    P.eps = h->eps.p; P.rsEps = h->eps.rs; P.use_eps_buf = 0;
-    P.pout = h->pout.p; P.rsPout = h->pout.rs;
-    P.psave = h->psave.p; P.rsSave = h->psave.rs;
-    P.XT = h->XT.p; P.XP = h->XP.p; P.rsX = h->XT.rs;
-    P.act_out = h->act_out.p; P.rsAct = h->act_out.rs;
-    P.logp = h->logp.p; P.rsLogp = h->logp.rs;
-    P.logstd_sum = h->logstd.p;
-    P.cnt = h->cnt;
+    l.pol = h->pol;
     h->use_eps_buf_idx = (int)h->plan.size();
     h->plan.push_back(l);
   }
@@ -932,37 +1199,6 @@ static int build_plan(b200sac* h) {
       h->plan.push_back(l2);
     }
   }
-  auto adam = [&](int which) {
-    Launch l;
-    l.kind = L_ADAM;
-    AdamArgs& P = l.ad;
-    memset(&P, 0, sizeof(P));
-    const int64_t beg = which == 0 ? L.critic_begin : (which == 1 ? L.actor_begin : L.cenc_begin);
-    const int64_t n = which == 0 ? L.critic_n : (which == 1 ? L.actor_n : L.cenc_n);
-    P.p = h->params + beg; P.m = h->adam_m + beg; P.v = h->adam_v + beg; P.g = h->grads + beg;
-    P.rsP = rsP; P.rsM = rsG; P.n = n;
-    P.gx = h->grads_x ? h->grads_x + beg : nullptr; P.xs = (long long)R * L.trainable; P.nx = h->gslices - 1;
-    P.target_delta = which == 0 ? L.target_delta : 0;
-    P.tau2_begin = (which == 0 && c.care) ? (L.cse_begin - L.critic_begin) : (long long)1 << 60;
-    P.tau2 = (float)c.tau_se; P.one_minus_tau2 = (float)(1.0 - c.tau_se);
-    P.which = which == 2 ? 4 : which;                    // counter slot: 0 critic, 1 actor, 4 context encoder
-    P.lr = which == 0 ? c.lr_critic : (which == 1 ? c.lr_actor : c.lr_ctx);
-    P.cnt = h->cnt;
-    P.tail = which == 0 ? TAIL_CRITIC_LOSS : (which == 1 ? TAIL_ALPHA_AND_LOSSES : TAIL_NONE);
-    P.lq = h->lq.p; P.la = h->la.p; P.rsY = h->y.rs;
-    P.logp_cur = h->logp.p + B; P.logstd_sum = h->logstd.p + B; P.rsLogp = h->logp.rs;
-    P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
-    P.log_alpha = h->params + L.off_alpha;
-    P.m_alpha = h->adam_m + L.off_alpha; P.v_alpha = h->adam_v + L.off_alpha; P.g_alpha = h->grads + L.off_alpha;
-    P.losses = h->losses; P.losses_host = h->loss_h_dev; P.R = R;
-    int nb = (int)((n + 256 * 4 - 1) / (256 * 4));
-    if (nb < 1) nb = 1;
-    if (nb > 592) nb = 592;
-    l.grid = dim3(nb + (P.tail != TAIL_NONE ? 1 : 0), R);
-    l.block = dim3(256);
-    l.join = true;                 // every gradient of the slice must have landed, including the forked weight gradients
-    h->plan.push_back(l);
-  };
   adam(0);
   if (c.care) {          // encoded states of s with the UPDATED critic encoder for the actor pass (learner.py:336-341)
     care_tables({2});
@@ -1029,6 +1265,7 @@ static int build_plan(b200sac* h) {
   }
   adam(1);
   if (c.care == 2) adam(2);        // update(): context_encoder_optimizer.step() (learner.py:399), gradients from the critic loss
+  }   // generic (per-layer) plan
 
   if (plan_rc) return plan_rc;
   // upload problem tables and rebase
@@ -1038,8 +1275,10 @@ static int build_plan(b200sac* h) {
     CU(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes));
     CU(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
   }
-  CU(cudaMalloc(&h->d_probs, h->h_probs.size() * sizeof(GemmProb)));
-  CU(cudaMemcpy(h->d_probs, h->h_probs.data(), h->h_probs.size() * sizeof(GemmProb), cudaMemcpyHostToDevice));
+  if (!h->h_probs.empty()) {
+    CU(cudaMalloc(&h->d_probs, h->h_probs.size() * sizeof(GemmProb)));
+    CU(cudaMemcpy(h->d_probs, h->h_probs.data(), h->h_probs.size() * sizeof(GemmProb), cudaMemcpyHostToDevice));
+  }
   for (auto& l : h->plan) {
     if (l.kind == L_GEMM_BIG || l.kind == L_GEMM_SMALL || l.kind == L_GEMM_THIN || l.kind == L_GEMM_TC) l.probs = h->d_probs + (size_t)(uintptr_t)l.probs;
     if (l.kind == L_GEMM_TC) l.tprobs = h->d_tprobs + (size_t)(uintptr_t)l.tprobs;
@@ -1055,7 +1294,6 @@ static int build_plan(b200sac* h) {
 // Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor
 // drains; every kernel begins with griddepcontrol.wait (common.cuh::kstamp), so data dependencies hold.
 static bool g_use_pdl = true;
-static bool g_stamp_host_off = true;           // false while b200sac_graph_timeline runs (one unforked step per graph)
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg;
@@ -1133,6 +1371,16 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
       case L_ADAM:
         launch_k(adam_kernel, l.grid, l.block, 0, s, h->K, l.ad);
         break;
+      case L_CHAIN: {
+        ChainArgs a = l.chain;
+        a.pol.use_eps_buf = use_eps_buf ? 1 : 0;
+        if (a.job[0].kind == CJ_FWD) launch_k(chain_kernel<true>, l.grid, l.block, l.smem, s, a, h->K);
+        else launch_k(chain_kernel<false>, l.grid, l.block, l.smem, s, a, h->K);
+        break;
+      }
+      case L_WGRAD:
+        launch_k(wgrad_kernel, l.grid, l.block, l.smem, s, l.wg);
+        break;
     }
     if (forked) {
       CU(cudaEventRecord(h->ev_fork_done, h->fork));
@@ -1165,8 +1413,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   h->device = device;
   h->R = cfg->replicas;
   // programmatic dependent launch with the exit-time trigger only (see common.cuh::KStamp); B200SAC_PDL=0 turns it off
-  g_use_pdl = true;
-  if (const char* e = getenv("B200SAC_PDL")) g_use_pdl = (e[0] != '0');
+  if (const char* e = getenv("B200SAC_PDL")) g_use_pdl = (e[0] != '0');      // process-wide switch, read at every create
 
   build_layout(cfg, h->L);
   const Layout& L = h->L;
@@ -1246,6 +1493,8 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   h->q = carve(cur, (size_t)2 * h->y.rs, R);
   h->dq = carve(cur, (size_t)2 * h->y.rs, R);
   h->dqa = carve(cur, (size_t)2 * h->y.rs, R);
+  h->qt = carve(cur, (size_t)2 * h->y.rs, R);
+  h->qp = carve(cur, (size_t)2 * h->y.rs, R);
   h->dxP = carve(cur, (size_t)2 * B * ldx, R);
   h->dout_dbg = carve(cur, (size_t)B * 2 * A, R);
   h->dact_dbg = carve(cur, (size_t)B * 2 * A, R);
@@ -1293,7 +1542,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   CUH(cudaMalloc(&h->slab, cur * sizeof(float)));
   CUH(cudaMemset(h->slab, 0, cur * sizeof(float)));
   for (Buf* b : {&h->XA, &h->XQ, &h->XT, &h->XP, &h->r, &h->d, &h->tid, &h->eps, &h->pout, &h->psave, &h->act_out, &h->logp,
-                 &h->logstd, &h->y, &h->lq, &h->la, &h->qmin, &h->q, &h->dq, &h->dqa, &h->dxP, &h->dout_dbg, &h->dact_dbg})
+                 &h->logstd, &h->y, &h->lq, &h->la, &h->qmin, &h->q, &h->dq, &h->dqa, &h->dxP, &h->dout_dbg, &h->dact_dbg, &h->qt, &h->qp})
     rebase(*b, h->slab);
   for (auto* v : {&h->hA, &h->dhA, &h->hQ, &h->hT, &h->hP, &h->dhQ})
     for (auto& b : *v) rebase(b, h->slab);
@@ -1304,7 +1553,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
     for (auto* v : {&h->mixH[0], &h->mixH[1], &h->mixH[2], &h->mixDH})
       for (auto& b : *v) rebase(b, h->slab);
   }
-  if (h->q.rs != 2 * h->y.rs || h->dq.rs != 2 * h->y.rs || h->dqa.rs != 2 * h->y.rs) {
+  if (h->q.rs != 2 * h->y.rs || h->dq.rs != 2 * h->y.rs || h->dqa.rs != 2 * h->y.rs || h->qt.rs != 2 * h->y.rs || h->qp.rs != 2 * h->y.rs) {
     destroy_impl(h);
     return fail(B200SAC_ERR_INVALID, "internal: q stride");
   }
@@ -1366,6 +1615,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   CUH(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
 
+  h->fused = fused_eligible(*cfg);
   if (int rc = build_plan(h)) {
     destroy_impl(h);
     return rc;
@@ -1413,6 +1663,20 @@ extern "C" int b200sac_export(b200sac_t* h, int32_t which, int32_t replica, floa
       for (int64_t i = 0; i < n; ++i) buf[i] += tmp[(size_t)i];
     }
   }
+  return 0;
+}
+
+// A few floats of one arena (e.g. log_alpha for the logger) without exporting the whole arena.
+extern "C" int b200sac_read_range(b200sac_t* h, int32_t which, int32_t replica, int64_t offset, int64_t n_floats, float* out_host,
+                                  void* stream) {
+  if (!h || !out_host) return fail(B200SAC_ERR_INVALID, "null argument");
+  float* p; int64_t n;
+  if (int rc = arena_of(h, which, &p, &n)) return rc;
+  if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica %d out of range", replica);
+  if (offset < 0 || n_floats < 1 || offset + n_floats > n) return fail(B200SAC_ERR_INVALID, "range [%lld, +%lld) outside the arena", (long long)offset, (long long)n_floats);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(out_host, p + (size_t)replica * n + offset, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
 
@@ -1595,16 +1859,18 @@ static int enqueue_body(b200sac* h, cudaStream_t st, int variant, const void* co
     }
   }
   CU(cudaGetLastError());
-  return run_plan(h, st, use_eps, evs ? evs + 1 : nullptr, evs == nullptr && g_stamp_host_off);
+  return run_plan(h, st, use_eps, evs ? evs + 1 : nullptr, evs == nullptr && !h->stamping);
 }
 
 // nsteps > 1 (device-ring sampling only): that many consecutive gradient steps captured in ONE graph, so a pipelined
-// run pays the graph-launch gap (~3-4 us between two graph launches on B200) once per kGraphSteps steps.
+// run pays the graph-launch gap (~3-4 us between two graph launches on B200) once per graph.  A run of n steps is cut
+// greedily into graphs of 8, 4, 2 and 1 steps.
 constexpr int kGraphSteps = 8;
-static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* const* p, int np, b200sac_replay* rb, int nsteps = 1) {
+static int get_graph(b200sac* h, cudaStream_t st, int variant, const void* const* p, int np, b200sac_replay* rb, int nsteps,
+                     cudaGraphExec_t* out) {
   GraphKey key;
   memset(&key, 0, sizeof(key));
-  key.variant = variant + 4 * (g_stamp_host_off ? 0 : 1) + 16 * (nsteps - 1);      // the timeline run captures unforked graphs
+  key.variant = variant + 4 * (h->stamping ? 1 : 0) + 16 * (nsteps - 1);      // the timeline run captures unforked graphs
   for (int i = 0; i < np && i < 9; ++i) key.p[i] = p[i];
   if (rb) key.p[8] = rb;
   auto it = h->graphs.find(key);
@@ -1625,10 +1891,41 @@ static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* con
     e = cudaGraphInstantiate(&ge, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail(B200SAC_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    if (cudaGraphUpload(ge, st) != cudaSuccess) cudaGetLastError();    // best effort: first launch does not pay the upload
     it = h->graphs.emplace(key, ge).first;
   }
-  CU(cudaGraphLaunch(it->second, st));
+  *out = it->second;
+  return 0;
+}
+
+static int launch_step(b200sac* h, cudaStream_t st, int variant, const void* const* p, int np, b200sac_replay* rb, int nsteps = 1) {
+  cudaGraphExec_t ge = nullptr;
+  if (int rc = get_graph(h, st, variant, p, np, rb, nsteps, &ge)) return rc;
+  CU(cudaGraphLaunch(ge, st));
   h->host_steps += nsteps;
+  return 0;
+}
+
+// Capture + instantiate every graph the sampled path can launch (device ring: the 8/4/2/1-step graphs; host ring: the
+// staged one-step graphs of both staging slots) without running a step, so that no later call pays graph construction.
+extern "C" int b200sac_prepare(b200sac_t* h, b200sac_replay_t* rb, void* stream) {
+  if (!h || !rb || rb->h != h) return fail(B200SAC_ERR_INVALID, "bad handle");
+  CU(cudaSetDevice(h->device));
+  StreamBridge sb(h, stream);
+  if (int rc = sb.begin()) return rc;
+  cudaGraphExec_t ge = nullptr;
+  if (rb->where == 0) {
+    const void* p[1] = {rb->rows};
+    for (int n = kGraphSteps; n >= 1; n >>= 1)
+      if (int rc = get_graph(h, sb.run, 2, p, 1, rb, n, &ge)) return rc;
+  } else {
+    for (int slot = 0; slot < 2; ++slot) {
+      const void* p[2] = {h->stage_d[slot], nullptr};
+      if (int rc = get_graph(h, sb.run, 1, p, 2, nullptr, 1, &ge)) return rc;
+    }
+  }
+  if (int rc = sb.end()) return rc;
+  CU(cudaStreamSynchronize(sb.run));
   return 0;
 }
 
@@ -1637,9 +1934,26 @@ extern "C" int b200sac_step(b200sac_t* h, const float* s, const float* a, const 
   if (!h || !s || !a || !r || !s2 || !d) return fail(B200SAC_ERR_INVALID, "null minibatch pointer");
   if ((eps_next == nullptr) != (eps_cur == nullptr)) return fail(B200SAC_ERR_INVALID, "eps_next and eps_cur must both be given or both NULL");
   CU(cudaSetDevice(h->device));
-  const void* p[7] = {s, a, r, s2, d, eps_next, eps_cur};
+  // The caller's arrays are copied (device to device, in stream order) into handle-owned buffers, so the captured graph
+  // sees the same pointers whatever tensors the caller passes: one graph per (with / without injected noise), never a
+  // re-capture per call.
+  const size_t RB = (size_t)h->R * h->cfg.batch, obs = (size_t)h->K.obs, A = (size_t)h->K.act;
+  const size_t n_s = RB * obs, n_a = RB * A, n_1 = RB;
+  if (!h->split_d) CU(cudaMalloc(&h->split_d, (2 * n_s + 3 * n_a + 2 * n_1) * sizeof(float)));
+  float* ds = h->split_d; float* da = ds + n_s; float* dr = da + n_a; float* ds2 = dr + n_1; float* dd = ds2 + n_s;
+  float* de1 = dd + n_1; float* de2 = de1 + n_a;
   StreamBridge sb(h, stream);
   if (int rc = sb.begin()) return rc;
+  CU(cudaMemcpyAsync(ds, s, n_s * sizeof(float), cudaMemcpyDefault, sb.run));
+  CU(cudaMemcpyAsync(da, a, n_a * sizeof(float), cudaMemcpyDefault, sb.run));
+  CU(cudaMemcpyAsync(dr, r, n_1 * sizeof(float), cudaMemcpyDefault, sb.run));
+  CU(cudaMemcpyAsync(ds2, s2, n_s * sizeof(float), cudaMemcpyDefault, sb.run));
+  CU(cudaMemcpyAsync(dd, d, n_1 * sizeof(float), cudaMemcpyDefault, sb.run));
+  if (eps_next) {
+    CU(cudaMemcpyAsync(de1, eps_next, n_a * sizeof(float), cudaMemcpyDefault, sb.run));
+    CU(cudaMemcpyAsync(de2, eps_cur, n_a * sizeof(float), cudaMemcpyDefault, sb.run));
+  }
+  const void* p[7] = {ds, da, dr, ds2, dd, eps_next ? de1 : nullptr, eps_next ? de2 : nullptr};
   if (int rc = launch_step(h, sb.run, 0, p, 7, nullptr)) return rc;
   return sb.end();
 }
@@ -1755,6 +2069,8 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
     case L_CHEADS: return "critic_heads";
     case L_AQHEADS: return "actor_q_heads";
     case L_HEADBWD: return (l.hb.policy_mode || l.hb.NO > 1) ? "head_bwd(policy)" : "head_bwd(q)";
+    case L_CHAIN:
+    case L_WGRAD: return l.label ? l.label : "chain";
     case L_ADAM: return l.ad.which == 0 ? "adam_critic+polyak" : (l.ad.which == 1 ? "adam_actor+alpha" : "adam_context_encoder");
   }
   return "?";
@@ -1913,9 +2229,9 @@ extern "C" int b200sac_graph_timeline(b200sac_t* h, b200sac_replay_t* rb, int32_
   if (int rc = b200sac_step_sampled(h, rb, 5, stream)) return rc;     // warm (graph instantiated)
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpyToSymbol(g_stamp, &sb_on, sizeof(StampBuf)));
-  g_stamp_host_off = false;
+  h->stamping = true;
   int rc = b200sac_step_sampled(h, rb, iters + 1, stream);
-  g_stamp_host_off = true;
+  h->stamping = false;
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpyToSymbol(g_stamp, &sb_off, sizeof(StampBuf)));
   if (rc) return rc;
@@ -1980,7 +2296,7 @@ extern "C" int b200sac_act(b200sac_t* h, int32_t replica, int32_t n, const float
     p.M = n; p.N = lo.out; p.K = lo.in; p.mode = GEMM_FWD; p.relu = 1;
     gemm_simt_kernel<<<dim3((p.N + GS_T - 1) / GS_T, (p.M + GS_T - 1) / GS_T, 1), GS_THREADS, 0, st>>>(grp);
   }
-  PolicyHeadArgs P = h->plan[(size_t)h->use_eps_buf_idx].pol;
+  PolicyHeadArgs P = h->pol;
   P.h += replica * P.rsH; P.W += replica * P.rsP; P.b += replica * P.rsP; P.eps += replica * P.rsEps;
   P.pout += replica * P.rsPout; P.psave += replica * P.rsSave; P.XT += replica * P.rsX; P.XP += replica * P.rsX;
   P.act_out += replica * P.rsAct; P.logp += replica * P.rsLogp; P.logstd_sum += replica * P.rsLogp; P.cnt += replica;
@@ -2040,7 +2356,28 @@ extern "C" int b200sac_debug_read(b200sac_t* h, const char* name, int32_t replic
   else if (nm == "qmin") { src = h->qmin.p + replica * h->qmin.rs; n = B; }
   else if (nm == "d_action") { src = h->dact_dbg.p + replica * h->dact_dbg.rs; n = (int64_t)B * A; }
   else if (nm == "d_head") { src = h->dout_dbg.p + replica * h->dout_dbg.rs; n = (int64_t)B * 2 * A; }
-  else return fail(B200SAC_ERR_INVALID, "unknown debug tensor '%s'", name);
+  else {
+    // hidden activations (the ReLU masks of the step): "hA.<l>" [2B][H] rows [s';s]; "hQ.<l>" / "hT.<l>" / "hP.<l>" [2][B][H]
+    // (critic update pass / target pass -- not kept by the layer-chained plan -- / actor pass); CARE mixture encoders
+    // "mixH.<inst>.<l>" [K][rows][pitch4(H)], inst 0 = critic's on [s';s] (rows 2B), 1 = target's on s', 2 = updated critic's on s
+    int l = -1, inst = -1;
+    char kind[8] = "";
+    const Buf* b = nullptr;
+    if (sscanf(name, "mixH.%d.%d", &inst, &l) == 2) {
+      if (!h->cfg.care || inst < 0 || inst > 2 || l < 0 || l >= (int)h->mixH[inst].size()) return fail(B200SAC_ERR_INVALID, "no such tensor '%s'", name);
+      b = &h->mixH[inst][l];
+      const int rows = inst == 0 ? 2 * B : B, pw = (h->cfg.mix_hidden[l] + 3) & ~3;
+      n = (int64_t)h->cfg.num_encoders * rows * pw;
+    } else if (sscanf(name, "h%1[AQTP].%d", kind, &l) == 2) {
+      const std::vector<Buf>& v = kind[0] == 'A' ? h->hA : (kind[0] == 'Q' ? h->hQ : (kind[0] == 'T' ? h->hT : h->hP));
+      if (l < 0 || l >= (int)v.size()) return fail(B200SAC_ERR_INVALID, "no such tensor '%s'", name);
+      b = &v[l];
+      n = (int64_t)2 * B * (kind[0] == 'A' ? h->cfg.actor_hidden[l] : h->cfg.critic_hidden[l]);
+    } else {
+      return fail(B200SAC_ERR_INVALID, "unknown debug tensor '%s'", name);
+    }
+    src = b->p + replica * b->rs;
+  }
   if (n_floats) *n_floats = n;
   if (cap_floats < n) return fail(B200SAC_ERR_INVALID, "buffer too small: need %lld floats", (long long)n);
   CU(cudaMemcpyAsync(out_host, src, n * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -2076,7 +2413,8 @@ extern "C" int b200sac_replay_create(b200sac_t* h, int64_t capacity, int32_t whe
   if (where == 0) {
     if (cudaMalloc(&rb->d_fill, sizeof(long long) * h->R * Teff) != cudaSuccess ||
         cudaMalloc(&rb->d_idx, sizeof(int) * h->R * h->cfg.batch) != cudaSuccess ||
-        cudaMemset(rb->d_fill, 0, sizeof(long long) * h->R * Teff) != cudaSuccess) {
+        cudaMemset(rb->d_fill, 0, sizeof(long long) * h->R * Teff) != cudaSuccess ||
+        cudaEventCreateWithFlags(&rb->ev_gather, cudaEventDisableTiming) != cudaSuccess) {
       cudaFree(rb->rows); cudaFree(rb->d_fill); cudaFree(rb->d_idx);
       delete rb;
       return fail(B200SAC_ERR_NOMEM, "replay index allocation failed");
@@ -2097,6 +2435,7 @@ extern "C" int b200sac_replay_destroy(b200sac_replay_t* rb) {
   }
   if (rb->where == 0) cudaFree(rb->rows); else cudaFreeHost(rb->rows);
   cudaFree(rb->d_fill); cudaFree(rb->d_idx);
+  if (rb->ev_gather) cudaEventDestroy(rb->ev_gather);
   delete rb;
   return 0;
 }
@@ -2126,6 +2465,9 @@ extern "C" int b200sac_replay_push(b200sac_replay_t* rb, int32_t replica, int64_
     bucket[(size_t)task].insert(bucket[(size_t)task].end(), row.begin(), row.end());
   }
   std::lock_guard<std::mutex> lk(rb->mu);
+  // Device ring: the gathers of every step enqueued so far must have read their rows before a wrapped ring overwrites
+  // them (a torn transition otherwise); step_sampled enqueues under the same mutex, so none can slip in while we copy.
+  if (rb->where == 0 && rb->gather_pending) { CU(cudaEventSynchronize(rb->ev_gather)); rb->gather_pending = false; }
   for (int task = 0; task < rb->Teff; ++task) {
     const float* src = bucket[(size_t)task].data();
     long long cnt = (long long)(bucket[(size_t)task].size() / (size_t)rs);
@@ -2249,13 +2591,17 @@ extern "C" int b200sac_step_sampled(b200sac_t* h, b200sac_replay_t* rb, int32_t 
         return fail(B200SAC_ERR_STATE, "replay not ready: a ring holds %lld transitions, need >= %d (4 x per-task batch)", f, 4 * per);
   }
   if (rb->where == 0) {
+    std::lock_guard<std::mutex> lk(rb->mu);           // ordered against b200sac_replay_push (see there)
     const void* p[1] = {rb->rows};
     int i = 0;
-    if (g_stamp_host_off)                       // (the in-graph timeline wants one step per graph)
-      for (; i + kGraphSteps <= n_steps; i += kGraphSteps)
-        if (int rc = launch_step(h, st, 2, p, 1, rb, kGraphSteps)) return rc;
+    if (!h->stamping)                           // (the in-graph timeline wants one step per graph)
+      for (int n = kGraphSteps; n > 1; n >>= 1)
+        for (; i + n <= n_steps; i += n)
+          if (int rc = launch_step(h, st, 2, p, 1, rb, n)) return rc;
     for (; i < n_steps; ++i)
       if (int rc = launch_step(h, st, 2, p, 1, rb)) return rc;
+    CU(cudaEventRecord(rb->ev_gather, st));
+    rb->gather_pending = true;
     return sb.end();
   }
   // pinned-host ring: draw + gather on the host into the pinned slot, H2D on the side stream.  The NEXT

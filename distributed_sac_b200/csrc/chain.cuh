@@ -1,0 +1,585 @@
+// Layer-chained MLP kernels for the "LunarLander-class" SAC step (every hidden width <= 256, exact-fp32 mode).
+//
+// The per-layer launches of the generic plan cost one kernel boundary + one cold operand round trip per layer; at
+// 256-wide layers the math of a layer is < 1 us of a B200 while its launch took 3.5-10 us (profiles/README.md, round 1).
+// Here a CTA owns CH_ROWS = 8 rows of ONE network and walks the whole chain of that network with the activations in
+// shared memory:
+//
+//   forward   X -> relu(W0 x + b0) -> relu(W1 . + b1) ... -> head         LunarLander_Distributed_SAC/src/model.py:38-48,117-127
+//             head = scalar Q head, or the tanh-Gaussian policy head (rsample, squash, log-prob: model.py:50-65)
+//   backward  d(head out) -> dY_last = (dout Wh) * [h_last > 0] -> (dY W_l) * [h_{l-1} > 0] ... -> dh_0 (-> d(action))
+//             autograd of the same modules; d(head out) is produced in the kernel from per-row scalars:
+//             critic update   dQ = 2c (Q - y), y = rs r + gamma (1-d)(min(Qt1,Qt2) - alpha logpi')   learner.py:210, model.py:139-140
+//             actor pass      min(Q1,Q2) gradient routing                                            learner.py:222-223
+//             policy          closed-form backward of rsample/tanh/log-prob (oracle/sac_manual.py)   model.py:50-60
+//
+// Rows are independent, so nothing is exchanged between CTAs and there is no barrier wider than the CTA.  Every CTA
+// streams the full weight matrices of its network through a 3-stage cp.async pipeline of [<=256 n][32 k] chunks (36 KB),
+// which runs ahead across layer boundaries (weights do not depend on activations); 128 CTAs x 256 KB per 256x256 layer
+// = 32 MB of L2 reads, ~2.7 us at the measured L2 rate -- the bound of this design; the 8 x 256 x 256 FMAs of a CTA fit
+// under it.  Inside a chunk the 8 warps split K (warp w takes k = 4w..4w+3 of the 32), each lane holds an 8-row x
+// 8-column accumulator tile (40 shared-memory wavefronts per 256 FFMA), and the eight partial tiles are added in warp
+// order in shared memory: a fixed summation order, bit-reproducible run to run and replica to replica.
+//
+// Weight gradients (the reduction over the batch) are a separate kernel, wgrad_kernel below: 32x32 output tiles, the
+// 8 warps split the batch rows, lanes hold 4x8 accumulators, fixed-order reduction.
+#pragma once
+#include "sac_kernels.cuh"
+
+namespace bsac {
+
+constexpr int CH_ROWS = 8;                 // rows per CTA
+constexpr int CH_MAXW = 256;               // widest layer / widest reduction
+constexpr int CH_KC = 32;                  // k rows per weight chunk
+constexpr int CH_NSTAGE = 3;               // weight chunks in flight
+constexpr int CH_MAXL = 8;                 // dense stages per job
+constexpr int CH_THREADS = 256;
+constexpr int CH_WARPS = CH_THREADS / 32;
+constexpr int CH_INP = CH_MAXW + 4;        // row pitch of the activation buffers
+constexpr int CH_WPF = CH_KC + 4;          // row pitch of a forward chunk [n][36]
+constexpr int CH_CHUNK_FLOATS = CH_MAXW * CH_WPF;                    // 9216 (>= 32 * 256 of a backward chunk)
+constexpr int CH_MAXJOBS = 3;
+// shared memory (floats): two activation buffers, head weights [16][260], d(head out) [8][16], action columns of W0
+// [256][8], partial tiles [8 warps][8 rows][256], weight stages
+constexpr int CH_SM_ACT = CH_ROWS * CH_INP;
+constexpr int CH_SM_HEADW = kMaxHeadOut * CH_INP;
+constexpr int CH_SM_SD = CH_ROWS * kMaxHeadOut;
+constexpr int CH_SM_W0A = CH_MAXW * kMaxAct;
+constexpr int CH_SM_PART = CH_WARPS * CH_ROWS * CH_MAXW;
+constexpr int CH_SMEM_FLOATS = 2 * CH_SM_ACT + CH_SM_HEADW + CH_SM_SD + CH_SM_W0A + CH_SM_PART + CH_NSTAGE * CH_CHUNK_FLOATS;
+constexpr size_t CH_SMEM_BYTES = (size_t)CH_SMEM_FLOATS * sizeof(float);
+
+enum { CJ_FWD = 0, CJ_BWD_CRITIC = 1, CJ_BWD_ACTORQ = 2, CJ_BWD_POLICY = 3 };
+enum { CH_HEAD_NONE = 0, CH_HEAD_SCALAR = 1, CH_HEAD_POLICY = 2, CH_TAIL_DACTION = 3 };
+
+struct ChainStage {
+  const float* W;          // parameter arena (replica stride rsP). forward: W[n][k] (nn.Linear layout); backward: the same
+                           // matrix read as W[k][n] (k = the layer's outputs, n = its inputs)
+  const float* bias;       // forward only (arena)
+  const float* mask;       // backward only: the forward activation [rows][N] whose > 0 gates the result (row 0 of the job)
+  float* out;              // optional global store of the stage output (row 0 of the job)
+  long long rsMask, rsOut;
+  int ldw, ldmask, ldo;
+  int K, N;                // reduction width, output width
+};
+
+struct ChainJob {
+  int kind, rows, nstages, head;
+  int net;                                             // twin index (0/1) into the [2][B] per-row buffers
+  const float* X; long long rsX; int ldx, K0;          // FWD: input rows [rows][ldx], K0 valid columns
+  const float* hlast; long long rsHlast; int ldh;      // BWD: last hidden activation [rows][Hh] (gate of the generated dY)
+  float* dylast; long long rsDy; int lddy;             // BWD: optional store of the generated dY (needed by the weight gradient)
+  const float* Wh; const float* bh; int NO, Hh;        // head weights [NO][Hh], bias (arena)
+  float* qout; long long rsQ;                          // scalar head: output (row 0 of this net)
+  const float* W0; int ldw0, col0, nact, H0;           // DACTION tail: first-layer weights [H0][ldw0], action columns col0..col0+nact
+  float* dx; long long rsDx; int lddx;                 // DACTION tail: out[rows][lddx] (+col0)
+  ChainStage st[CH_MAXL];
+};
+
+// per-row scalars the backward jobs turn into d(head output)
+struct ChainRows {
+  const float* r; const float* d; const int* tid; long long rsR;
+  const float* logp; long long rsLogp;                 // [0,B) next-state half, [B,2B) current-state half
+  const float* log_alpha;                              // arena
+  const float* qt; const float* q; const float* qp;    // [2][B] target / local (s,a) / local (s,a~) head outputs, replica stride 2*rsY
+  float* y; float* dq; float* lq; float* dqa; float* la; float* qmin; long long rsY;   // dq, dqa: [2][B], replica stride 2*rsY
+  const float* dxP; long long rsDxNet, rsDxRep; int lddx;   // critic input gradients [2][B][ldx] (policy job)
+  const float* psave; long long rsSave;                // rows B.. (current-state half), pre-offset by the host
+  float* dout_dbg; float* dact_dbg; long long rsDbg;   // d(mu|log_std) [B][2A] (also the head weight-gradient operand), d(action) [B][A]
+};
+
+struct ChainArgs {
+  int njobs;
+  long long rsP;
+  ChainJob job[CH_MAXJOBS];
+  PolicyHeadArgs pol;
+  ChainRows rw;
+};
+
+B200_D void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+B200_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> B200_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One weight chunk into a stage buffer.  forward: [N n][kc k] gathered from W[n][k0..k0+kc) into rows of pitch 36;
+// backward: rows k0..k0+kc of W[k][N] (contiguous N floats each) into rows of pitch N.
+B200_D void chain_issue_chunk(float* __restrict__ buf, const float* __restrict__ W, int ldw, int N, int k0, int kc, bool bwd, int tid) {
+  // pieces of 16 B; the common shapes (32-k forward chunks, 256-wide backward rows) index without a division
+  if (!bwd) {
+    const int q4 = kc >> 2, total = N * q4;
+    if (q4 == 8) {
+      const int q = tid & 7;
+      for (int n = tid >> 3; n < N; n += CH_THREADS / 8) cp_async16(buf + n * CH_WPF + 4 * q, W + (long long)n * ldw + k0 + 4 * q);
+    } else {
+      for (int e = tid; e < total; e += CH_THREADS) {
+        const int n = e / q4, q = e - n * q4;
+        cp_async16(buf + n * CH_WPF + 4 * q, W + (long long)n * ldw + k0 + 4 * q);
+      }
+    }
+  } else {
+    const int q4 = N >> 2, total = kc * q4;
+    if (q4 == 64) {
+      const int q = tid & 63;
+      for (int kk = tid >> 6; kk < kc; kk += CH_THREADS / 64) cp_async16(buf + kk * N + 4 * q, W + (long long)(k0 + kk) * ldw + 4 * q);
+    } else {
+      for (int e = tid; e < total; e += CH_THREADS) {
+        const int kk = e / q4, q = e - kk * q4;
+        cp_async16(buf + kk * N + 4 * q, W + (long long)(k0 + kk) * ldw + 4 * q);
+      }
+    }
+  }
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainArgs A, StepConst K) {
+  KStamp ks_;
+  extern __shared__ __align__(16) float sm[];
+  const ChainJob& J = A.job[blockIdx.y];
+  const int rep = blockIdx.z;
+  const int row0 = blockIdx.x * CH_ROWS;
+  if (row0 >= J.rows) return;
+  const int nrows = (J.rows - row0 < CH_ROWS) ? J.rows - row0 : CH_ROWS;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const long long po = (long long)rep * A.rsP;
+
+  float* actA = sm;
+  float* actB = actA + CH_SM_ACT;
+  float* headW = actB + CH_SM_ACT;
+  float* sd = headW + CH_SM_HEADW;
+  float* w0a = sd + CH_SM_SD;
+  float* part = w0a + CH_SM_W0A;
+  float* wst = part + CH_SM_PART;
+
+  constexpr bool fwd = FWD;               // (the host launches the <true> instance for CJ_FWD jobs, <false> for the backward kinds)
+  float* In = actA;
+  float* Out = actB;
+
+  // ---- prologue: head weights and (forward) the input rows go out as the first cp.async group --------------------------
+  if (J.NO > 0) {
+    const float* __restrict__ Wh = J.Wh + po;
+    const int q4 = J.Hh >> 2;
+    for (int e = tid; e < J.NO * q4; e += CH_THREADS) {
+      const int j = e / q4, q = e - j * q4;
+      cp_async16(headW + j * CH_INP + 4 * q, Wh + (long long)j * J.Hh + 4 * q);
+    }
+  }
+  if constexpr (FWD) {
+    const float* __restrict__ X = J.X + (long long)rep * J.rsX + (long long)row0 * J.ldx;
+    const int k4 = (J.K0 + 3) >> 2;
+    for (int e = tid; e < CH_ROWS * k4; e += CH_THREADS) {
+      const int m = e / k4, q = e - m * k4;
+      if (m < nrows) cp_async16(In + m * CH_INP + 4 * q, X + (long long)m * J.ldx + 4 * q);
+      else *reinterpret_cast<float4*>(In + m * CH_INP + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  cp_async_commit();
+
+  // ---- weight pipeline -------------------------------------------------------------------------------------------------
+  int is = 0, ic = 0, issued = 0;        // next chunk to issue: stage, chunk within the stage, running count
+  auto issue_next = [&]() {
+    if (is < J.nstages) {
+      const ChainStage& S = J.st[is];
+      const int K4 = (S.K + 3) & ~3;
+      const int k0 = ic * CH_KC;
+      const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
+      chain_issue_chunk(wst + (issued % CH_NSTAGE) * CH_CHUNK_FLOATS, S.W + po, S.ldw, S.N, k0, kc, !fwd, tid);
+      ++issued;
+      if (k0 + CH_KC >= K4) { ic = 0; ++is; } else { ++ic; }
+    }
+    cp_async_commit();
+  };
+  issue_next();
+  issue_next();
+
+  // ---- backward jobs: d(head output) of the CTA's rows, then dY_last = (dout Wh) * [h_last > 0] -------------------------
+  if constexpr (!FWD) {
+    const ChainRows& R = A.rw;
+    const int B = K.B, Aa = K.act;
+    const int row = row0 + w;                      // warp w owns row w
+    // gate activations of this thread's column (issued before anything is waited for)
+    float hv[CH_ROWS];
+    {
+      const float* __restrict__ hl = J.hlast + (long long)rep * J.rsHlast + (long long)row0 * J.ldh;
+#pragma unroll
+      for (int m = 0; m < CH_ROWS; ++m) hv[m] = (tid < J.Hh && m < nrows) ? hl[(long long)m * J.ldh + tid] : 0.f;
+    }
+    if (J.kind == CJ_BWD_ACTORQ && J.nact > 0) {   // action columns of the first-layer weights for the tail
+      const float* __restrict__ W0 = J.W0 + po;
+      const int H0 = J.H0;
+      for (int e = tid; e < H0 * J.nact; e += CH_THREADS) {
+        const int k = e / J.nact, j = e - k * J.nact;
+        w0a[k * kMaxAct + j] = __ldg(W0 + (long long)k * J.ldw0 + J.col0 + j);
+      }
+    }
+    if (w < nrows) {
+      if (J.kind == CJ_BWD_CRITIC) {
+        if (lane == 0) {
+          const int t = (R.tid + rep * R.rsR)[row];
+          const float r = (R.r + rep * R.rsR)[row], d = (R.d + rep * R.rsR)[row];
+          const float lp = (R.logp + rep * R.rsLogp)[row];
+          const float* QT = R.qt + rep * 2 * R.rsY;
+          const float* Q = R.q + rep * 2 * R.rsY;
+          const float qt1 = QT[row], qt2 = QT[B + row], q1 = Q[row], q2 = Q[B + row];
+          const float alpha = (float)exp((double)(R.log_alpha + po)[t]);
+          const float t1 = K.reward_scale * r;
+          const float t2 = K.gamma * (1.f - d);
+          const float t3 = fminf(qt1, qt2) - alpha * lp;
+          const float y = t1 + t2 * t3;
+          const float qn = J.net == 0 ? q1 : q2;
+          const float dqv = 2.f * K.c_loss * (qn - y);
+          sd[w * kMaxHeadOut] = dqv;
+          (R.dq + rep * 2 * R.rsY)[J.net * B + row] = dqv;
+          if (J.net == 0) {
+            const float e1 = y - q1, e2 = y - q2;
+            (R.y + rep * R.rsY)[row] = y;
+            (R.lq + rep * R.rsY)[row] = e1 * e1 + e2 * e2;
+          }
+        }
+      } else if (J.kind == CJ_BWD_ACTORQ) {
+        if (lane == 0) {
+          const int t = (R.tid + rep * R.rsR)[row];
+          const float lp = (R.logp + rep * R.rsLogp)[B + row];
+          const float* QP = R.qp + rep * 2 * R.rsY;
+          const float q1 = QP[row], q2 = QP[B + row];
+          float g1, g2;
+          if (q1 == q2) { g1 = g2 = -0.5f * K.c_loss; }
+          else if (q1 < q2) { g1 = -K.c_loss; g2 = 0.f; }
+          else { g1 = 0.f; g2 = -K.c_loss; }
+          const float g = J.net == 0 ? g1 : g2;
+          sd[w * kMaxHeadOut] = g;
+          (R.dqa + rep * 2 * R.rsY)[J.net * B + row] = g;
+          if (J.net == 0) {
+            const float alpha = (float)exp((double)(R.log_alpha + po)[t]);
+            const float qm = fminf(q1, q2);
+            (R.la + rep * R.rsY)[row] = -(qm - alpha * lp);
+            (R.qmin + rep * R.rsY)[row] = qm;
+          }
+        }
+      } else {                                     // CJ_BWD_POLICY: lane j < A owns action j
+        if (lane < Aa) {
+          const float* __restrict__ sv = R.psave + rep * R.rsSave + ((long long)row * Aa + lane) * kSaveW;
+          const float* __restrict__ dx0 = R.dxP + rep * R.rsDxRep + (long long)row * R.lddx + K.in_w + lane;
+          const float da = dx0[0] + dx0[R.rsDxNet];
+          const float alpha = (float)exp((double)(R.log_alpha + po)[(R.tid + rep * R.rsR)[row]]);
+          float dmu, dls;
+          policy_dout_point(K, sv, da, alpha, dmu, dls);
+          sd[w * kMaxHeadOut + lane] = dmu;
+          sd[w * kMaxHeadOut + Aa + lane] = dls;
+          float* o = R.dout_dbg + rep * R.rsDbg + (long long)row * 2 * Aa;
+          o[lane] = dmu;
+          o[Aa + lane] = dls;
+          (R.dact_dbg + rep * R.rsDbg)[(long long)row * Aa + lane] = da;
+        }
+      }
+    }
+    cp_async_wait<2>();                            // the head weights (first group) have landed
+    __syncthreads();
+    if (tid < J.Hh) {
+      float* __restrict__ dyl = J.dylast ? J.dylast + (long long)rep * J.rsDy + (long long)row0 * J.lddy : nullptr;
+#pragma unroll
+      for (int m = 0; m < CH_ROWS; ++m) {
+        float v = 0.f;
+        if (m < nrows) {
+          for (int j = 0; j < J.NO; ++j) v = fmaf(sd[m * kMaxHeadOut + j], headW[j * CH_INP + tid], v);
+          if (!(hv[m] > 0.f)) v = 0.f;
+          if (dyl) dyl[(long long)m * J.lddy + tid] = v;
+        }
+        In[m * CH_INP + tid] = v;
+      }
+    }
+    __syncthreads();                               // In (and the staged action columns) visible to every warp
+  }
+
+  // ---- the dense stages ------------------------------------------------------------------------------------------------
+  int g = 0;
+  for (int s = 0; s < J.nstages; ++s) {
+    const ChainStage& S = J.st[s];
+    const int N = S.N, K4 = (S.K + 3) & ~3;
+    // epilogue operands of this thread's column, requested now
+    float ebias = 0.f, emask[CH_ROWS];
+    if constexpr (FWD) {
+      if (tid < N) ebias = __ldg(S.bias + po + tid);
+    } else {
+      const float* __restrict__ mk = S.mask + (long long)rep * S.rsMask + (long long)row0 * S.ldmask;
+#pragma unroll
+      for (int m = 0; m < CH_ROWS; ++m) emask[m] = (tid < N && m < nrows) ? mk[(long long)m * S.ldmask + tid] : 0.f;
+    }
+    float acc[CH_ROWS][8];
+#pragma unroll
+    for (int m = 0; m < CH_ROWS; ++m)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[m][i] = 0.f;
+
+    for (int k0 = 0; k0 < K4; k0 += CH_KC, ++g) {
+      cp_async_wait<1>();
+      __syncthreads();                  // chunk g is visible; everyone is done with chunk g-1 (its buffer is refilled next)
+      issue_next();
+      const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
+      const float* __restrict__ Wc = wst + (g % CH_NSTAGE) * CH_CHUNK_FLOATS;
+      if (4 * w < kc) {
+        // every operand of the chunk is requested before the first FMA (no branches in between: the loads of columns
+        // >= N read stale shared memory into accumulators nobody reads)
+        float4 a[CH_ROWS];
+#pragma unroll
+        for (int m = 0; m < CH_ROWS; ++m) a[m] = *reinterpret_cast<const float4*>(In + m * CH_INP + k0 + 4 * w);
+        if constexpr (FWD) {
+          float4 wv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wv[i] = *reinterpret_cast<const float4*>(Wc + (lane + 32 * i) * CH_WPF + 4 * w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int m = 0; m < CH_ROWS; ++m) {
+              float t = acc[m][i];
+              t = fmaf(a[m].x, wv[i].x, t); t = fmaf(a[m].y, wv[i].y, t); t = fmaf(a[m].z, wv[i].z, t); t = fmaf(a[m].w, wv[i].w, t);
+              acc[m][i] = t;
+            }
+          }
+        } else {
+          float4 w0[4], w1[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float* __restrict__ wr = Wc + (4 * w + q) * N;
+            w0[q] = *reinterpret_cast<const float4*>(wr + 4 * lane);
+            w1[q] = *reinterpret_cast<const float4*>(wr + 128 + 4 * lane);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int m = 0; m < CH_ROWS; ++m) {
+              const float av = q == 0 ? a[m].x : (q == 1 ? a[m].y : (q == 2 ? a[m].z : a[m].w));
+              acc[m][0] = fmaf(av, w0[q].x, acc[m][0]); acc[m][1] = fmaf(av, w0[q].y, acc[m][1]);
+              acc[m][2] = fmaf(av, w0[q].z, acc[m][2]); acc[m][3] = fmaf(av, w0[q].w, acc[m][3]);
+              acc[m][4] = fmaf(av, w1[q].x, acc[m][4]); acc[m][5] = fmaf(av, w1[q].y, acc[m][5]);
+              acc[m][6] = fmaf(av, w1[q].z, acc[m][6]); acc[m][7] = fmaf(av, w1[q].w, acc[m][7]);
+            }
+          }
+        }
+      }
+    }
+    // ---- stage epilogue: the 8 partial tiles -> fixed-order sum -> bias+ReLU | ReLU' gate -> next input -----------------
+    {
+      float* __restrict__ pw = part + w * (CH_ROWS * CH_MAXW);
+      if constexpr (FWD) {
+#pragma unroll
+        for (int m = 0; m < CH_ROWS; ++m)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pw[m * CH_MAXW + lane + 32 * i] = acc[m][i];
+      } else {
+#pragma unroll
+        for (int m = 0; m < CH_ROWS; ++m) {
+          *reinterpret_cast<float4*>(pw + m * CH_MAXW + 4 * lane) = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
+          *reinterpret_cast<float4*>(pw + m * CH_MAXW + 128 + 4 * lane) = make_float4(acc[m][4], acc[m][5], acc[m][6], acc[m][7]);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < N) {
+      float* __restrict__ go = S.out ? S.out + (long long)rep * S.rsOut + (long long)row0 * S.ldo : nullptr;
+#pragma unroll
+      for (int m = 0; m < CH_ROWS; ++m) {
+        float v = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < CH_WARPS; ++ww) v += part[(ww * CH_ROWS + m) * CH_MAXW + tid];
+        if constexpr (FWD) v = fmaxf(v + ebias, 0.f);
+        else if (!(emask[m] > 0.f)) v = 0.f;
+        Out[m * CH_INP + tid] = v;
+        if (go && m < nrows) go[(long long)m * S.ldo + tid] = v;
+      }
+    } else if (tid < ((N + 3) & ~3)) {             // pad columns of the next reduction read as zero
+#pragma unroll
+      for (int m = 0; m < CH_ROWS; ++m) Out[m * CH_INP + tid] = 0.f;
+    }
+    __syncthreads();
+    float* t = In; In = Out; Out = t;
+  }
+  cp_async_wait<0>();
+
+  // ---- head / tail: warp w owns row w ----------------------------------------------------------------------------------
+  if (w >= nrows) return;
+  const int row = row0 + w;
+  const float* __restrict__ hr = In + w * CH_INP;
+  if (FWD && J.head == CH_HEAD_SCALAR) {
+    float a = 0.f;
+    for (int k = lane; k < J.Hh; k += 32) a = fmaf(hr[k], headW[k], a);
+    a = warp_sum(a) + __ldg(J.bh + po);
+    if (lane == 0) (J.qout + (long long)rep * J.rsQ)[row] = a;
+  } else if (FWD && J.head == CH_HEAD_POLICY) {
+    const int NO = 2 * K.act, H = J.Hh;
+    float e = policy_noise(K, A.pol, rep, row, lane);
+    float acc[kMaxHeadOut];
+#pragma unroll
+    for (int j = 0; j < kMaxHeadOut; ++j) acc[j] = 0.f;
+    for (int k = lane; k < H; k += 32) {
+      const float hvv = hr[k];
+#pragma unroll
+      for (int j = 0; j < kMaxHeadOut; ++j)
+        if (j < NO) acc[j] = fmaf(hvv, headW[j * CH_INP + k], acc[j]);
+    }
+    const float* __restrict__ bias = J.bh + po;
+#pragma unroll
+    for (int j = 0; j < kMaxHeadOut; ++j)
+      if (j < NO) acc[j] = warp_sum(acc[j]) + __ldg(bias + j);
+    policy_finish(K, A.pol, rep, row, lane, acc, e);
+  } else if (!FWD && J.head == CH_TAIL_DACTION) {
+    const int H0 = J.H0;
+    float acc[kMaxAct];
+#pragma unroll
+    for (int j = 0; j < kMaxAct; ++j) acc[j] = 0.f;
+    for (int k = lane; k < H0; k += 32) {
+      const float dv = hr[k];
+#pragma unroll
+      for (int j = 0; j < kMaxAct; ++j)
+        if (j < J.nact) acc[j] = fmaf(dv, w0a[k * kMaxAct + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxAct; ++j)
+      if (j < J.nact) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+      float* o = J.dx + (long long)rep * J.rsDx + (long long)row * J.lddx + J.col0;
+#pragma unroll
+      for (int j = 0; j < kMaxAct; ++j)
+        if (j < J.nact) o[j] = acc[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Weight / bias gradients of one network group in a single launch:
+//   C[k][n] = sum_m A[m][k] * B[m][n],   C2[k] = sum_m A[m][k]
+// (autograd of nn.Linear: A = d(pre-activation) [M][out], B = the layer's input [M][in]; the scalar / policy head's
+// weight gradient is the same form with A = d(head output) [M][NO]).  One CTA = one 32 x 32 tile of one job; the
+// 8 warps split the batch rows (contiguous groups), each lane holds a 4 x 8 accumulator tile (3 shared-memory
+// wavefronts per 32 FFMA), the partial tiles are added in warp order.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int WG_T = 32;
+constexpr int WG_ROWS = 256;               // batch rows staged per pass
+constexpr int WG_MAXJOBS = 20;
+constexpr int WG_THREADS = 256;
+constexpr size_t WG_SMEM_BYTES = (size_t)(2 * WG_ROWS * WG_T + 8 * WG_T * WG_T + 8 * WG_T) * sizeof(float);
+
+struct WgradJob {
+  const float* A; const float* B;          // work-slab pointers (row 0)
+  float* C; float* C2;                     // gradient arena (replica stride rsG); C2 may be null
+  long long rsA, rsB;
+  int lda, ldb, ldc;
+  int Kout, Nin;
+  int tile0, tn;                           // first blockIdx.x of the job, tiles along Nin
+};
+struct WgradArgs {
+  int njobs, M;
+  long long rsG;
+  WgradJob job[WG_MAXJOBS];
+};
+
+B200_D void wg_stage(float* __restrict__ dst, const float* __restrict__ src, int ld, int c0, int cmax, int m0, int M, int tid) {
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  for (int e = tid; e < WG_ROWS * (WG_T / 4); e += WG_THREADS) {
+    const int mm = e >> 3, q = (e & 7) << 2;
+    const int m = m0 + mm, c = c0 + q;
+    float* d = dst + mm * WG_T + q;
+    if (m < M && vec && c + 3 < cmax) {
+      cp_async16(d, src + (long long)m * ld + c);
+    } else {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M) {
+        const float* p = src + (long long)m * ld + c;
+        if (c < cmax) x.x = __ldg(p);
+        if (c + 1 < cmax) x.y = __ldg(p + 1);
+        if (c + 2 < cmax) x.z = __ldg(p + 2);
+        if (c + 3 < cmax) x.w = __ldg(p + 3);
+      }
+      *reinterpret_cast<float4*>(d) = x;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_constant__ WgradArgs A) {
+  KStamp ks_;
+  extern __shared__ __align__(16) float sm[];
+  int ji = 0;
+  for (int j = 1; j < A.njobs; ++j)
+    if ((int)blockIdx.x >= A.job[j].tile0) ji = j;
+  const WgradJob& J = A.job[ji];
+  const int rep = blockIdx.y;
+  const int t = (int)blockIdx.x - J.tile0;
+  const int bk = t / J.tn, bn = t - bk * J.tn;
+  const int k0 = bk * WG_T, n0 = bn * WG_T;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int ky = lane >> 2, nx = lane & 3;
+
+  float* As = sm;
+  float* Bs = As + WG_ROWS * WG_T;
+  float* part = Bs + WG_ROWS * WG_T;
+  float* bpart = part + 8 * WG_T * WG_T;
+  const float* __restrict__ Ag = J.A + (long long)rep * J.rsA;
+  const float* __restrict__ Bg = J.B + (long long)rep * J.rsB;
+  const int M = A.M;
+
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float asum[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int m0 = 0; m0 < M; m0 += WG_ROWS) {
+    if (m0 > 0) __syncthreads();
+    wg_stage(As, Ag, J.lda, k0, J.Kout, m0, M, tid);
+    wg_stage(Bs, Bg, J.ldb, n0, J.Nin, m0, M, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int mcnt = (M - m0 < WG_ROWS) ? M - m0 : WG_ROWS;
+    const int per = (mcnt + 7) >> 3;
+    const int mb = w * per, me = (mb + per < mcnt) ? mb + per : mcnt;
+#pragma unroll 4
+    for (int m = mb; m < me; ++m) {
+      const float4 a = *reinterpret_cast<const float4*>(As + m * WG_T + 4 * ky);
+      const float4 b0 = *reinterpret_cast<const float4*>(Bs + m * WG_T + 8 * nx);
+      const float4 b1 = *reinterpret_cast<const float4*>(Bs + m * WG_T + 8 * nx + 4);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        asum[i] += av[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+  }
+  // partial tiles -> fixed-order sum
+  {
+    float* pw = part + w * (WG_T * WG_T);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<float4*>(pw + (4 * ky + i) * WG_T + 8 * nx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(pw + (4 * ky + i) * WG_T + 8 * nx + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    if (nx == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bpart[w * WG_T + 4 * ky + i] = asum[i];
+    }
+  }
+  __syncthreads();
+  float* __restrict__ C = J.C + (long long)rep * A.rsG;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int o = tid + WG_THREADS * u;
+    const int kk = o >> 5, nn = o & 31;
+    float v = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) v += part[ww * (WG_T * WG_T) + o];
+    if (k0 + kk < J.Kout && n0 + nn < J.Nin) C[(long long)(k0 + kk) * J.ldc + n0 + nn] = v;
+  }
+  if (bn == 0 && J.C2 != nullptr && tid < WG_T && k0 + tid < J.Kout) {
+    float v = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) v += bpart[ww * WG_T + tid];
+    (J.C2 + (long long)rep * A.rsG)[k0 + tid] = v;
+  }
+}
+
+}  // namespace bsac

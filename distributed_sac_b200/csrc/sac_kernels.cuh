@@ -271,21 +271,12 @@ B200_D PolicyPoint policy_point(float mu, float raw, float eps, float k) {
   return p;
 }
 
-__global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
-  KStamp ks_;
-  const int rep = blockIdx.y;
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int row = blockIdx.x * (blockDim.x / 32) + warp;
-  const int B = K.B, A = K.act, NO = 2 * K.act, H = K.Ha;
-  if (row >= (P.rows > 0 ? P.rows : 2 * B)) return;
-  const float* hr = P.h + rep * P.rsH + (long long)row * P.ldh;
-  const float* W = P.W + rep * P.rsP;
-  const float* bias = P.b + rep * P.rsP;
-  // the noise of this (row, action) does not depend on the head: fetch / generate it while the GEMV operands arrive
+// noise of one (row, action): from the injected buffer, or Philox keyed by (seed, replica, step, row, action)
+B200_D float policy_noise(const StepConst& K, const PolicyHeadArgs& P, int rep, int row, int lane) {
   float e = 0.f;
-  if (lane < A) {
+  if (lane < K.act) {
     if (P.use_eps_buf) {
-      e = (P.eps + rep * P.rsEps)[(long long)row * A + lane];
+      e = (P.eps + rep * P.rsEps)[(long long)row * K.act + lane];
     } else {
       Philox ph(K.seed ^ (0xA0761D6478BD642Full * (unsigned long long)(rep + 1)));
       const long long step = P.cnt[rep].v[3];
@@ -296,33 +287,14 @@ __global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
       e = z0;
     }
   }
-  float bj[kMaxHeadOut];
-#pragma unroll
-  for (int j = 0; j < kMaxHeadOut; ++j) bj[j] = j < NO ? bias[j] : 0.f;
-  float acc[kMaxHeadOut];
-#pragma unroll
-  for (int j = 0; j < kMaxHeadOut; ++j) acc[j] = 0.f;
-  for (int k0 = 0; k0 < H; k0 += 128) {       // four lane-strides of h and of every head row in flight per round trip
-    float hv[4], wv[4][kMaxHeadOut];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k = k0 + lane + 32 * u;
-      hv[u] = k < H ? hr[k] : 0.f;
-#pragma unroll
-      for (int j = 0; j < kMaxHeadOut; ++j) wv[u][j] = (j < NO && k < H) ? __ldg(W + (long long)j * H + k) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (k0 + lane + 32 * u < H) {
-#pragma unroll
-        for (int j = 0; j < kMaxHeadOut; ++j)
-          if (j < NO) acc[j] = fmaf(hv[u], wv[u][j], acc[j]);
-      }
-  }
-#pragma unroll
-  for (int j = 0; j < kMaxHeadOut; ++j)
-    if (j < NO) acc[j] = warp_sum(acc[j]) + bj[j];
-  // lane j < A owns action j
+  return e;
+}
+
+// Everything after the head GEMV of one row: acc[j] = head output j (bias included, identical in every lane);
+// lane j < A owns action j.  Shared by policy_head_kernel and the chained forward kernel (chain.cuh).
+B200_D void policy_finish(const StepConst& K, const PolicyHeadArgs& P, int rep, int row, int lane,
+                          const float (&acc)[kMaxHeadOut], float e) {
+  const int B = K.B, A = K.act, NO = 2 * K.act;
   float mu = 0.f, raw = 0.f;
 #pragma unroll
   for (int j = 0; j < kMaxAct; ++j) {
@@ -357,6 +329,47 @@ __global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
     (P.logp + rep * P.rsLogp)[row] = tot;
     (P.logstd_sum + rep * P.rsLogp)[row] = tls;
   }
+}
+
+__global__ void policy_head_kernel(StepConst K, PolicyHeadArgs P) {
+  KStamp ks_;
+  const int rep = blockIdx.y;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = blockIdx.x * (blockDim.x / 32) + warp;
+  const int B = K.B, NO = 2 * K.act, H = K.Ha;
+  if (row >= (P.rows > 0 ? P.rows : 2 * B)) return;
+  const float* hr = P.h + rep * P.rsH + (long long)row * P.ldh;
+  const float* W = P.W + rep * P.rsP;
+  const float* bias = P.b + rep * P.rsP;
+  // the noise of this (row, action) does not depend on the head: fetch / generate it while the GEMV operands arrive
+  const float e = policy_noise(K, P, rep, row, lane);
+  float bj[kMaxHeadOut];
+#pragma unroll
+  for (int j = 0; j < kMaxHeadOut; ++j) bj[j] = j < NO ? bias[j] : 0.f;
+  float acc[kMaxHeadOut];
+#pragma unroll
+  for (int j = 0; j < kMaxHeadOut; ++j) acc[j] = 0.f;
+  for (int k0 = 0; k0 < H; k0 += 128) {       // four lane-strides of h and of every head row in flight per round trip
+    float hv[4], wv[4][kMaxHeadOut];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + lane + 32 * u;
+      hv[u] = k < H ? hr[k] : 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxHeadOut; ++j) wv[u][j] = (j < NO && k < H) ? __ldg(W + (long long)j * H + k) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (k0 + lane + 32 * u < H) {
+#pragma unroll
+        for (int j = 0; j < kMaxHeadOut; ++j)
+          if (j < NO) acc[j] = fmaf(hv[u], wv[u][j], acc[j]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxHeadOut; ++j)
+    if (j < NO) acc[j] = warp_sum(acc[j]) + bj[j];
+  policy_finish(K, P, rep, row, lane, acc, e);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@ import pickle as _pickle
 import time
 from datetime import datetime
 
+import numpy as np
 import torch
 
 from . import _lib, names
@@ -78,6 +79,7 @@ class _Handle:
 class _BaseLearner:
     family = "LL"
     log_name = "LunarLander_Distributed_SAC"
+    _iteration_key = "episode_idx"
 
     # ---- construction ---------------------------------------------------------------------
     def _init_common(self, cfg_path, write_mode, save_period, checkpoint_path, server, device_index, seed,
@@ -185,6 +187,37 @@ class _BaseLearner:
         self.publish_begin()
         return self.publish_wait()
 
+    def parameters_blob(self, blocking=False):
+        """The bytes Learner.run() stores under the Redis key 'parameters' (LL/learner.py:298-299): _pickle.dumps of
+        {'actor': state_dict_on_cpu[, ...]} with the reference's key names -- what Player.pull_parameters unpickles
+        (LL/player.py:75-85).  pickle.dumps of a dict of torch tensors costs ~0.3 ms per call (one torch.save per
+        storage); the shapes never change, so the pickle stream is built ONCE from tensors of the same shapes and every
+        later call only copies the fresh float data from the pinned snapshot over the tensors' payload bytes.
+        blocking=True: take the snapshot now (get_parameters semantics); else collect the one started by publish_begin()."""
+        if blocking:
+            self.publish_begin()
+        views = self.core.publish_views()
+        tpl = getattr(self, "_blob_tpl", None)
+        if tpl is None:
+            rng = np.random.default_rng(12345)
+            fake = {net: {ref: torch.from_numpy(rng.random(views[canon].shape, dtype=np.float32) + 1.0) for ref, canon in m.items()}
+                    for net, m in self._pub_maps}
+            blob = _pickle.dumps(fake)
+            where = []
+            for net, m in self._pub_maps:
+                for ref, canon in m.items():
+                    payload = fake[net][ref].numpy().tobytes()
+                    at = blob.find(payload)
+                    if at < 0 or blob.find(payload, at + 1) >= 0:
+                        raise RuntimeError(f"cannot locate the payload of {net}.{ref} in the pickle stream")
+                    where.append((canon, at, views[canon].shape))
+            tpl = self._blob_tpl = (blob, where)
+        blob, where = tpl
+        buf = bytearray(blob)
+        for canon, at, shape in where:
+            np.frombuffer(buf, dtype=np.float32, count=int(np.prod(shape)), offset=at).reshape(shape)[...] = views[canon]
+        return bytes(buf)
+
     def my_print(self, content):
         os.makedirs(os.path.dirname(self.log_file), exist_ok=True)
         with open(self.log_file, "a") as writer:
@@ -212,16 +245,19 @@ class _BaseLearner:
 
     @property
     def log_alpha(self):
-        return self.core.get_named()["log_alpha"].clone()
+        return self.core.read_named("log_alpha")
 
     # ---- checkpointing (reference format, LL/learner.py:144-182) ------------------------------
-    def _adam_state_dict(self, canon_names, lr, step):
+    def _adam_state_dict(self, canon_names, lr, step, n_frozen_first=0):
+        """torch.optim.Adam.state_dict() layout.  n_frozen_first: parameters that sit in the optimizer's param group before
+        the trainable ones but never get state (the frozen nn.Embedding of the CARE context encoder is parameter 0 of
+        `Adam(context_encoder.parameters())`, MT10_Distributed_CARE/src/learner.py:137-141)."""
         m, v = self.core.get_named(_lib.ADAM_M), self.core.get_named(_lib.ADAM_V)
-        state = {i: {"step": torch.tensor(float(step)), "exp_avg": m[n], "exp_avg_sq": v[n]}
-                 for i, n in enumerate(canon_names)}
+        state = {n_frozen_first + i: {"step": torch.tensor(float(step)), "exp_avg": m[n], "exp_avg_sq": v[n]}
+                 for i, n in enumerate(canon_names)} if step > 0 else {}
         group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
-                 "params": list(range(len(canon_names)))}
+                 "params": list(range(n_frozen_first + len(canon_names)))}
         return {"state": state, "param_groups": [group]}
 
     def _canon(self, nets):
@@ -230,10 +266,10 @@ class _BaseLearner:
             out += list(self._key_map(net).values())
         return out
 
-    def _load_adam(self, sd, canon_names, slot):
+    def _load_adam(self, sd, canon_names, slot, n_frozen_first=0):
         m, v, step = {}, {}, 0
         for i, n in enumerate(canon_names):
-            st = sd["state"].get(i)
+            st = sd["state"].get(n_frozen_first + i)
             if st is None:
                 continue
             m[n], v[n] = st["exp_avg"], st["exp_avg_sq"]
@@ -251,7 +287,9 @@ class _BaseLearner:
     def save_checkpoint(self, episode_idx):
         named = self.core.get_named()
         sc, sa, sl = self.core.get_steps()[:3]
-        state = {"episode_idx": episode_idx, "total_step": self.total_step}
+        # LL / VSAC write 'episode_idx' (LL/learner.py:146, VS:148); MTSAC / CARE / MT1-CARE write and READ 'update_iteration'
+        # (MS/learner.py:159,178; C10:180,202; C1:147,169)
+        state = {self._iteration_key: episode_idx, "total_step": self.total_step}
         state.update(self._critic_checkpoint_entries(named))
         state["critic_optimizer"] = self._adam_state_dict(self._canon(("q1", "q2")), self.lr_critic, sc)
         state["actor"] = self._module_state_dict("actor", named=named)
@@ -288,7 +326,7 @@ class _BaseLearner:
 
     def run(self, max_updates=None):
         self.server.set("update_iteration", _pickle.dumps(-1))
-        self.server.set("parameters", _pickle.dumps(self.get_parameters()))
+        self.server.set("parameters", self.parameters_blob(blocking=True))
         self.wait_until_memoryReady()
         self.my_print("######################### Start train #########################")
         self.soft_update(None, None, 1.0)           # copy parameters to target
@@ -300,7 +338,7 @@ class _BaseLearner:
             self.publish_begin()
             res = self._loss_tuple(self.core.read_losses(1)[0])
             self.server.set("update_iteration", _pickle.dumps(update_iteration))
-            self.server.set("parameters", _pickle.dumps(self.publish_wait()))
+            self.server.set("parameters", self.parameters_blob())
             if self.write_mode:
                 self.write(update_iteration, *res)
                 if update_iteration % self.print_period == 0:
@@ -397,6 +435,7 @@ class MTSACLearner(_BaseLearner):
     save_period, checkpoint_path).  One learner over T tasks, one-hot appended to the state."""
     family = "MS"
     log_name = "MT10_Distributed_MTSAC"
+    _iteration_key = "update_iteration"
 
     def __init__(self, train_classes, train_tasks, cfg_path, write_mode=True, save_period=1000, checkpoint_path=None,
                  *, server=None, device_index=0, seed=0, replay_where="host", precision=1):
@@ -477,6 +516,12 @@ class CARELearner(MTSACLearner):
         super()._init_common(*a, **kw)
         e = self.encoder_cfg
         emb_path, names_path = e.get("pretrained_embedding_json_path"), e.get("task_name_json_path")
+        if emb_path and names_path and not (os.path.exists(emb_path) and os.path.exists(names_path)):
+            # the reference fails fast here (context_encoder.py:31-36 opens both files); training on the random
+            # stand-in table would publish meaningless context vectors without any error
+            if not os.environ.get("B200SAC_ALLOW_RANDOM_EMBEDDING"):
+                raise FileNotFoundError(f"CARE task-embedding files not found (cwd {os.getcwd()}): {emb_path}, {names_path}; "
+                                        "set B200SAC_ALLOW_RANDOM_EMBEDDING=1 to train on a random embedding table")
         if emb_path and names_path and os.path.exists(emb_path) and os.path.exists(names_path):
             table, order = cfg_read(emb_path), cfg_read(names_path)
             E = torch.tensor([table[n] for n in order], dtype=torch.float32)       # context_encoder.py:43-47
@@ -519,9 +564,11 @@ class CARELearner(MTSACLearner):
         d["local_critic"].update(self._module_state_dict("critic_se", named=named))
         d["target_critic"].update(self._module_state_dict("target_se", named=named))
         d["context_encoder"] = self._module_state_dict("context_encoder", named=named)
-        if not self.use_modified_care:
-            d["context_encoder_optimizer"] = self._adam_state_dict(list(self._cenc_map().values()),
-                                                                   self.core.cfg.lr_ctx, self.core.get_steps()[3])
+        # Adam(context_encoder.parameters()): parameter 0 is the frozen embedding (no state); CARE(M) has nothing else, the
+        # reference still saves -- and its load_checkpoint indexes -- the (empty) optimizer state (C10/learner.py:184,206)
+        cenc = [] if self.use_modified_care else list(self._cenc_map().values())
+        step = 0 if self.use_modified_care else self.core.get_steps()[3]
+        d["context_encoder_optimizer"] = self._adam_state_dict(cenc, self.core.cfg.lr_ctx, step, n_frozen_first=1)
         return d
 
     def _load_critic_checkpoint_entries(self, ck):
@@ -531,7 +578,7 @@ class CARELearner(MTSACLearner):
         if "context_encoder" in ck:
             self._load_module_state_dict("context_encoder", ck["context_encoder"])
         if not self.use_modified_care and "context_encoder_optimizer" in ck:
-            self._load_adam(ck["context_encoder_optimizer"], list(self._cenc_map().values()), 3)
+            self._load_adam(ck["context_encoder_optimizer"], list(self._cenc_map().values()), 3, n_frozen_first=1)
 
     def _canon(self, nets):
         out = []

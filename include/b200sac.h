@@ -123,6 +123,10 @@ int b200sac_destroy(b200sac_t* h);
 /* Copy one replica's arena out / in.  `buf` may be a host or a device pointer. */
 int b200sac_export(b200sac_t* h, int32_t which, int32_t replica, float* buf, int64_t n_floats, void* stream);
 int b200sac_import(b200sac_t* h, int32_t which, int32_t replica, const float* buf, int64_t n_floats, void* stream);
+/* n_floats floats at `offset` of one replica's arena into HOST memory (the logger's read of log_alpha, learner.py:199:
+ * a handful of floats instead of the whole arena).  Synchronises the stream. */
+int b200sac_read_range(b200sac_t* h, int32_t which, int32_t replica, int64_t offset, int64_t n_floats, float* out_host,
+                       void* stream);
 /* Device address of an arena (replica 0; replicas are contiguous, stride = arena floats).  For
  * zero-copy views and for the one-time NCCL broadcast of initial weights done by the host shim. */
 int b200sac_arena_ptr(b200sac_t* h, int32_t which, float** dev_ptr, int64_t* floats_per_replica);
@@ -152,6 +156,11 @@ int b200sac_step_host(b200sac_t* h, const float* s, const float* a, const float*
  * Pinned-host ring: indices drawn on the host, rows gathered into pinned staging and
  * copied on a side stream, overlapped with the previous step. */
 int b200sac_step_sampled(b200sac_t* h, b200sac_replay_t* rb, int32_t n_steps, void* stream);
+
+/* Capture and instantiate every CUDA graph b200sac_step_sampled / b200sac_update can launch for this ring (device ring:
+ * the 8-, 4-, 2- and 1-step graphs a run is cut into; host ring: the staged one-step graph of both staging slots) without
+ * running a step, so that no later call pays graph construction (milliseconds).  Synchronises the stream. */
+int b200sac_prepare(b200sac_t* h, b200sac_replay_t* rb, void* stream);
 
 /* Learner.update() (learner.py:246-264) in one call: b200sac_step_sampled(h, rb, 1) followed by the losses of that
  * step, out[replicas][4] = {critic, actor, alpha loss, entropy}.  Synchronises the stream. */
@@ -185,7 +194,10 @@ int b200sac_publish_begin(b200sac_t* h, int32_t replica, int32_t n_ranges, const
 int b200sac_publish_wait(b200sac_t* h, const float** host_ptr, int64_t* n_floats);
 
 /* Debug / parity access to per-step intermediates of replica `replica`:
- * name in {"y","q1","q2","a_next","logp_next","a_cur","logp_cur","qmin","d_action","d_head","r","d"}. */
+ * name in {"y","q1","q2","a_next","logp_next","a_cur","logp_cur","qmin","d_action","d_head","r","d"}, or a hidden
+ * activation whose sign pattern is the ReLU mask the step used: "hA.<l>" [2B][H] (rows [s';s]), "hQ.<l>" / "hP.<l>" /
+ * "hT.<l>" [2][B][H] (critic-update pass / actor pass / target pass; the layer-chained plan does not keep hT),
+ * "mixH.<inst>.<l>" [K][rows][pitch4(H)] (CARE mixture encoders). */
 int b200sac_debug_read(b200sac_t* h, const char* name, int32_t replica, float* out_host, int64_t cap_floats,
                        int64_t* n_floats, void* stream);
 

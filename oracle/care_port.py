@@ -162,15 +162,15 @@ def _seq(p, prefix, x, n, last_relu=False):
     return x
 
 
-def state_encode(spec, p, pre, z_context, mtobs, detach_z_encs=False):
-    """stateEncoder.forward (state_encoder.py:98-129)."""
+def state_encode(spec, p, pre, z_context, mtobs, detach_z_encs=False, tag=None):
+    """stateEncoder.forward (state_encoder.py:98-129).  `tag` names the pass for sac_port.ReluTape (test hook)."""
     x = mtobs[:, :spec.state_dim]
     nl = len(mix_dims(spec))
     for l in range(nl):
         W, b = p[f"{pre}.mix.{l}.W"], p[f"{pre}.mix.{l}.b"]
         x = (torch.einsum("kio,bi->kbo", W, x) if x.dim() == 2 else torch.einsum("kio,kbi->kbo", W, x)) + b
         if l < nl - 1:
-            x = torch.relu(x)
+            x = sp.relu_tagged(x, None if tag is None else f"{pre}.mix:{tag}:{l}")
     z_encs = x.transpose(1, 0)                                   # (B, K, out)
     if detach_z_encs:
         z_encs = z_encs.detach()
@@ -240,11 +240,11 @@ class CarePortLearner:
     def params(self):
         return {k: v.detach().clone() for k, v in self.p.items() if not k.startswith("ase.")}
 
-    def _policy(self, se_prefix, z, obs, eps, detach):
+    def _policy(self, se_prefix, z, obs, eps, detach, tag=None):
         spec, p = self.spec, self.p
         A = spec.act_dim
-        enc = state_encode(spec, p, se_prefix, z, obs, detach_z_encs=detach)
-        out = sp.mlp(p, "actor", enc)
+        enc = state_encode(spec, p, se_prefix, z, obs, detach_z_encs=detach, tag=tag)
+        out = sp.mlp(p, "actor", enc, tag)
         mu, log_std = out[:, :A], torch.clamp(out[:, A:], -20, 2)
         std = torch.exp(log_std)
         u = mu + std * eps
@@ -254,10 +254,10 @@ class CarePortLearner:
         logp = (gauss - torch.log(k * (1 - (act / k) ** 2 + 1e-6))).sum(-1, keepdim=True)
         return act, logp, torch.log(std)
 
-    def _q(self, se_prefix, qa, qb, z, obs, act, detach=False):
-        enc = state_encode(self.spec, self.p, se_prefix, z, obs, detach_z_encs=detach)
+    def _q(self, se_prefix, qa, qb, z, obs, act, detach=False, tag=None):
+        enc = state_encode(self.spec, self.p, se_prefix, z, obs, detach_z_encs=detach, tag=tag)
         x = torch.cat([enc, act], -1)
-        return sp.mlp(self.p, qa, x), sp.mlp(self.p, qb, x)
+        return sp.mlp(self.p, qa, x, tag), sp.mlp(self.p, qb, x, tag)
 
     def update(self, s, a, r, s2, d, eps_next=None, eps_cur=None, want_intermediates=False):
         """Learner.update() minus sampling (learner.py:377-404 + 281-369)."""
@@ -273,17 +273,17 @@ class CarePortLearner:
         z = context_encode(spec, p, tid)                          # contextEncoder.forward
 
         with torch.no_grad():
-            a2, logp2, _ = self._policy("ase", z, s2, eps_next, False)
-            qt1, qt2 = self._q("tse", "q1_target", "q2_target", z, s2, a2)
+            a2, logp2, _ = self._policy("ase", z, s2, eps_next, False, "next")
+            qt1, qt2 = self._q("tse", "q1_target", "q2_target", z, s2, a2, tag="next")
             y = spec.reward_scale * r + spec.gamma * (1 - d) * (torch.min(qt1, qt2) - alpha * logp2)
 
-        q1, q2 = self._q("cse", "q1", "q2", z, s, a)
+        q1, q2 = self._q("cse", "q1", "q2", z, s, a, tag="cur")
         q_loss = torch.mean((y - q1) ** 2) / div + torch.mean((y - q2) ** 2) / div
         q_loss.backward()                                         # also deposits d/d(context encoder) in CARE(O)
         self.opt_critic.step()
 
-        a_cur, logp, log_std = self._policy("ase", z.detach(), s, eps_cur, True)
-        q1n, q2n = self._q("cse", "q1", "q2", z.detach(), s, a_cur, detach=True)
+        a_cur, logp, log_std = self._policy("ase", z.detach(), s, eps_cur, True, "cur")
+        q1n, q2n = self._q("cse", "q1", "q2", z.detach(), s, a_cur, detach=True, tag="pi")
         qmin = torch.min(q1n, q2n)
         pi_loss = torch.mean(-(qmin - alpha * logp)) / div
         pi_loss.backward()

@@ -308,10 +308,158 @@ CASES = {
                                                       critic=dict(critic_hidden_dim=[32, 64, 48]))),
 }
 
+# ---------------------------------------------------------------------------------------------------------------
+# Full-size cases at the CONFIGURED shapes (BASELINE.json configs 3-5, long LL chain).  A full dump of a 1.7 M-parameter
+# learner (parameters, targets, two Adam moments, before and after) would be ~50 MB per case, so these fixtures are
+# "summaries": the INPUTS are regenerated from seeds on the test side (parameters from the port's seeded init -- loaded
+# into the unmodified reference learner here --, minibatches and noise from seeded generators; torch's CPU generators
+# are deterministic for a given torch build, and the GPU box runs this image), and of the reference's OUTPUTS the file
+# keeps per-step losses, the first step's forward intermediates in full, and per tensor its sum, its L2 norm and 1024
+# seeded sample elements.  tests/test_oracle_fullsize.py pins the port to them on CPU (same ATen ops: ~1e-7); the GPU
+# tests compare the CUDA step with them on every quantity that no ReLU kink can move (forward values, losses) and with
+# the port -- masks forced, kinks proven -- on the rest (tests/_golden.py::kink_checked_step).
+# ---------------------------------------------------------------------------------------------------------------
+N_SAMPLE = 1024
+
+
+def summarize(d, prefix, tensors, seed=99):
+    g = torch.Generator().manual_seed(seed)
+    for k, t in tensors.items():
+        t = t.detach().reshape(-1).double()
+        n = t.numel()
+        idx = torch.randperm(n, generator=g)[:min(n, N_SAMPLE)].sort().values
+        d[f"{prefix}/{k}/sum"] = np.float64(t.sum().item())
+        d[f"{prefix}/{k}/l2"] = np.float64(t.norm().item())
+        d[f"{prefix}/{k}/idx"] = idx.numpy().astype(np.int64)
+        d[f"{prefix}/{k}/val"] = t[idx].float().numpy()
+
+
+def _set_params(named, params):
+    with torch.no_grad():
+        for k, prm in named.items():
+            prm.data.copy_(params[k].reshape(prm.shape))
+
+
+def make_full_case(name, family, n_steps, param_seed, data_seed, cfg_overrides=None):
+    weighted = bool((cfg_overrides or {}).get("use_weighted_loss", family == "MS"))
+    lrn, _ = rh.make_learner(family, cfg_overrides, seed=0)
+    spec = _spec_of(lrn, family, weighted)
+    params = sp.init_params(spec, seed=param_seed)
+    named = _named_params(lrn, family)
+    _set_params(named, params)
+    d = {"spec": json.dumps(spec.to_json()), "family": family, "n_steps": n_steps, "param_seed": param_seed,
+         "data_seed": data_seed, "kind": "summary"}
+    g = torch.Generator().manual_seed(data_seed + 17)
+    batches, eps_n, eps_c, losses = [], [], [], []
+    for i in range(n_steps):
+        batches.append(sp.synthetic_batch(spec, seed=data_seed + i))
+        eps_n.append(torch.randn(spec.batch, spec.act_dim, generator=g))
+        eps_c.append(torch.randn(spec.batch, spec.act_dim, generator=g))
+    s, a, r, s2, dn = batches[0]
+    with torch.no_grad(), rh.injected_eps([eps_n[0], eps_c[0]]):
+        if family in ("LL", "VS"):
+            alpha = lrn.log_alpha.exp()
+            a2, lp2 = lrn.actor.get_action_log_prob(s2)
+            qt = torch.min(lrn.target_critic_1(s2, a2), lrn.target_critic_2(s2, a2))
+            q1, q2 = lrn.local_critic_1(s, a), lrn.local_critic_2(s, a)
+            ac, lpc = lrn.actor.get_action_log_prob(s)
+        else:
+            alpha = lrn.get_log_alpha(s).exp()
+            a2, lp2, _ = lrn.actor.get_action_log_prob_log_std(mtobss=s2)
+            qt = torch.min(*lrn.target_critic(mtobss=s2, action=a2))
+            q1, q2 = lrn.local_critic(mtobss=s, action=a)
+            ac, lpc, _ = lrn.actor.get_action_log_prob_log_std(mtobss=s)
+        y = lrn.reward_scale * r + lrn.gamma * (1 - dn) * (qt - alpha * lp2)
+    for k, t in dict(y=y, q1=q1, q2=q2, a_next=a2, logp_next=lp2, a_cur=ac, logp_cur=lpc).items():
+        d["i0/" + k] = t.numpy()
+    for i in range(n_steps):
+        lrn.memory.sample = (lambda b: (lambda: tuple(t.clone() for t in b)))(batches[i])
+        with rh.injected_eps([eps_n[i], eps_c[i]]) as q:
+            res = lrn.update()
+            assert not q
+        losses.append(list(res) + [float("nan")] * (3 - len(res)))
+    d["losses"] = np.array(losses, np.float64)
+    summarize(d, "p_out", {k: p_.detach() for k, p_ in named.items()})
+    m, v, step = _adam_snapshot(lrn, named, spec)
+    summarize(d, "m_out", m); summarize(d, "v_out", v)
+    d["step_out"] = step
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  losses[0]={losses[0]}  losses[-1]={losses[-1]}")
+
+
+def make_full_care_case(name, n_steps, param_seed, data_seed, modified=True):
+    import care_port as cp
+    lrn, _ = rh.make_learner("C10", dict(use_modified_care=modified), seed=0)
+    spec = cp.CareSpec(modified=modified, weighted_loss=modified)
+    params = cp.init_params(spec, seed=param_seed)
+    named = _care_named(lrn)
+    _set_params(named, params)
+    with torch.no_grad():       # the actor's own state encoder starts tied to the critic's (learner.py:130-134, :402)
+        ase = dict(lrn.actor.state_encoder.named_parameters()); cse = dict(lrn.local_critic.state_encoder.named_parameters())
+        for k in ase:
+            ase[k].data.copy_(cse[k].data)
+    d = {"spec": json.dumps(spec.to_json()), "family": "C10", "n_steps": n_steps, "param_seed": param_seed,
+         "data_seed": data_seed, "kind": "summary"}
+    g = torch.Generator().manual_seed(data_seed + 17)
+    batches, eps_n, eps_c, losses = [], [], [], []
+    for i in range(n_steps):
+        batches.append(cp.synthetic_batch(spec, seed=data_seed + i))
+        eps_n.append(torch.randn(spec.batch, spec.act_dim, generator=g))
+        eps_c.append(torch.randn(spec.batch, spec.act_dim, generator=g))
+    s, a, r, s2, dn = batches[0]
+    with torch.no_grad(), rh.injected_eps([eps_n[0], eps_c[0]]):
+        alpha = lrn.get_log_alpha(s).exp()
+        z = lrn.context_encoder.forward(s)
+        a2, lp2, _ = lrn.actor.get_action_log_prob_log_std(mtobss=s2, z_context=z)
+        qt = torch.min(*lrn.target_critic.forward(mtobss=s2, z_context=z, action=a2))
+        q1, q2 = lrn.local_critic.forward(mtobss=s, z_context=z, action=a)
+        ac, lpc, _ = lrn.actor.get_action_log_prob_log_std(mtobss=s, z_context=z)
+        y = lrn.reward_scale * r + lrn.gamma * (1 - dn) * (qt - alpha * lp2)
+    for k, t in dict(y=y, q1=q1, q2=q2, a_next=a2, logp_next=lp2, a_cur=ac, logp_cur=lpc).items():
+        d["i0/" + k] = t.numpy()
+    for i in range(n_steps):
+        lrn.memory.sample = (lambda b: (lambda: tuple(t.clone() for t in b)))(batches[i])
+        with rh.injected_eps([eps_n[i], eps_c[i]]) as q:
+            res = lrn.update()
+            assert not q
+        losses.append(list(res))
+    d["losses"] = np.array(losses, np.float64)
+    summarize(d, "p_out", {k: p_.detach() for k, p_ in named.items()})
+    trainable = [k for k in named if not (k.startswith("tse.") or "_target" in k or k == "embedding")]
+    opts = {"critic": lrn.critic_optimizer, "actor": lrn.actor_optimizer, "alpha": lrn.log_alpha_optimizer,
+            "ctx": lrn.context_encoder_optimizer}
+    m, v, steps = {}, {}, {"critic": 0, "actor": 0, "alpha": 0, "ctx": 0}
+    for k in trainable:
+        tag = "alpha" if k == "log_alpha" else ("actor" if k.startswith("actor.") else ("ctx" if k.startswith("cenc.") else "critic"))
+        st = opts[tag].state[named[k]]
+        m[k], v[k] = st["exp_avg"].clone(), st["exp_avg_sq"].clone()
+        steps[tag] = int(st["step"])
+    summarize(d, "m_out", m); summarize(d, "v_out", v)
+    d["step_out"] = np.array([steps["critic"], steps["actor"], steps["alpha"]] + ([] if modified else [steps["ctx"]]), np.int64)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  losses[0]={losses[0]}  losses[-1]={losses[-1]}")
+
+
+FULL_CASES = {
+    "full_vs_s3": dict(family="VS", n_steps=3, param_seed=21, data_seed=700),                 # config 3: 39/4/400^3, B 1024
+    "full_ms_s3": dict(family="MS", n_steps=3, param_seed=22, data_seed=710),                 # config 4: B 1280, weighted loss
+    "full_ll_s100": dict(family="LL", n_steps=100, param_seed=23, data_seed=720),             # 100 chained steps
+}
+FULL_CARE_CASES = {
+    "full_c10m_s2": dict(n_steps=2, param_seed=24, data_seed=730, modified=True),             # config 5: CARE(M) B 1280 K 6
+    "full_c10o_s2": dict(n_steps=2, param_seed=25, data_seed=740, modified=False),
+}
+
 if __name__ == "__main__":
-    todo = sys.argv[1:] or (list(CASES) + list(CARE_CASES))
+    todo = sys.argv[1:] or (list(CASES) + list(CARE_CASES) + list(FULL_CASES) + list(FULL_CARE_CASES))
     for c in todo:
-        if c in CARE_CASES:
+        if c in FULL_CASES:
+            make_full_case(c, **FULL_CASES[c])
+        elif c in FULL_CARE_CASES:
+            make_full_care_case(c, **FULL_CARE_CASES[c])
+        elif c in CARE_CASES:
             make_care_case(c, **CARE_CASES[c])
         else:
             make_case(c, **CASES[c])

@@ -3,8 +3,10 @@
 Works only where /root/reference exists (the build container).  Nothing under
 tests -m gpu, smoke() or bench.py may import this file: the GPU box has no
 /root/reference.  It is used by oracle/gen_golden.py to produce the committed
-fixtures under tests/golden/ and by tests/test_oracle_vs_reference.py (skipped
-when the reference is absent) to pin oracle/sac_port.py to the real code.
+fixtures under tests/golden/, by tests/test_oracle_vs_reference.py (skipped when the
+reference is absent) to pin oracle/sac_port.py to the real code, and by bench.py's CPU
+arm (`cpu_baseline.kind == "reference"`) when a reference checkout is reachable
+(B200SAC_REFERENCE, /root/reference or baseline/_ref) -- never by the product path.
 
 How the reference is made importable:
   * `redis` -> oracle/redis_stub.py, installed in sys.modules first;
@@ -23,7 +25,15 @@ import tempfile
 
 import torch
 
-REF_ROOT = os.environ.get("B200SAC_REFERENCE", "/root/reference")
+def _find_reference():
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("B200SAC_REFERENCE"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "LunarLander_Distributed_SAC", "src")):
+            return cand
+    return os.environ.get("B200SAC_REFERENCE", "/root/reference")
+
+
+REF_ROOT = _find_reference()
 
 VARIANTS = {
     # name: (src dir, cfg file)
@@ -121,3 +131,20 @@ def injected_eps(eps_list):
         yield queue
     finally:
         tdn._standard_normal = orig
+
+
+def fill_memory(lrn, variant, batch):
+    """Append transitions (tensors s, a, r, s2, d; MT: s carries the one-hot task id in its last columns) to the reference
+    ReplayBuffer's own deque(s), as its Redis-drain thread would (LL/replay_buffer.py:52-59, MS/replay_buffers.py:57-63)."""
+    import numpy as np
+    s, a, r, s2, d = [t.numpy() for t in batch]
+    mem = lrn.memory
+    E = mem.experience
+    if hasattr(mem, "memories"):
+        T = len(mem.memories)
+        task = np.argmax(s[:, -T:], axis=1)
+        for i in range(s.shape[0]):
+            mem.memories[int(task[i])].append(E(s[i].astype(np.float64), a[i], float(r[i, 0]), s2[i].astype(np.float64), bool(d[i, 0])))
+    else:
+        for i in range(s.shape[0]):
+            mem.memory.append(E(s[i].astype(np.float64), a[i], float(r[i, 0]), s2[i].astype(np.float64), bool(d[i, 0])))

@@ -156,19 +156,49 @@ def synthetic_batch(spec: SacSpec, seed=1234, batch=None):
     return s, a, r, s2, d
 
 
-def mlp(params, net, x):
+class ReluTape:
+    """Test hook for the ReLU-kink analysis (tests/test_gpu_parity.py).  While installed (`with ReluTape(...)`), every
+    ReLU of the port records its pre-activation under a tag "<net>:<pass>:<layer>" and, if `forced` holds a boolean mask
+    for that tag, gates with THAT mask instead of z > 0 (forward z * mask, backward grad * mask).  Two correct fp32
+    evaluations of the same step can put a pre-activation within rounding of zero on different sides of the ReLU; with
+    the masks of the implementation under test forced into the oracle, everything else must agree to 1e-4, and every
+    forced bit that differs from the oracle's own must sit on such a numerically-zero pre-activation."""
+    current = None
+
+    def __init__(self, forced=None):
+        self.forced = forced or {}
+        self.z = {}
+
+    def __enter__(self):
+        ReluTape.current = self
+        return self
+
+    def __exit__(self, *exc):
+        ReluTape.current = None
+
+
+def relu_tagged(z, tag):
+    tape = ReluTape.current
+    if tape is None or tag is None:
+        return torch.relu(z)
+    tape.z[tag] = z.detach()
+    m = tape.forced.get(tag)
+    return torch.relu(z) if m is None else z * m.to(z.dtype)
+
+
+def mlp(params, net, x, tag=None):
     n = len([k for k in params if k.startswith(net + ".") and k.endswith(".weight")])
     for i in range(n):
         x = F.linear(x, params[f"{net}.{i}.weight"], params[f"{net}.{i}.bias"])
         if i < n - 1:
-            x = torch.relu(x)
+            x = relu_tagged(x, None if tag is None else f"{net}:{tag}:{i}")
     return x
 
 
-def policy_sample(spec, params, obs, eps):
+def policy_sample(spec, params, obs, eps, tag=None):
     """LL/model.py:38-65. Returns action, log_prob (B,1), log_std (B,act)."""
     A = spec.act_dim
-    out = mlp(params, "actor", obs)
+    out = mlp(params, "actor", obs, tag)
     mu = out[:, :A]
     log_std = torch.clamp(out[:, A:], -20, 2)
     std = torch.exp(log_std)
@@ -252,20 +282,20 @@ class PortLearner:
         div = float(B) if spec.weighted_loss else 1.0
 
         with torch.no_grad():
-            a2, logp2, _ = policy_sample(spec, p, s2, eps_next)
+            a2, logp2, _ = policy_sample(spec, p, s2, eps_next, "next")
             x2 = torch.cat([s2, a2], -1)
-            qt = torch.min(mlp(p, "q1_target", x2), mlp(p, "q2_target", x2))
+            qt = torch.min(mlp(p, "q1_target", x2, "next"), mlp(p, "q2_target", x2, "next"))
             y = spec.reward_scale * r + spec.gamma * (1 - d) * (qt - alpha * logp2)
 
         x = torch.cat([s, a], -1)
-        q1, q2 = mlp(p, "q1", x), mlp(p, "q2", x)
+        q1, q2 = mlp(p, "q1", x, "cur"), mlp(p, "q2", x, "cur")
         q_loss = torch.mean((y - q1) ** 2) / div + torch.mean((y - q2) ** 2) / div
         q_loss.backward()
         self.opt_critic.step()
 
-        a_cur, logp, log_std = policy_sample(spec, p, s, eps_cur)
+        a_cur, logp, log_std = policy_sample(spec, p, s, eps_cur, "cur")
         xa = torch.cat([s, a_cur], -1)
-        q1n, q2n = mlp(p, "q1", xa), mlp(p, "q2", xa)      # already-updated critics
+        q1n, q2n = mlp(p, "q1", xa, "pi"), mlp(p, "q2", xa, "pi")      # already-updated critics
         qmin = torch.min(q1n, q2n)
         pi_loss = torch.mean(-(qmin - alpha * logp)) / div
         pi_loss.backward()

@@ -1,0 +1,83 @@
+"""GPU: the CUDA step against the full-size fixtures of the UNMODIFIED reference (BASELINE.json configs 3-5 at their
+configured shapes and a 100-step LunarLander chain; oracle/gen_golden.py FULL_CASES, pinned to the port on CPU by
+tests/test_oracle_fullsize.py).
+
+The CUDA learner runs the whole chain on its own (no re-synchronisation).  Checked against the reference fixture,
+strictly at 1e-4: the first step's forward intermediates and the losses of EVERY step -- quantities no ReLU kink can
+move beyond the bar.  The gradient-derived state is checked strictly at 1e-4 too, with the kinks proven instead of
+budgeted: a port learner follows the same chain with the masks the CUDA step used forced in (tests/_golden.py), every
+forced bit that differs from the port's own must sit on a numerically-zero pre-activation, and the final CUDA state must
+equal that port's state; when no bit differed at all, the CUDA state must equal the reference's summary directly."""
+import math
+
+import pytest
+import torch
+
+import sac_port as sp
+from _golden import (FULL_CARE_CASES, FULL_CASES, REL, FullCase, care_core_config, check_port_state, core_config,
+                     cuda_relu_masks, rel_l2, rel_scalar)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from distributed_sac_b200 import _lib
+    _lib.load()
+    return torch.device("cuda", 0)
+
+
+def _cases():
+    out = []
+    for name in FULL_CASES + FULL_CARE_CASES:
+        for precision in (0, 1):
+            if name in FULL_CARE_CASES and precision == 0:
+                continue          # (CARE at B = 1280 in exact-fp32 FFMA is covered by the small fixtures; 3xTF32 is its production mode)
+            out.append(pytest.param(name, precision, id=f"{name}-{'fp32' if precision == 0 else 'tc3xtf32'}"))
+    return out
+
+
+@pytest.mark.parametrize("name,precision", _cases())
+def test_chain_matches_reference_fixture_at_full_size(cuda, name, precision):
+    from distributed_sac_b200 import _lib
+    from distributed_sac_b200.core import SacCore
+    c = FullCase(name)
+    cfg = care_core_config(c.spec, precision=precision) if c.care else core_config(c.spec, precision=precision)
+    core = SacCore(cfg, 0, seed=0)
+    core.set_named(c.params)
+    port = c.make_port()
+    total_flips = 0
+    for i in range(c.n_steps):
+        core.step(*c.batches[i], c.eps_next[i], c.eps_cur[i])
+        if i == 0:
+            for k, ref in c.i0.items():
+                got = core.debug(k).reshape(ref.shape)
+                assert rel_l2(got, ref) <= REL, (k, rel_l2(got, ref))
+        L = core.read_losses(1)[0, 0]
+        assert rel_scalar(float(L[0]), c.losses[i, 0]) <= REL, ("critic_loss", i, float(L[0]), c.losses[i, 0])
+        assert rel_scalar(float(L[1]), c.losses[i, 1]) <= REL, ("actor_loss", i, float(L[1]), c.losses[i, 1])
+        if not math.isnan(c.losses[i, 2]):
+            assert rel_scalar(float(L[3]), c.losses[i, 2]) <= REL, ("entropy", i)
+        # the same step in the port with the CUDA masks forced; differing bits must be kinks
+        forced = cuda_relu_masks(core, c.spec, 0, c.care)
+        with sp.ReluTape(forced) as tape:
+            port.update_SAC(*c.batches[i], c.eps_next[i], c.eps_cur[i])
+        for tag, m in forced.items():
+            z = tape.z[tag]
+            diff = (z > 0) != m
+            n = int(diff.sum())
+            if n:
+                tol = REL * max(1.0, float(z.abs().mean()))
+                worst = float(z[diff].abs().max())
+                assert worst <= tol, f"step {i}: mask bit of {tag} differs at |z| = {worst:.3e} > {tol:.3e}: not a ReLU kink"
+                total_flips += n
+    check_port_state(core, port)                       # strict 1e-4: CUDA chain == port chain with the same masks
+    assert tuple(core.get_steps()) == tuple(int(x) for x in c.step_out)
+    if total_flips == 0:                               # no kink anywhere in the chain: the reference's own numbers, directly
+        c.check_summary("p_out", core.get_named(_lib.PARAMS), REL, "CUDA parameters")
+        c.check_summary("m_out", core.get_named(_lib.ADAM_M), REL, "CUDA Adam m")
+        c.check_summary("v_out", core.get_named(_lib.ADAM_V), REL, "CUDA Adam v")
+    print(f"[kinks] {name} precision {precision}: {total_flips} mask bits differed over {c.n_steps} steps (all at numerically-zero pre-activations)")
+    core.close()

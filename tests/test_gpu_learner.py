@@ -165,8 +165,24 @@ def test_care_learner_surface(cuda, tmp_path, modified):
     ck = torch.load(path, map_location="cpu", weights_only=False)
     assert "state_encoder.trunk.0.weight" in ck["local_critic"] and "Q_function_2.6.bias" in ck["target_critic"]
     assert len(ck["critic_optimizer"]["state"]) == (14 if modified else 8) + 16 and len(ck["actor_optimizer"]["state"]) == 8
-    if not modified:
-        assert len(ck["context_encoder_optimizer"]["state"]) == 10 and int(ck["context_encoder_optimizer"]["state"][0]["step"]) == 4
+    # MTSAC / CARE checkpoints carry 'update_iteration' (C10/learner.py:180,202), and the context-encoder optimizer is
+    # Adam(context_encoder.parameters()): parameter 0 = the frozen embedding (never any state), CARE(M) has nothing else
+    assert ck["update_iteration"] == 24 and "episode_idx" not in ck
+    ceo = ck["context_encoder_optimizer"]
+    if modified:
+        assert ceo["state"] == {} and ceo["param_groups"][0]["params"] == [0]
+    else:
+        assert sorted(ceo["state"]) == list(range(1, 11)) and int(ceo["state"][1]["step"]) == 4
+        assert ceo["param_groups"][0]["params"] == list(range(11))
+        assert ceo["state"][1]["exp_avg"].shape == (100, 768) and ceo["state"][10]["exp_avg"].shape == (50,)
+    # the bytes run() publishes == a plain pickle of get_parameters() once unpickled
+    pub = pickle.loads(lrn.parameters_blob(blocking=True))
+    ref_pub = lrn.get_parameters()
+    assert set(pub) == set(ref_pub)
+    for net in ref_pub:
+        assert set(pub[net]) == set(ref_pub[net])
+        for k in ref_pub[net]:
+            assert pub[net][k].dtype == torch.float32 and torch.equal(pub[net][k], ref_pub[net][k]), (net, k)
     before = lrn.core.export_arena()
     lrn2 = CARELearner(None, names_, str(p), write_mode=False, server=redis_stub.StrictRedis(host=str(tmp_path) + "d"),
                        seed=5, checkpoint_path=path)
@@ -188,6 +204,9 @@ def test_publication_snapshot_is_consistent_and_async(cuda, tmp_path):
     full = lrn._module_state_dict("actor")                       # slow path: whole arena D2H
     blob = lrn.get_parameters()["actor"]
     assert set(blob) == set(full) and all(torch.equal(blob[k], full[k]) for k in full)
+    fast = pickle.loads(lrn.parameters_blob(blocking=True))["actor"]      # template-patched pickle stream (run() publishes this)
+    assert set(fast) == set(full) and all(torch.equal(fast[k], full[k]) and fast[k].is_contiguous() for k in full)
+    assert torch.equal(lrn.log_alpha, lrn.core.get_named()["log_alpha"])          # small-range read == arena export
     lrn.publish_begin()                                          # snapshot after step 3 ...
     lrn.core.step_sampled(lrn.memory.ring, 40)                   # ... while 40 more steps are enqueued behind it
     snap = lrn.publish_wait()["actor"]

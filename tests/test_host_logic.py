@@ -130,3 +130,41 @@ def test_publication_ranges_and_unpack_without_a_gpu():
         assert t.numpy().base is None or not np.shares_memory(t.numpy(), calls["buf"])
     w0 = table["actor.0.weight"]
     assert w0[5] >= w0[2] and w0[5] % 4 == 0                       # padded pitch of the first layer is hidden from the caller
+
+
+def test_parameters_blob_template_patching_round_trips():
+    """Learner.parameters_blob(): the pickle stream is built once from tensors of the published shapes and later calls only
+    overwrite the tensors' payload bytes -- unpickling must give exactly what a plain pickle.dumps of the state_dict gives."""
+    import pickle
+    import numpy as np
+    import torch
+    from distributed_sac_b200.learner import _BaseLearner
+
+    class FakeCore:
+        def __init__(self): self.views = {}
+        def publish_views(self): return self.views
+
+    lrn = _BaseLearner.__new__(_BaseLearner)
+    lrn.core = FakeCore()
+    shapes = {"actor.0.weight": (256, 8), "actor.0.bias": (256,), "actor.1.weight": (256, 256), "actor.1.bias": (256,),
+              "actor.2.weight": (4, 256), "actor.2.bias": (4,)}
+    km = {"layer_intermediate.0.weight": "actor.0.weight", "layer_intermediate.0.bias": "actor.0.bias",
+          "layer_intermediate.1.weight": "actor.1.weight", "layer_intermediate.1.bias": "actor.1.bias",
+          "mu_log_std_layer.weight": "actor.2.weight", "mu_log_std_layer.bias": "actor.2.bias"}
+    lrn._pub_maps = [("actor", km)]
+    rng = np.random.default_rng(0)
+    for rnd in range(3):
+        # a non-contiguous view for the first-layer weight (padded row pitch in the arena), zeros for the biases
+        padded = rng.standard_normal((256, 12)).astype(np.float32)
+        lrn.core.views = {k: (np.zeros(sh, np.float32) if "bias" in k and rnd == 0 else rng.standard_normal(sh).astype(np.float32))
+                          for k, sh in shapes.items()}
+        lrn.core.views["actor.0.weight"] = padded[:, :8]
+        blob = lrn.parameters_blob()
+        got = pickle.loads(blob)
+        assert set(got) == {"actor"} and set(got["actor"]) == set(km)
+        for ref, canon in km.items():
+            t = got["actor"][ref]
+            assert isinstance(t, torch.Tensor) and t.dtype == torch.float32 and tuple(t.shape) == shapes[canon]
+            assert np.array_equal(t.numpy(), np.asarray(lrn.core.views[canon]))
+        plain = pickle.loads(pickle.dumps({"actor": {ref: torch.from_numpy(np.ascontiguousarray(lrn.core.views[c_])) for ref, c_ in km.items()}}))
+        assert all(torch.equal(plain["actor"][k], got["actor"][k]) for k in km)
