@@ -177,14 +177,15 @@ class SacCore:
             a = a.reshape(-1)
         return a
 
-    def act(self, obs, stochastic=True, eps=None, replica=0) -> torch.Tensor:
-        """Batched Actor.get_action for n <= 2*batch observation rows (CPU or CUDA tensor [n][obs_dim]); returns a CPU tensor
-        [n][act_dim].  eps ([n][act_dim]) injects the noise; stochastic=False gives k*tanh(mu)."""
+    def act(self, obs, stochastic=True, eps=None, replica=0, no_tanh=False) -> torch.Tensor:
+        """Batched Actor.get_action for n <= 2*batch (CARE: batch) observation rows (CPU or CUDA tensor [n][obs_dim]); returns a
+        CPU tensor [n][act_dim].  eps ([n][act_dim]) injects the noise; stochastic=False gives k*tanh(mu), or k*mu with
+        no_tanh=True (the LunarLander actor's deterministic action)."""
         obs = obs.to(torch.float32).contiguous()
         n = obs.shape[0]
         e = None if eps is None else eps.to(torch.float32).contiguous()
         out = torch.empty(n, self.cfg.act_dim)
-        _lib.check(self.lib.b200sac_act(self._h, replica, n, _ptr(obs), _ptr(e), 1 if stochastic else 0, _ptr(out), _stream()))
+        _lib.check(self.lib.b200sac_act(self._h, replica, n, _ptr(obs), _ptr(e), 1 if stochastic else (-1 if no_tanh else 0), _ptr(out), _stream()))
         return out
 
     # ---- publication path (Learner.get_parameters, LL/learner.py:272-276) ---------------------------

@@ -315,6 +315,7 @@ struct b200sac {
   float* pub_h = nullptr;         // pinned host copy handed to the caller
   int64_t pub_cap = 0, pub_n = 0;
   bool pub_pending = false;
+  long long* chain_dbg = nullptr; // B200SAC_CHAIN_DBG=1: [plan launches][CH_DBG_SLOTS] clock64 timelines of the chain kernels
   float* split_d = nullptr;       // b200sac_step: handle-owned copy of the caller's minibatch arrays (stable graph pointers)
   float* loss_h = nullptr;        // mapped pinned loss ring [kLossSlots][R][4], written by the tail kernels
   float* loss_h_dev = nullptr;    // its device-side address
@@ -368,6 +369,7 @@ static int destroy_impl(b200sac* h) {
   if (h->ev_pub_done) cudaEventDestroy(h->ev_pub_done);
   cudaFree(h->pub_d);
   cudaFree(h->split_d);
+  cudaFree(h->chain_dbg);
   if (h->pub_h) cudaFreeHost(h->pub_h);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->fork) cudaStreamDestroy(h->fork);
@@ -498,7 +500,12 @@ static int build_plan_fused(b200sac* h, const std::function<void(int)>& adam) {
     l.smem = CH_SMEM_BYTES;
     return l;
   };
+  if (getenv("B200SAC_CHAIN_DBG")) {
+    CU(cudaMalloc(&h->chain_dbg, sizeof(long long) * CH_DBG_SLOTS * 16));
+    CU(cudaMemset(h->chain_dbg, 0, sizeof(long long) * CH_DBG_SLOTS * 16));
+  }
   auto finish_chain = [&](Launch& l) {
+    if (h->chain_dbg && h->plan.size() < 16) l.chain.dbg = h->chain_dbg + h->plan.size() * CH_DBG_SLOTS;
     int maxb = 1;
     for (int j = 0; j < l.chain.njobs; ++j) {
       const int nb = (l.chain.job[j].rows + CH_ROWS - 1) / CH_ROWS;
@@ -2266,14 +2273,94 @@ extern "C" int b200sac_read_losses(b200sac_t* h, int32_t n_last, float* out_host
 // MT10_Distributed_MTSAC/src/model.py:58-73) for many environments at once.  stochastic = 0 gives k*tanh(mu).
 // Uses the actor's own work buffers, so it is ordered with the steps on `stream` like any other call of the handle.
 // ------------------------------------------------------------------------------------------
+// LunarLander's deterministic action: k * mu, no tanh (LunarLander_Distributed_SAC/src/model.py:78-80)
+__global__ void act_scaled_mu_kernel(const float* __restrict__ pout, int A, int n, float k, float* __restrict__ act) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * A) return;
+  act[e] = k * pout[(long long)(e / A) * 2 * A + (e % A)];
+}
+
+// task id of n observation rows: argmax of the trailing one-hot (context_encoder.py:101-106), first maximum like torch.argmax
+__global__ void act_task_ids_kernel(const float* __restrict__ X, int obs, int T, int n, int* __restrict__ tid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* row = X + (long long)i * obs + (obs - T);
+  int t = 0;
+  float best = row[0];
+  for (int q = 1; q < T; ++q)
+    if (row[q] > best) { best = row[q]; t = q; }
+  tid[i] = t;
+}
+
+// CARE actors (MT10_Distributed_CARE/src/player.py:199-209: z = context_encoder(mtobs); actor.get_action(mtobs, z)):
+// encode the n observation rows sitting in XS[0..n) of `replica` with the critic's state encoder -- the actor's is its
+// hard copy (learner.py:402) -- into XA[0..n): per-task tables, K mixture encoders, attention mix.
+static int care_encode_rows(b200sac* h, cudaStream_t st, int replica, int n) {
+  const b200sac_cfg& c = h->cfg;
+  const Layout& L = h->L;
+  const int B = c.batch, Kenc = c.num_encoders, nmix = (int)L.mix.size();
+  auto pitch = [](int w) { return (w + 3) & ~3; };
+  float* par = h->params + (long long)replica * L.arena;
+  float* XS = h->XS.p + (long long)replica * h->XS.rs;
+  int* tid = (int*)(h->tid.p + (long long)replica * h->tid.rs);
+  act_task_ids_kernel<<<(n + 255) / 256, 256, 0, st>>>(XS, h->K.obs, c.num_tasks, n, tid);
+  {
+    CareTabArgs P;
+    memset(&P, 0, sizeof(P));
+    P.params = par; P.rsP = 0; P.emb_off = L.off_emb;
+    P.trunk = h->care_trunk; P.ctx = h->care_ctx;
+    P.T = c.num_tasks; P.K = Kenc; P.row_w = h->care_row_w; P.off_att = h->care_off_att;
+    P.original = c.care == 2 ? 1 : 0;
+    P.inst_delta[0] = 0;
+    P.tab[0] = h->careTab[0].p + (long long)replica * h->careTab[0].rs; P.rsTab = 0;
+    care_tables_kernel<<<dim3(c.num_tasks, 1, 1), 512, 0, st>>>(P);
+  }
+  for (int l = 0; l < nmix; ++l) {
+    const LayerOff& lo = L.mix[l];
+    const bool last = (l == nmix - 1);
+    const Buf& ob = last ? h->mixZ[0] : h->mixH[0][l];
+    GemmGroup grp;
+    memset(&grp, 0, sizeof(grp));
+    for (int k0 = 0; k0 < Kenc; k0 += GS_MAXG) {
+      const int cnt = (Kenc - k0 < GS_MAXG) ? Kenc - k0 : GS_MAXG;
+      grp.G = cnt;
+      for (int q = 0; q < cnt; ++q) {
+        const int k = k0 + q;
+        GemmProb& p = grp.p[q];
+        memset(&p, 0, sizeof(p));
+        if (l == 0) { p.A = XS; p.lda = h->K.obs; }
+        else { p.A = h->mixH[0][l - 1].p + (long long)replica * h->mixH[0][l - 1].rs + (long long)k * 2 * B * pitch(lo.in); p.lda = pitch(lo.in); }
+        p.B = par + lo.w + (long long)k * lo.out * lo.in; p.ldb = lo.in;
+        p.bias = par + lo.b + (long long)k * lo.out;
+        p.C = ob.p + (long long)replica * ob.rs + (long long)k * 2 * B * pitch(lo.out); p.ldc = pitch(lo.out);
+        p.M = n; p.N = lo.out; p.K = lo.in; p.mode = GEMM_FWD; p.relu = last ? 0 : 1;
+      }
+      gemm_simt_kernel<<<dim3((lo.out + GS_T - 1) / GS_T, (n + GS_T - 1) / GS_T, cnt), GS_THREADS, 0, st>>>(grp);
+    }
+  }
+  {
+    CareMixArgs P;
+    memset(&P, 0, sizeof(P));
+    P.Z = h->mixZ[0].p + (long long)replica * h->mixZ[0].rs; P.rsZ = 0; P.kstride = (long long)2 * B * pitch(c.mix_out); P.ldz = pitch(c.mix_out);
+    P.tab = h->careTab[0].p + (long long)replica * h->careTab[0].rs; P.rsTab = 0; P.row_w = h->care_row_w; P.off_att = h->care_off_att;
+    P.off_ctx = h->care_off_ctx;
+    P.tid = tid; P.rsR = 0;
+    P.rows = n; P.B = B; P.K = Kenc; P.mo = c.mix_out; P.co = c.ctx_out;
+    P.dst1 = h->XA.p + (long long)replica * h->XA.rs; P.rsD1 = 0; P.ld1 = h->K.ldxa;
+    care_mix_kernel<<<dim3((n + 7) / 8, 1), 256, 0, st>>>(P);
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int b200sac_act(b200sac_t* h, int32_t replica, int32_t n, const float* obs, const float* eps, int32_t stochastic,
                            float* actions_out, void* stream) {
   if (!h || !obs || !actions_out) return fail(B200SAC_ERR_INVALID, "null argument");
   if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica %d out of range", replica);
   const b200sac_cfg& c = h->cfg;
   const int B = c.batch, A = c.act_dim, La = c.n_actor_hidden;
-  if (n < 1 || n > 2 * B) return fail(B200SAC_ERR_INVALID, "n must be in [1, 2*batch = %d], got %d", 2 * B, n);
-  if (c.care) return fail(B200SAC_ERR_INVALID, "b200sac_act: CARE actors need the state encoder path (not built)");
+  const int nmax = c.care ? B : 2 * B;           // CARE: one task id per row lives in the [batch] task-id buffer
+  if (n < 1 || n > nmax) return fail(B200SAC_ERR_INVALID, "n must be in [1, %d] (2*batch; batch for CARE handles), got %d", nmax, n);
   CU(cudaSetDevice(h->device));
   StreamBridge sb(h, stream);
   if (int rc = sb.begin()) return rc;
@@ -2281,8 +2368,13 @@ extern "C" int b200sac_act(b200sac_t* h, int32_t replica, int32_t n, const float
   const Layout& L = h->L;
   const int obs_w = h->K.obs;
   float* XA = h->XA.p + (long long)replica * h->XA.rs;
-  CU(cudaMemcpy2DAsync(XA, (size_t)h->K.ldxa * sizeof(float), obs, (size_t)obs_w * sizeof(float), (size_t)obs_w * sizeof(float),
-                       (size_t)n, cudaMemcpyDefault, st));
+  if (c.care) {
+    CU(cudaMemcpyAsync(h->XS.p + (long long)replica * h->XS.rs, obs, (size_t)n * obs_w * sizeof(float), cudaMemcpyDefault, st));
+    if (int rc = care_encode_rows(h, st, replica, n)) return rc;
+  } else {
+    CU(cudaMemcpy2DAsync(XA, (size_t)h->K.ldxa * sizeof(float), obs, (size_t)obs_w * sizeof(float), (size_t)obs_w * sizeof(float),
+                         (size_t)n, cudaMemcpyDefault, st));
+  }
   for (int l = 0; l < La; ++l) {
     const LayerOff& lo = L.actor[l];
     GemmGroup grp;
@@ -2305,7 +2397,7 @@ extern "C" int b200sac_act(b200sac_t* h, int32_t replica, int32_t n, const float
   if (eps != nullptr) {
     CU(cudaMemcpyAsync(epsb, eps, (size_t)n * A * sizeof(float), cudaMemcpyDefault, st));
     P.use_eps_buf = 1;
-  } else if (!stochastic) {
+  } else if (stochastic <= 0) {
     CU(cudaMemsetAsync(epsb, 0, (size_t)n * A * sizeof(float), st));       // u = mu: Actor.get_action(stochastic=False)
     P.use_eps_buf = 1;
   } else {
@@ -2314,6 +2406,8 @@ extern "C" int b200sac_act(b200sac_t* h, int32_t replica, int32_t n, const float
   StepConst K = h->K;
   K.seed ^= 0x5851F42D4C957F2Dull * (unsigned long long)(++h->act_calls);    // fresh noise per call, not per training step
   policy_head_kernel<<<dim3((n + 7) / 8, 1), 256, 0, st>>>(K, P);
+  if (stochastic < 0 && eps == nullptr)          // k * mu instead of k * tanh(mu)
+    act_scaled_mu_kernel<<<(n * A + 255) / 256, 256, 0, st>>>(P.pout, A, n, (float)c.action_scale, P.act_out);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(actions_out, h->act_out.p + (long long)replica * h->act_out.rs, (size_t)n * A * sizeof(float), cudaMemcpyDefault, st));
   if (int rc = sb.end()) return rc;
@@ -2356,6 +2450,10 @@ extern "C" int b200sac_debug_read(b200sac_t* h, const char* name, int32_t replic
   else if (nm == "qmin") { src = h->qmin.p + replica * h->qmin.rs; n = B; }
   else if (nm == "d_action") { src = h->dact_dbg.p + replica * h->dact_dbg.rs; n = (int64_t)B * A; }
   else if (nm == "d_head") { src = h->dout_dbg.p + replica * h->dout_dbg.rs; n = (int64_t)B * 2 * A; }
+  else if (nm == "chain_dbg") {
+    if (!h->chain_dbg) return fail(B200SAC_ERR_INVALID, "chain_dbg needs B200SAC_CHAIN_DBG=1 at create time");
+    src = reinterpret_cast<const float*>(h->chain_dbg); n = 2 * CH_DBG_SLOTS * 16;     // int64 stamps viewed as float pairs
+  }
   else {
     // hidden activations (the ReLU masks of the step): "hA.<l>" [2B][H] rows [s';s]; "hQ.<l>" / "hT.<l>" / "hP.<l>" [2][B][H]
     // (critic update pass / target pass -- not kept by the layer-chained plan -- / actor pass); CARE mixture encoders

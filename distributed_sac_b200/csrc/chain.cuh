@@ -88,9 +88,11 @@ struct ChainRows {
   float* dout_dbg; float* dact_dbg; long long rsDbg;   // d(mu|log_std) [B][2A] (also the head weight-gradient operand), d(action) [B][A]
 };
 
+constexpr int CH_DBG_SLOTS = 64;
 struct ChainArgs {
   int njobs;
   long long rsP;
+  long long* dbg;                          // optional clock64() timeline of CTA (0,0,0), CH_DBG_SLOTS entries (B200SAC_CHAIN_DBG=1)
   ChainJob job[CH_MAXJOBS];
   PolicyHeadArgs pol;
   ChainRows rw;
@@ -134,7 +136,12 @@ B200_D void chain_issue_chunk(float* __restrict__ buf, const float* __restrict__
 
 template <bool FWD>
 __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainArgs A, StepConst K) {
+  long long* const dbg = (A.dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0) ? A.dbg : nullptr;
+  int dbg_i = 0;
+#define CH_STAMP() do { if (dbg != nullptr && dbg_i < CH_DBG_SLOTS) dbg[dbg_i++] = clock64(); } while (0)
+  CH_STAMP();                              // 0: kernel entry
   KStamp ks_;
+  CH_STAMP();                              // 1: predecessor complete (griddepcontrol.wait)
   extern __shared__ __align__(16) float sm[];
   const ChainJob& J = A.job[blockIdx.y];
   const int rep = blockIdx.z;
@@ -192,6 +199,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   };
   issue_next();
   issue_next();
+  CH_STAMP();                              // 2: prologue loads issued
 
   // ---- backward jobs: d(head output) of the CTA's rows, then dY_last = (dout Wh) * [h_last > 0] -------------------------
   if constexpr (!FWD) {
@@ -292,6 +300,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     __syncthreads();                               // In (and the staged action columns) visible to every warp
   }
 
+  CH_STAMP();                              // 3: backward prologue done (forward: == 2)
   // ---- the dense stages ------------------------------------------------------------------------------------------------
   int g = 0;
   for (int s = 0; s < J.nstages; ++s) {
@@ -315,6 +324,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     for (int k0 = 0; k0 < K4; k0 += CH_KC, ++g) {
       cp_async_wait<1>();
       __syncthreads();                  // chunk g is visible; everyone is done with chunk g-1 (its buffer is refilled next)
+      CH_STAMP();                       // per chunk: data landed + barrier passed
       issue_next();
       const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
       const float* __restrict__ Wc = wst + (g % CH_NSTAGE) * CH_CHUNK_FLOATS;
@@ -328,13 +338,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           float4 wv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) wv[i] = *reinterpret_cast<const float4*>(Wc + (lane + 32 * i) * CH_WPF + 4 * w);
+          // k component outermost: 64 independent FMAs between two uses of an accumulator (per accumulator the
+          // summation order is still k ascending)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int q = 0; q < 4; ++q) {
 #pragma unroll
-            for (int m = 0; m < CH_ROWS; ++m) {
-              float t = acc[m][i];
-              t = fmaf(a[m].x, wv[i].x, t); t = fmaf(a[m].y, wv[i].y, t); t = fmaf(a[m].z, wv[i].z, t); t = fmaf(a[m].w, wv[i].w, t);
-              acc[m][i] = t;
+            for (int i = 0; i < 8; ++i) {
+              const float wq = q == 0 ? wv[i].x : (q == 1 ? wv[i].y : (q == 2 ? wv[i].z : wv[i].w));
+#pragma unroll
+              for (int m = 0; m < CH_ROWS; ++m) {
+                const float av = q == 0 ? a[m].x : (q == 1 ? a[m].y : (q == 2 ? a[m].z : a[m].w));
+                acc[m][i] = fmaf(av, wq, acc[m][i]);
+              }
             }
           }
         } else {
@@ -359,6 +374,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         }
       }
     }
+    CH_STAMP();                         // per stage: last chunk computed
     // ---- stage epilogue: the 8 partial tiles -> fixed-order sum -> bias+ReLU | ReLU' gate -> next input -----------------
     {
       float* __restrict__ pw = part + w * (CH_ROWS * CH_MAXW);
@@ -393,6 +409,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       for (int m = 0; m < CH_ROWS; ++m) Out[m * CH_INP + tid] = 0.f;
     }
     __syncthreads();
+    CH_STAMP();                         // per stage: epilogue done
     float* t = In; In = Out; Out = t;
   }
   cp_async_wait<0>();
@@ -444,6 +461,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         if (j < J.nact) o[j] = acc[j];
     }
   }
+  CH_STAMP();                              // last: head / tail done
+  if (dbg != nullptr) dbg[CH_DBG_SLOTS - 1] = dbg_i;
+#undef CH_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------------------------------

@@ -167,7 +167,8 @@ class _BaseLearner:
     def act_batch(self, states, stochastic=True):
         """Actor.get_action (LL/model.py:67-82) for a batch of environments at once with the learner's current actor:
         states [n][obs_dim] (n <= 2*batch_size) -> actions [n][action_dim] on the CPU."""
-        return self.core.act(torch.as_tensor(states), stochastic=stochastic)
+        # the LunarLander actor's deterministic action is k*mu, every other family's k*tanh(mu) (LL/model.py:78-80, VS/model.py:78-80)
+        return self.core.act(torch.as_tensor(states), stochastic=stochastic, no_tanh=(self.family == "LL"))
 
     # ---- parameter publication (LL/learner.py:272-276; consumed by Player.pull_parameters, player.py:75-85) ----
     _published = ("actor",)
@@ -255,9 +256,9 @@ class _BaseLearner:
         m, v = self.core.get_named(_lib.ADAM_M), self.core.get_named(_lib.ADAM_V)
         state = {n_frozen_first + i: {"step": torch.tensor(float(step)), "exp_avg": m[n], "exp_avg_sq": v[n]}
                  for i, n in enumerate(canon_names)} if step > 0 else {}
-        group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False,
-                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
-                 "params": list(range(n_frozen_first + len(canon_names)))}
+        # the param-group keys are whatever this torch's Adam writes (they changed across releases); values = Adam defaults
+        group = dict(torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=lr).state_dict()["param_groups"][0])
+        group["params"] = list(range(n_frozen_first + len(canon_names)))
         return {"state": state, "param_groups": [group]}
 
     def _canon(self, nets):

@@ -177,8 +177,12 @@ int b200sac_soft_update(b200sac_t* h, double tau, void* stream);
 /* Batched policy inference for n <= 2*batch observation rows obs[n][obs_dim] (obs_dim = state_dim + num_tasks), host or
  * device memory: actions[n][act_dim] = k * tanh(mu + std * eps) -- Actor.get_action
  * (LunarLander_Distributed_SAC/src/model.py:67-82, MT10_Distributed_MTSAC/src/model.py:58-73) vectorised over environments.
- * eps (nullable, [n][act_dim]) injects the noise; eps == NULL: stochastic != 0 draws fresh Philox noise, stochastic == 0
- * returns the deterministic action k * tanh(mu).  Not available for CARE handles.  Synchronises the stream. */
+ * CARE handles (n <= batch): the rows are first encoded like the player does it, z = context_encoder(mtobs) then the
+ * actor's state encoder -- the hard copy of the critic's -- (MT10_Distributed_CARE/src/player.py:199-209, model.py:90-114).
+ * eps (nullable, [n][act_dim]) injects the noise; eps == NULL: stochastic = 1 draws fresh Philox noise; stochastic = 0
+ * returns the deterministic action k * tanh(mu) of the VSAC / MTSAC / CARE actors (MT1_Distributed_VSAC/src/model.py:63,80);
+ * stochastic = -1 returns k * mu, no squashing, which is what the LunarLander actor's get_action(stochastic=False) does
+ * (LunarLander_Distributed_SAC/src/model.py:67-82).  Synchronises the stream. */
 int b200sac_act(b200sac_t* h, int32_t replica, int32_t n, const float* obs, const float* eps, int32_t stochastic,
                 float* actions_out, void* stream);
 
