@@ -544,7 +544,7 @@ def main():
     ap.add_argument("--replicas", type=int, default=1, help="independent learners co-scheduled per GPU")
     ap.add_argument("--ring", type=int, default=DEVICE_RING, help="transitions in the device replay ring (per learner)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed update() calls for the e2e leg (default: max(steps, 1000) capped at 2000)")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU time budget of the headline cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of the headline cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--precision", type=int, default=-1,
                     help="0 = fp32 FFMA (layer-chained kernels for LL-class shapes), 1 = 3xTF32 tcgen05 GEMMs, -1 = probe both, headline = faster")
@@ -564,6 +564,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     b = Bench(args)
+    t_mark = [time.perf_counter()]
+
+    def log(what):
+        if b.rank == 0:
+            now = time.perf_counter()
+            print(f"[bench] {what}: {now - t_mark[0]:.1f} s", file=sys.stderr, flush=True)
+            t_mark[0] = now
     W = max(args.warmup, 3)
     K = args.steps
     R = args.replicas
@@ -581,6 +588,7 @@ def main():
             leg = b.gpu_leg(wl, R, pr, 100, 16, 600, 1 << 16)
             by_precision["probe"]["fp32" if pr == 0 else "tc3xtf32"] = leg["value"]
         args.precision = 0 if by_precision["probe"]["fp32"] >= by_precision["probe"]["tc3xtf32"] else 1
+    log("back-end probe")
     head = b.gpu_leg(wl, R, args.precision, K, W, 8000 if wl == "LL" else 2000, args.ring, detail=True, clocks=clocks, bcast=True)
     clk = clocks.stop()
     by_precision["final"]["fp32" if args.precision == 0 else "tc3xtf32"] = head["value"]
@@ -597,10 +605,12 @@ def main():
             traffic_src = "profiles/r2_traffic.json: " + tj["source"]
     roofline = roofline_block(b, head, wl, R, traffic, traffic_src)
 
+    log("headline device-resident leg")
     # ---- e2e leg ---------------------------------------------------------------------------------------------------
     Ke = args.e2e_steps or min(max(K, 1000), 2000)
     e2e = b.e2e_leg(wl, args.precision, Ke, W, with_publication=True)
 
+    log("e2e leg")
     # ---- the other BASELINE configs, config 4's placement, learners-per-GPU sweep -------------------------------------
     configs, sweep = {}, {}
     if args.configs == "auto":
@@ -612,6 +622,7 @@ def main():
                            "roofline": {"hbm_frac": leg["hbm_frac"], "tensor_frac": leg["tensor_frac"],
                                         "algorithmic_bytes_per_step": WORK[w2]["mbytes"] * 1e6, "algorithmic_flop_per_step": WORK[w2]["gflop"] * 1e9},
                            "gemm_backend": leg["gemm_backend"], "launches_per_step": leg["launches_per_step"], "timing": leg["timing"]["window_ms"]}
+            log(f"config leg {w2}")
         # BASELINE config 4: 10 independent MTSAC learners over the GPUs of this run (8 GPUs: 2,2,1,1,1,1,1,1)
         place = shard_replicas(10, world)
         mine = len(place[b.rank])
@@ -621,19 +632,23 @@ def main():
                                        "ms_per_step": leg["ms_per_step"], "n_gpus": world, "learners": leg["learners"],
                                        "roofline": {"hbm_frac_of_rank0": leg["hbm_frac"], "tensor_frac_of_rank0": leg["tensor_frac"]},
                                        "timing": leg["timing"]["window_ms"]}
+        log("config 4 placement")
         for r_extra in [int(x) for x in args.sweep.split(",") if x]:
             sweep[str(r_extra)] = {}
             for pr in (0, 1):
                 leg = b.gpu_leg(wl, r_extra, pr, 50, 16, 200, max(1 << 14, (1 << 19) // r_extra), seed0=77)
                 sweep[str(r_extra)]["fp32" if pr == 0 else "tc3xtf32"] = {"value": leg["value"], "hbm_frac": leg["hbm_frac"]}
 
+    log("learners-per-GPU sweep")
     cpu = None
     if b.rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_block(wl, args.cpu_seconds)
+        log("cpu_baseline headline")
         if args.configs == "auto":
             for w2 in configs:
                 if w2 in WORK:
-                    configs[w2]["cpu_baseline"] = cpu_baseline_block(w2, 5.0)
+                    configs[w2]["cpu_baseline"] = cpu_baseline_block(w2, 4.0)
+                    log(f"cpu_baseline {w2}")
 
     if b.rank == 0:
         line = {

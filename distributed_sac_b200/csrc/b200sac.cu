@@ -269,7 +269,7 @@ struct b200sac {
   float* slab = nullptr;
   size_t slab_floats = 0;
   Buf XA, XQ, XT, XP, r, d, tid, eps, pout, psave, act_out, logp, logstd, y, q, dq, lq, dqa, la, qmin, dxP,
-      dout_dbg, dact_dbg, qt, qp;
+      dout_dbg, dact_dbg, qt, qp, alpha;
   bool stamping = false;          // true while b200sac_graph_timeline runs on this handle (one unforked step per graph)
   bool fused = false;             // layer-chained plan (chain.cuh): every hidden width <= 256, exact-fp32 mode, no CARE
   PolicyHeadArgs pol;             // the policy head's arguments (also used by b200sac_act)
@@ -315,6 +315,7 @@ struct b200sac {
   float* pub_h = nullptr;         // pinned host copy handed to the caller
   int64_t pub_cap = 0, pub_n = 0;
   bool pub_pending = false;
+  CUtensorMap* d_cmaps = nullptr; // layer-chained plan: 2-D tensor maps of the forward weight matrices, [R][maps per learner]
   long long* chain_dbg = nullptr; // B200SAC_CHAIN_DBG=1: [plan launches][CH_DBG_SLOTS] clock64 timelines of the chain kernels
   float* split_d = nullptr;       // b200sac_step: handle-owned copy of the caller's minibatch arrays (stable graph pointers)
   float* loss_h = nullptr;        // mapped pinned loss ring [kLossSlots][R][4], written by the tail kernels
@@ -370,6 +371,7 @@ static int destroy_impl(b200sac* h) {
   cudaFree(h->pub_d);
   cudaFree(h->split_d);
   cudaFree(h->chain_dbg);
+  cudaFree(h->d_cmaps);
   if (h->pub_h) cudaFreeHost(h->pub_h);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->fork) cudaStreamDestroy(h->fork);
@@ -467,7 +469,7 @@ static bool fused_eligible(const b200sac_cfg& c) {
   return true;
 }
 
-static int build_plan_fused(b200sac* h, const std::function<void(int)>& adam) {
+static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& adam) {
   const b200sac_cfg& c = h->cfg;
   const Layout& L = h->L;
   const int B = c.batch, R = h->R, A = c.act_dim;
@@ -482,17 +484,21 @@ static int build_plan_fused(b200sac* h, const std::function<void(int)>& adam) {
   rw.r = h->r.p; rw.d = h->d.p; rw.tid = (const int*)h->tid.p; rw.rsR = h->r.rs;
   rw.logp = h->logp.p; rw.rsLogp = h->logp.rs;
   rw.log_alpha = W(L.off_alpha);
+  rw.alpha = h->alpha.p; rw.rsAlpha = h->alpha.rs;
   rw.qt = h->qt.p; rw.q = h->q.p; rw.qp = h->qp.p;
   rw.y = h->y.p; rw.dq = h->dq.p; rw.lq = h->lq.p; rw.dqa = h->dqa.p; rw.la = h->la.p; rw.qmin = h->qmin.p; rw.rsY = h->y.rs;
   rw.dxP = h->dxP.p; rw.rsDxNet = (long long)B * h->K.ldx; rw.rsDxRep = h->dxP.rs; rw.lddx = h->K.ldx;
   rw.psave = h->psave.p + (long long)B * A * kSaveW; rw.rsSave = h->psave.rs;
   rw.dout_dbg = h->dout_dbg.p; rw.dact_dbg = h->dact_dbg.p; rw.rsDbg = h->dout_dbg.rs;
 
-  auto new_chain = [&](const char* label) {
+  struct FMap { int64_t off; int K, N, ld; };
+  std::vector<FMap> fmaps;                 // forward weight matrices that need a tensor map (one per chained forward stage)
+  auto new_chain = [&](const char* label, int early_weights = 1) {
     Launch l;
     l.kind = L_CHAIN;
     l.label = label;
     memset(&l.chain, 0, sizeof(l.chain));
+    l.chain.early_weights = (early_weights && getenv("B200SAC_NO_EARLY_WEIGHTS") == nullptr) ? 1 : 0;
     l.chain.rsP = rsP;
     l.chain.pol = h->pol;
     l.chain.rw = rw;
@@ -506,9 +512,15 @@ static int build_plan_fused(b200sac* h, const std::function<void(int)>& adam) {
   }
   auto finish_chain = [&](Launch& l) {
     if (h->chain_dbg && h->plan.size() < 16) l.chain.dbg = h->chain_dbg + h->plan.size() * CH_DBG_SLOTS;
+    // rows per CTA: every CTA streams the whole weight matrices whatever its row count, so fewer rows per CTA only pay
+    // while the launch still fits the GPU: 8 rows when that already gives >= 96 CTAs, else 4 (twice the CTAs, half the math each)
+    long long total = 0;
+    for (int j = 0; j < l.chain.njobs; ++j) total += (l.chain.job[j].rows + 7) / 8;
+    l.bn = (total * R >= 96) ? 8 : 4;             // (bn is reused as "rows per CTA" for chain launches)
+    if (const char* e = getenv("B200SAC_CHAIN_ROWS")) l.bn = atoi(e) == 4 ? 4 : 8;
     int maxb = 1;
     for (int j = 0; j < l.chain.njobs; ++j) {
-      const int nb = (l.chain.job[j].rows + CH_ROWS - 1) / CH_ROWS;
+      const int nb = (l.chain.job[j].rows + l.bn - 1) / l.bn;
       maxb = nb > maxb ? nb : maxb;
     }
     l.grid = dim3(maxb, l.chain.njobs, R);
@@ -524,6 +536,8 @@ static int build_plan_fused(b200sac* h, const std::function<void(int)>& adam) {
       const LayerOff& lo = net[l];
       ChainStage& S = J.st[l];
       S.W = W(lo.w); S.bias = W(lo.b); S.ldw = lo.ld; S.K = lo.in; S.N = lo.out;
+      S.tm_idx = (int)fmaps.size();
+      fmaps.push_back(FMap{lo.w, lo.in, lo.out, lo.ld});
       if (store) { S.out = (*store)[l].p + (long long)net_idx * rows_per_net * lo.out; S.rsOut = (*store)[l].rs; S.ldo = lo.out; }
     }
     const LayerOff& hd = net[nh];
@@ -629,11 +643,12 @@ static int build_plan_fused(b200sac* h, const std::function<void(int)>& adam) {
     for (int net = 0; net < 2; ++net)
       nets.push_back(WNet{&L.q[net], Lc, &h->dhQ, &h->hQ, 0, h->XQ.p, h->XQ.rs, h->K.ldx, h->dq.p + (long long)net * B, h->dq.rs, 1, net});
     if (int rc = wgrad_launch(nets, "wgrad{q1,q2}")) return rc;
-    adam(0);
+    adam(0, 0);
   }
   // ---- D: actor pass through the updated critics ------------------------------------------------------------------------
   {
-    Launch l = new_chain("chain_fwd{q1,q2}(s,a~)");
+    // (the launch right before this one is the critic Adam: no weight request before the dependency wait)
+    Launch l = new_chain("chain_fwd{q1,q2}(s,a~)", 0);
     l.chain.njobs = 2;
     for (int net = 0; net < 2; ++net) {
       ChainJob& J = l.chain.job[net];
@@ -652,6 +667,9 @@ static int build_plan_fused(b200sac* h, const std::function<void(int)>& adam) {
       J.dx = h->dxP.p + (long long)net * B * h->K.ldx; J.rsDx = h->dxP.rs; J.lddx = h->K.ldx;
     }
     finish_chain(l2);
+    // actor loss / entropy / temperature gradient + its Adam step need only what D produced (the step's alpha is the
+    // snapshot taken at ingest): they run on the fork stream beside the policy backward instead of trailing the actor Adam
+    adam(1, 2);
   }
   // ---- E: policy backward, weight gradients, Adam + temperature ------------------------------------------------------------
   {
@@ -663,11 +681,33 @@ static int build_plan_fused(b200sac* h, const std::function<void(int)>& adam) {
     nets.push_back(WNet{&L.actor, La, &h->dhA, &h->hA, (long long)B, h->XA.p + (long long)B * h->K.ldxa, h->XA.rs, h->K.ldxa,
                         h->dout_dbg.p, h->dout_dbg.rs, 2 * A, 0});
     if (int rc = wgrad_launch(nets, "wgrad{actor}")) return rc;
-    adam(1);
+    adam(1, 1);
   }
   (void)Hc; (void)Ha;
-  CU(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
+  {  // tensor maps [R][n]: W [N][K] row-major (pitch ld), box {32 k, N rows}, SWIZZLE_128B, OOB k zero-filled
+    const int n = (int)fmaps.size();
+    std::vector<CUtensorMap> maps((size_t)R * n);
+    for (int rep = 0; rep < R; ++rep)
+      for (int i = 0; i < n; ++i)
+        if (int rc = make_map(&maps[(size_t)rep * n + i], h->params + (long long)rep * rsP + fmaps[i].off, fmaps[i].K, fmaps[i].N,
+                              fmaps[i].ld, fmaps[i].N))
+          return rc;
+    CU(cudaMalloc(&h->d_cmaps, maps.size() * sizeof(CUtensorMap)));
+    CU(cudaMemcpy(h->d_cmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    for (auto& l : h->plan)
+      if (l.kind == L_CHAIN)
+        for (int j = 0; j < l.chain.njobs; ++j)
+          if (l.chain.job[j].kind == CJ_FWD)
+            for (int st = 0; st < l.chain.job[j].nstages; ++st) {
+              ChainStage& S = l.chain.job[j].st[st];
+              S.tm = h->d_cmaps + S.tm_idx;
+              S.rsTm = n;
+            }
+  }
+  CU(cudaFuncSetAttribute(chain_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(chain_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(chain_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(chain_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
   CU(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES));
   return 0;
 }
@@ -936,7 +976,8 @@ static int build_plan(b200sac* h) {
     P.logstd_sum = h->logstd.p;
     P.cnt = h->cnt;
   }
-  auto adam = [&](int which) {
+  // mode 0: parameter update + the tail job (last CTA); 1: parameter update only; 2: the tail job alone, on the fork stream
+  auto adam = [&](int which, int mode) {
     Launch l;
     l.kind = L_ADAM;
     AdamArgs& P = l.ad;
@@ -953,6 +994,7 @@ static int build_plan(b200sac* h) {
     P.lr = which == 0 ? c.lr_critic : (which == 1 ? c.lr_actor : c.lr_ctx);
     P.cnt = h->cnt;
     P.tail = which == 0 ? TAIL_CRITIC_LOSS : (which == 1 ? TAIL_ALPHA_AND_LOSSES : TAIL_NONE);
+    if (mode == 1) P.tail = TAIL_NONE;
     P.lq = h->lq.p; P.la = h->la.p; P.rsY = h->y.rs;
     P.logp_cur = h->logp.p + B; P.logstd_sum = h->logstd.p + B; P.rsLogp = h->logp.rs;
     P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
@@ -965,6 +1007,7 @@ static int build_plan(b200sac* h) {
     l.grid = dim3(nb + (P.tail != TAIL_NONE ? 1 : 0), R);
     l.block = dim3(256);
     l.join = true;                 // every gradient of the slice must have landed, including the forked weight gradients
+    if (mode == 2) { l.grid = dim3(1, R); l.join = false; l.branch = 1; }
     h->plan.push_back(l);
   };
   if (h->fused) {
@@ -1206,7 +1249,7 @@ static int build_plan(b200sac* h) {
       h->plan.push_back(l2);
     }
   }
-  adam(0);
+  adam(0, 0);
   if (c.care) {          // encoded states of s with the UPDATED critic encoder for the actor pass (learner.py:336-341)
     care_tables({2});
     care_mixture_fwd({std::make_tuple(2, B, B)});
@@ -1270,8 +1313,8 @@ static int build_plan(b200sac* h) {
       gemm_launch(ps);
     }
   }
-  adam(1);
-  if (c.care == 2) adam(2);        // update(): context_encoder_optimizer.step() (learner.py:399), gradients from the critic loss
+  adam(1, 0);
+  if (c.care == 2) adam(2, 0);        // update(): context_encoder_optimizer.step() (learner.py:399), gradients from the critic loss
   }   // generic (per-layer) plan
 
   if (plan_rc) return plan_rc;
@@ -1381,8 +1424,14 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
       case L_CHAIN: {
         ChainArgs a = l.chain;
         a.pol.use_eps_buf = use_eps_buf ? 1 : 0;
-        if (a.job[0].kind == CJ_FWD) launch_k(chain_kernel<true>, l.grid, l.block, l.smem, s, a, h->K);
-        else launch_k(chain_kernel<false>, l.grid, l.block, l.smem, s, a, h->K);
+        const bool f = a.job[0].kind == CJ_FWD;
+        if (l.bn == 8) {
+          if (f) launch_k(chain_kernel<true, 8>, l.grid, l.block, l.smem, s, a, h->K);
+          else launch_k(chain_kernel<false, 8>, l.grid, l.block, l.smem, s, a, h->K);
+        } else {
+          if (f) launch_k(chain_kernel<true, 4>, l.grid, l.block, l.smem, s, a, h->K);
+          else launch_k(chain_kernel<false, 4>, l.grid, l.block, l.smem, s, a, h->K);
+        }
         break;
       }
       case L_WGRAD:
@@ -1502,6 +1551,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   h->dqa = carve(cur, (size_t)2 * h->y.rs, R);
   h->qt = carve(cur, (size_t)2 * h->y.rs, R);
   h->qp = carve(cur, (size_t)2 * h->y.rs, R);
+  h->alpha = carve(cur, 64, R);
   h->dxP = carve(cur, (size_t)2 * B * ldx, R);
   h->dout_dbg = carve(cur, (size_t)B * 2 * A, R);
   h->dact_dbg = carve(cur, (size_t)B * 2 * A, R);
@@ -1549,7 +1599,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   CUH(cudaMalloc(&h->slab, cur * sizeof(float)));
   CUH(cudaMemset(h->slab, 0, cur * sizeof(float)));
   for (Buf* b : {&h->XA, &h->XQ, &h->XT, &h->XP, &h->r, &h->d, &h->tid, &h->eps, &h->pout, &h->psave, &h->act_out, &h->logp,
-                 &h->logstd, &h->y, &h->lq, &h->la, &h->qmin, &h->q, &h->dq, &h->dqa, &h->dxP, &h->dout_dbg, &h->dact_dbg, &h->qt, &h->qp})
+                 &h->logstd, &h->y, &h->lq, &h->la, &h->qmin, &h->q, &h->dq, &h->dqa, &h->dxP, &h->dout_dbg, &h->dact_dbg, &h->qt, &h->qp, &h->alpha})
     rebase(*b, h->slab);
   for (auto* v : {&h->hA, &h->dhA, &h->hQ, &h->hT, &h->hP, &h->dhQ})
     for (auto& b : *v) rebase(b, h->slab);
@@ -1570,6 +1620,7 @@ extern "C" int b200sac_create(const b200sac_cfg* cfg, int32_t device, uint64_t s
   O.tid = (int*)h->tid.p; O.cnt = h->cnt;
   O.rsXA = h->XA.rs; O.rsXQ = h->XQ.rs; O.rsR = h->r.rs; O.rsEps = h->eps.rs;
   O.XS = cfg->care ? h->XS.p : nullptr; O.rsXS = cfg->care ? h->XS.rs : 0;
+  O.log_alpha = h->params + L.off_alpha; O.rsP = L.arena; O.alpha = h->alpha.p; O.rsAlpha = h->alpha.rs;
   if (h->d.rs != h->r.rs || h->tid.rs != h->r.rs || h->lq.rs != h->y.rs || h->la.rs != h->y.rs || h->qmin.rs != h->y.rs ||
       h->logstd.rs != h->logp.rs) {
     destroy_impl(h);
@@ -2078,7 +2129,10 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
     case L_HEADBWD: return (l.hb.policy_mode || l.hb.NO > 1) ? "head_bwd(policy)" : "head_bwd(q)";
     case L_CHAIN:
     case L_WGRAD: return l.label ? l.label : "chain";
-    case L_ADAM: return l.ad.which == 0 ? "adam_critic+polyak" : (l.ad.which == 1 ? "adam_actor+alpha" : "adam_context_encoder");
+    case L_ADAM:
+      if (l.ad.which == 1 && l.branch == 1) return "alpha+losses(forked)";
+      if (l.ad.which == 1 && l.ad.tail == TAIL_NONE) return "adam_actor";
+      return l.ad.which == 0 ? "adam_critic+polyak" : (l.ad.which == 1 ? "adam_actor+alpha" : "adam_context_encoder");
   }
   return "?";
 }

@@ -14,21 +14,25 @@
 //             policy          closed-form backward of rsample/tanh/log-prob (oracle/sac_manual.py)   model.py:50-60
 //
 // Rows are independent, so nothing is exchanged between CTAs and there is no barrier wider than the CTA.  Every CTA
-// streams the full weight matrices of its network through a 3-stage cp.async pipeline of [<=256 n][32 k] chunks (36 KB),
-// which runs ahead across layer boundaries (weights do not depend on activations); 128 CTAs x 256 KB per 256x256 layer
-// = 32 MB of L2 reads, ~2.7 us at the measured L2 rate -- the bound of this design; the 8 x 256 x 256 FMAs of a CTA fit
-// under it.  Inside a chunk the 8 warps split K (warp w takes k = 4w..4w+3 of the 32), each lane holds an 8-row x
+// streams the full weight matrices of its network through a 3-stage TMA pipeline of 32-k chunks (32 KB each, landing on
+// mbarriers): forward chunks [<=256 n][32 k] come through a 2-D tensor map with the 128-byte swizzle straight from the
+// nn.Linear-layout matrix (cp.async.bulk.tensor.2d, out-of-range k zero-filled), backward chunks are 32 consecutive rows of
+// the same matrix = one contiguous cp.async.bulk.  One elected thread issues a chunk; nobody's registers or LSU slots are
+// spent on the copy (the first version staged with per-thread cp.async: measured ~1000 cycles of issue per chunk on top
+// of ~1000 cycles of math).  The pipeline runs ahead across layer boundaries (weights do not depend on activations);
+// 128 CTAs x 256 KB per 256x256 layer = 32 MB of L2 reads, ~2.7 us at the measured L2 rate -- the bound of this design.  Inside a chunk the 8 warps split K (warp w takes k = 4w..4w+3 of the 32), each lane holds an 8-row x
 // 8-column accumulator tile (40 shared-memory wavefronts per 256 FFMA), and the eight partial tiles are added in warp
 // order in shared memory: a fixed summation order, bit-reproducible run to run and replica to replica.
 //
 // Weight gradients (the reduction over the batch) are a separate kernel, wgrad_kernel below: 32x32 output tiles, the
 // 8 warps split the batch rows, lanes hold 4x8 accumulators, fixed-order reduction.
 #pragma once
+#include "gemm_tc.cuh"        // mbarrier / TMA wrappers
 #include "sac_kernels.cuh"
 
 namespace bsac {
 
-constexpr int CH_ROWS = 8;                 // rows per CTA
+constexpr int CH_ROWS = 8;                 // rows per CTA (template parameter ROWS = 8 or 4; buffers are sized for 8)
 constexpr int CH_MAXW = 256;               // widest layer / widest reduction
 constexpr int CH_KC = 32;                  // k rows per weight chunk
 constexpr int CH_NSTAGE = 3;               // weight chunks in flight
@@ -36,8 +40,7 @@ constexpr int CH_MAXL = 8;                 // dense stages per job
 constexpr int CH_THREADS = 256;
 constexpr int CH_WARPS = CH_THREADS / 32;
 constexpr int CH_INP = CH_MAXW + 4;        // row pitch of the activation buffers
-constexpr int CH_WPF = CH_KC + 4;          // row pitch of a forward chunk [n][36]
-constexpr int CH_CHUNK_FLOATS = CH_MAXW * CH_WPF;                    // 9216 (>= 32 * 256 of a backward chunk)
+constexpr int CH_CHUNK_FLOATS = CH_MAXW * CH_KC;                     // 8192 floats = 32 KB: [256 n][32 k] swizzled | [32 k][256 n]
 constexpr int CH_MAXJOBS = 3;
 // shared memory (floats): two activation buffers, head weights [16][260], d(head out) [8][16], action columns of W0
 // [256][8], partial tiles [8 warps][8 rows][256], weight stages
@@ -46,8 +49,9 @@ constexpr int CH_SM_HEADW = kMaxHeadOut * CH_INP;
 constexpr int CH_SM_SD = CH_ROWS * kMaxHeadOut;
 constexpr int CH_SM_W0A = CH_MAXW * kMaxAct;
 constexpr int CH_SM_PART = CH_WARPS * CH_ROWS * CH_MAXW;
-constexpr int CH_SMEM_FLOATS = 2 * CH_SM_ACT + CH_SM_HEADW + CH_SM_SD + CH_SM_W0A + CH_SM_PART + CH_NSTAGE * CH_CHUNK_FLOATS;
-constexpr size_t CH_SMEM_BYTES = (size_t)CH_SMEM_FLOATS * sizeof(float);
+constexpr int CH_SM_BARS = 16;             // mbarriers (64 B)
+constexpr int CH_SMEM_FLOATS = CH_NSTAGE * CH_CHUNK_FLOATS + CH_SM_BARS + 2 * CH_SM_ACT + CH_SM_HEADW + CH_SM_SD + CH_SM_W0A + CH_SM_PART;
+constexpr size_t CH_SMEM_BYTES = (size_t)CH_SMEM_FLOATS * sizeof(float) + 1024;     // + slack to align the stage buffers to 1 KB
 
 enum { CJ_FWD = 0, CJ_BWD_CRITIC = 1, CJ_BWD_ACTORQ = 2, CJ_BWD_POLICY = 3 };
 enum { CH_HEAD_NONE = 0, CH_HEAD_SCALAR = 1, CH_HEAD_POLICY = 2, CH_TAIL_DACTION = 3 };
@@ -58,6 +62,8 @@ struct ChainStage {
   const float* bias;       // forward only (arena)
   const float* mask;       // backward only: the forward activation [rows][N] whose > 0 gates the result (row 0 of the job)
   float* out;              // optional global store of the stage output (row 0 of the job)
+  const CUtensorMap* tm;   // forward only: 2-D map of W [N][K] (box 32 k x N rows, SWIZZLE_128B), replica 0; replica r at tm + r * rsTm
+  int tm_idx, rsTm;        // (host: index into the handle's map table until the table is uploaded)
   long long rsMask, rsOut;
   int ldw, ldmask, ldo;
   int K, N;                // reduction width, output width
@@ -81,6 +87,7 @@ struct ChainRows {
   const float* r; const float* d; const int* tid; long long rsR;
   const float* logp; long long rsLogp;                 // [0,B) next-state half, [B,2B) current-state half
   const float* log_alpha;                              // arena
+  const float* alpha; long long rsAlpha;               // exp(log_alpha[t]) of this step, written once by the ingest kernel
   const float* qt; const float* q; const float* qp;    // [2][B] target / local (s,a) / local (s,a~) head outputs, replica stride 2*rsY
   float* y; float* dq; float* lq; float* dqa; float* la; float* qmin; long long rsY;   // dq, dqa: [2][B], replica stride 2*rsY
   const float* dxP; long long rsDxNet, rsDxRep; int lddx;   // critic input gradients [2][B][ldx] (policy job)
@@ -91,6 +98,8 @@ struct ChainRows {
 constexpr int CH_DBG_SLOTS = 64;
 struct ChainArgs {
   int njobs;
+  int early_weights;                       // 1: the weight matrices were not written by the launch right before this one, so the
+                                           // first chunks are requested BEFORE griddepcontrol.wait (they land while the predecessor drains)
   long long rsP;
   long long* dbg;                          // optional clock64() timeline of CTA (0,0,0), CH_DBG_SLOTS entries (B200SAC_CHAIN_DBG=1)
   ChainJob job[CH_MAXJOBS];
@@ -105,61 +114,71 @@ B200_D void cp_async16(float* smem_dst, const float* gsrc) {
 B200_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> B200_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One weight chunk into a stage buffer.  forward: [N n][kc k] gathered from W[n][k0..k0+kc) into rows of pitch 36;
-// backward: rows k0..k0+kc of W[k][N] (contiguous N floats each) into rows of pitch N.
-B200_D void chain_issue_chunk(float* __restrict__ buf, const float* __restrict__ W, int ldw, int N, int k0, int kc, bool bwd, int tid) {
-  // pieces of 16 B; the common shapes (32-k forward chunks, 256-wide backward rows) index without a division
-  if (!bwd) {
-    const int q4 = kc >> 2, total = N * q4;
-    if (q4 == 8) {
-      const int q = tid & 7;
-      for (int n = tid >> 3; n < N; n += CH_THREADS / 8) cp_async16(buf + n * CH_WPF + 4 * q, W + (long long)n * ldw + k0 + 4 * q);
-    } else {
-      for (int e = tid; e < total; e += CH_THREADS) {
-        const int n = e / q4, q = e - n * q4;
-        cp_async16(buf + n * CH_WPF + 4 * q, W + (long long)n * ldw + k0 + 4 * q);
-      }
-    }
-  } else {
-    const int q4 = N >> 2, total = kc * q4;
-    if (q4 == 64) {
-      const int q = tid & 63;
-      for (int kk = tid >> 6; kk < kc; kk += CH_THREADS / 64) cp_async16(buf + kk * N + 4 * q, W + (long long)(k0 + kk) * ldw + 4 * q);
-    } else {
-      for (int e = tid; e < total; e += CH_THREADS) {
-        const int kk = e / q4, q = e - kk * q4;
-        cp_async16(buf + kk * N + 4 * q, W + (long long)(k0 + kk) * ldw + 4 * q);
-      }
-    }
-  }
+B200_D void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <bool FWD>
+template <bool FWD, int ROWS>
 __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainArgs A, StepConst K) {
   long long* const dbg = (A.dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0) ? A.dbg : nullptr;
   int dbg_i = 0;
 #define CH_STAMP() do { if (dbg != nullptr && dbg_i < CH_DBG_SLOTS) dbg[dbg_i++] = clock64(); } while (0)
   CH_STAMP();                              // 0: kernel entry
-  KStamp ks_;
-  CH_STAMP();                              // 1: predecessor complete (griddepcontrol.wait)
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(1024) float sm_raw[];
+  float* sm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));   // SWIZZLE_128B tiles: 1 KB aligned
   const ChainJob& J = A.job[blockIdx.y];
   const int rep = blockIdx.z;
-  const int row0 = blockIdx.x * CH_ROWS;
-  if (row0 >= J.rows) return;
-  const int nrows = (J.rows - row0 < CH_ROWS) ? J.rows - row0 : CH_ROWS;
+  const int row0 = blockIdx.x * ROWS;
+  const bool live = row0 < J.rows;
+  const int nrows = (J.rows - row0 < ROWS) ? J.rows - row0 : ROWS;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const long long po = (long long)rep * A.rsP;
 
-  float* actA = sm;
+  float* wst = sm;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + CH_NSTAGE * CH_CHUNK_FLOATS);
+  float* actA = wst + CH_NSTAGE * CH_CHUNK_FLOATS + CH_SM_BARS;
   float* actB = actA + CH_SM_ACT;
   float* headW = actB + CH_SM_ACT;
   float* sd = headW + CH_SM_HEADW;
   float* w0a = sd + CH_SM_SD;
   float* part = w0a + CH_SM_W0A;
-  float* wst = part + CH_SM_PART;
 
-  constexpr bool fwd = FWD;               // (the host launches the <true> instance for CJ_FWD jobs, <false> for the backward kinds)
+  // ---- weight pipeline: thread 0 issues chunk g into stage g % 3; the chunk lands on bars[g % 3] (phase (g / 3) & 1) -------
+  int is = 0, ic = 0, issued = 0;        // next chunk to issue: stage, chunk within the stage, running count
+  auto issue_next = [&]() {
+    if (tid == 0 && is < J.nstages) {
+      const ChainStage& S = J.st[is];
+      const int K4 = (S.K + 3) & ~3;
+      const int k0 = ic * CH_KC;
+      const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
+      const int slot = issued % CH_NSTAGE;
+      const uint32_t bar = smem_u32(bars + slot), dst = smem_u32(wst + slot * CH_CHUNK_FLOATS);
+      if constexpr (FWD) {
+        mbar_expect_tx(bar, (uint32_t)S.N * CH_KC * 4u);
+        tma_load_2d(dst, S.tm + (long long)rep * S.rsTm, k0, 0, bar);
+      } else {
+        const uint32_t bytes = (uint32_t)kc * (uint32_t)S.N * 4u;
+        mbar_expect_tx(bar, bytes);
+        bulk_load_1d(dst, S.W + po + (long long)k0 * S.ldw, bytes, bar);
+      }
+      ++issued;
+      if (k0 + CH_KC >= K4) { ic = 0; ++is; } else { ++ic; }
+    }
+  };
+  if (tid == 0 && live) {
+    if constexpr (FWD) asm volatile("prefetch.tensormap [%0];" ::"l"(J.st[0].tm + (long long)rep * J.st[0].rsTm) : "memory");
+#pragma unroll
+    for (int i = 0; i < CH_NSTAGE; ++i) mbar_init(smem_u32(bars + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (A.early_weights) { issue_next(); issue_next(); }
+  }
+  KStamp ks_;
+  CH_STAMP();                              // 1: predecessor complete (griddepcontrol.wait)
+  if (!live) return;
+  __syncthreads();                         // barriers initialised
+  if (!A.early_weights) { issue_next(); issue_next(); }
+
   float* In = actA;
   float* Out = actB;
 
@@ -175,30 +194,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   if constexpr (FWD) {
     const float* __restrict__ X = J.X + (long long)rep * J.rsX + (long long)row0 * J.ldx;
     const int k4 = (J.K0 + 3) >> 2;
-    for (int e = tid; e < CH_ROWS * k4; e += CH_THREADS) {
+    for (int e = tid; e < ROWS * k4; e += CH_THREADS) {
       const int m = e / k4, q = e - m * k4;
       if (m < nrows) cp_async16(In + m * CH_INP + 4 * q, X + (long long)m * J.ldx + 4 * q);
       else *reinterpret_cast<float4*>(In + m * CH_INP + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  cp_async_commit();
 
-  // ---- weight pipeline -------------------------------------------------------------------------------------------------
-  int is = 0, ic = 0, issued = 0;        // next chunk to issue: stage, chunk within the stage, running count
-  auto issue_next = [&]() {
-    if (is < J.nstages) {
-      const ChainStage& S = J.st[is];
-      const int K4 = (S.K + 3) & ~3;
-      const int k0 = ic * CH_KC;
-      const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
-      chain_issue_chunk(wst + (issued % CH_NSTAGE) * CH_CHUNK_FLOATS, S.W + po, S.ldw, S.N, k0, kc, !fwd, tid);
-      ++issued;
-      if (k0 + CH_KC >= K4) { ic = 0; ++is; } else { ++ic; }
-    }
-    cp_async_commit();
-  };
-  issue_next();
-  issue_next();
+  cp_async_commit();                       // (the head weights / input rows requested above)
   CH_STAMP();                              // 2: prologue loads issued
 
   // ---- backward jobs: d(head output) of the CTA's rows, then dY_last = (dout Wh) * [h_last > 0] -------------------------
@@ -207,11 +210,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     const int B = K.B, Aa = K.act;
     const int row = row0 + w;                      // warp w owns row w
     // gate activations of this thread's column (issued before anything is waited for)
-    float hv[CH_ROWS];
+    float hv[ROWS];
     {
       const float* __restrict__ hl = J.hlast + (long long)rep * J.rsHlast + (long long)row0 * J.ldh;
 #pragma unroll
-      for (int m = 0; m < CH_ROWS; ++m) hv[m] = (tid < J.Hh && m < nrows) ? hl[(long long)m * J.ldh + tid] : 0.f;
+      for (int m = 0; m < ROWS; ++m) hv[m] = (tid < J.Hh && m < nrows) ? hl[(long long)m * J.ldh + tid] : 0.f;
     }
     if (J.kind == CJ_BWD_ACTORQ && J.nact > 0) {   // action columns of the first-layer weights for the tail
       const float* __restrict__ W0 = J.W0 + po;
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           const float* QT = R.qt + rep * 2 * R.rsY;
           const float* Q = R.q + rep * 2 * R.rsY;
           const float qt1 = QT[row], qt2 = QT[B + row], q1 = Q[row], q2 = Q[B + row];
-          const float alpha = (float)exp((double)(R.log_alpha + po)[t]);
+          const float alpha = (R.alpha + rep * R.rsAlpha)[t];
           const float t1 = K.reward_scale * r;
           const float t2 = K.gamma * (1.f - d);
           const float t3 = fminf(qt1, qt2) - alpha * lp;
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           sd[w * kMaxHeadOut] = g;
           (R.dqa + rep * 2 * R.rsY)[J.net * B + row] = g;
           if (J.net == 0) {
-            const float alpha = (float)exp((double)(R.log_alpha + po)[t]);
+            const float alpha = (R.alpha + rep * R.rsAlpha)[t];
             const float qm = fminf(q1, q2);
             (R.la + rep * R.rsY)[row] = -(qm - alpha * lp);
             (R.qmin + rep * R.rsY)[row] = qm;
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           const float* __restrict__ sv = R.psave + rep * R.rsSave + ((long long)row * Aa + lane) * kSaveW;
           const float* __restrict__ dx0 = R.dxP + rep * R.rsDxRep + (long long)row * R.lddx + K.in_w + lane;
           const float da = dx0[0] + dx0[R.rsDxNet];
-          const float alpha = (float)exp((double)(R.log_alpha + po)[(R.tid + rep * R.rsR)[row]]);
+          const float alpha = (R.alpha + rep * R.rsAlpha)[(R.tid + rep * R.rsR)[row]];
           float dmu, dls;
           policy_dout_point(K, sv, da, alpha, dmu, dls);
           sd[w * kMaxHeadOut + lane] = dmu;
@@ -282,12 +285,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         }
       }
     }
-    cp_async_wait<2>();                            // the head weights (first group) have landed
+    CH_STAMP();                                    // (bwd) per-row scalars -> d(head output) done by warp 0
+    cp_async_wait<0>();                            // the head weights have landed
     __syncthreads();
+    CH_STAMP();                                    // (bwd) head weights landed, every warp's d(head output) visible
     if (tid < J.Hh) {
       float* __restrict__ dyl = J.dylast ? J.dylast + (long long)rep * J.rsDy + (long long)row0 * J.lddy : nullptr;
 #pragma unroll
-      for (int m = 0; m < CH_ROWS; ++m) {
+      for (int m = 0; m < ROWS; ++m) {
         float v = 0.f;
         if (m < nrows) {
           for (int j = 0; j < J.NO; ++j) v = fmaf(sd[m * kMaxHeadOut + j], headW[j * CH_INP + tid], v);
@@ -307,23 +312,26 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     const ChainStage& S = J.st[s];
     const int N = S.N, K4 = (S.K + 3) & ~3;
     // epilogue operands of this thread's column, requested now
-    float ebias = 0.f, emask[CH_ROWS];
+    float ebias = 0.f, emask[ROWS];
     if constexpr (FWD) {
       if (tid < N) ebias = __ldg(S.bias + po + tid);
     } else {
       const float* __restrict__ mk = S.mask + (long long)rep * S.rsMask + (long long)row0 * S.ldmask;
 #pragma unroll
-      for (int m = 0; m < CH_ROWS; ++m) emask[m] = (tid < N && m < nrows) ? mk[(long long)m * S.ldmask + tid] : 0.f;
+      for (int m = 0; m < ROWS; ++m) emask[m] = (tid < N && m < nrows) ? mk[(long long)m * S.ldmask + tid] : 0.f;
     }
-    float acc[CH_ROWS][8];
+    // (a packed-FFMA2 version of the two loops below was measured: same chunk time backward, 30 % slower forward --
+    //  the operand packing costs what the halved FMA count saves -- so the loops stay scalar FFMA)
+    float acc[ROWS][8];
 #pragma unroll
-    for (int m = 0; m < CH_ROWS; ++m)
+    for (int m = 0; m < ROWS; ++m)
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[m][i] = 0.f;
 
     for (int k0 = 0; k0 < K4; k0 += CH_KC, ++g) {
-      cp_async_wait<1>();
-      __syncthreads();                  // chunk g is visible; everyone is done with chunk g-1 (its buffer is refilled next)
+      if (g == 0) cp_async_wait<0>();   // forward: the input rows (this thread's pieces; the barrier below publishes them)
+      mbar_wait(smem_u32(bars + g % CH_NSTAGE), (uint32_t)((g / CH_NSTAGE) & 1));
+      __syncthreads();                  // everyone is done with chunk g-1: its buffer is refilled next
       CH_STAMP();                       // per chunk: data landed + barrier passed
       issue_next();
       const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
@@ -331,13 +339,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       if (4 * w < kc) {
         // every operand of the chunk is requested before the first FMA (no branches in between: the loads of columns
         // >= N read stale shared memory into accumulators nobody reads)
-        float4 a[CH_ROWS];
+        float4 a[ROWS];
 #pragma unroll
-        for (int m = 0; m < CH_ROWS; ++m) a[m] = *reinterpret_cast<const float4*>(In + m * CH_INP + k0 + 4 * w);
+        for (int m = 0; m < ROWS; ++m) a[m] = *reinterpret_cast<const float4*>(In + m * CH_INP + k0 + 4 * w);
         if constexpr (FWD) {
           float4 wv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) wv[i] = *reinterpret_cast<const float4*>(Wc + (lane + 32 * i) * CH_WPF + 4 * w);
+          for (int i = 0; i < 8; ++i) wv[i] = *reinterpret_cast<const float4*>(Wc + (lane + 32 * i) * CH_KC + 4 * (w ^ (lane & 7)));   // 128-B swizzle: chunk ^ (row & 7)
           // k component outermost: 64 independent FMAs between two uses of an accumulator (per accumulator the
           // summation order is still k ascending)
 #pragma unroll
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
             for (int i = 0; i < 8; ++i) {
               const float wq = q == 0 ? wv[i].x : (q == 1 ? wv[i].y : (q == 2 ? wv[i].z : wv[i].w));
 #pragma unroll
-              for (int m = 0; m < CH_ROWS; ++m) {
+              for (int m = 0; m < ROWS; ++m) {
                 const float av = q == 0 ? a[m].x : (q == 1 ? a[m].y : (q == 2 ? a[m].z : a[m].w));
                 acc[m][i] = fmaf(av, wq, acc[m][i]);
               }
@@ -363,7 +371,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
 #pragma unroll
-            for (int m = 0; m < CH_ROWS; ++m) {
+            for (int m = 0; m < ROWS; ++m) {
               const float av = q == 0 ? a[m].x : (q == 1 ? a[m].y : (q == 2 ? a[m].z : a[m].w));
               acc[m][0] = fmaf(av, w0[q].x, acc[m][0]); acc[m][1] = fmaf(av, w0[q].y, acc[m][1]);
               acc[m][2] = fmaf(av, w0[q].z, acc[m][2]); acc[m][3] = fmaf(av, w0[q].w, acc[m][3]);
@@ -377,15 +385,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     CH_STAMP();                         // per stage: last chunk computed
     // ---- stage epilogue: the 8 partial tiles -> fixed-order sum -> bias+ReLU | ReLU' gate -> next input -----------------
     {
-      float* __restrict__ pw = part + w * (CH_ROWS * CH_MAXW);
+      float* __restrict__ pw = part + w * (ROWS * CH_MAXW);
       if constexpr (FWD) {
 #pragma unroll
-        for (int m = 0; m < CH_ROWS; ++m)
+        for (int m = 0; m < ROWS; ++m)
 #pragma unroll
           for (int i = 0; i < 8; ++i) pw[m * CH_MAXW + lane + 32 * i] = acc[m][i];
       } else {
 #pragma unroll
-        for (int m = 0; m < CH_ROWS; ++m) {
+        for (int m = 0; m < ROWS; ++m) {
           *reinterpret_cast<float4*>(pw + m * CH_MAXW + 4 * lane) = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
           *reinterpret_cast<float4*>(pw + m * CH_MAXW + 128 + 4 * lane) = make_float4(acc[m][4], acc[m][5], acc[m][6], acc[m][7]);
         }
@@ -395,10 +403,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     if (tid < N) {
       float* __restrict__ go = S.out ? S.out + (long long)rep * S.rsOut + (long long)row0 * S.ldo : nullptr;
 #pragma unroll
-      for (int m = 0; m < CH_ROWS; ++m) {
+      for (int m = 0; m < ROWS; ++m) {
         float v = 0.f;
 #pragma unroll
-        for (int ww = 0; ww < CH_WARPS; ++ww) v += part[(ww * CH_ROWS + m) * CH_MAXW + tid];
+        for (int ww = 0; ww < CH_WARPS; ++ww) v += part[(ww * ROWS + m) * CH_MAXW + tid];
         if constexpr (FWD) v = fmaxf(v + ebias, 0.f);
         else if (!(emask[m] > 0.f)) v = 0.f;
         Out[m * CH_INP + tid] = v;
@@ -406,59 +414,106 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       }
     } else if (tid < ((N + 3) & ~3)) {             // pad columns of the next reduction read as zero
 #pragma unroll
-      for (int m = 0; m < CH_ROWS; ++m) Out[m * CH_INP + tid] = 0.f;
+      for (int m = 0; m < ROWS; ++m) Out[m * CH_INP + tid] = 0.f;
     }
     __syncthreads();
     CH_STAMP();                         // per stage: epilogue done
     float* t = In; In = Out; Out = t;
   }
   cp_async_wait<0>();
+  __syncthreads();                         // (jobs without dense stages: head weights / inputs visible)
 
   // ---- head / tail: warp w owns row w ----------------------------------------------------------------------------------
-  if (w >= nrows) return;
   const int row = row0 + w;
   const float* __restrict__ hr = In + w * CH_INP;
   if (FWD && J.head == CH_HEAD_SCALAR) {
-    float a = 0.f;
-    for (int k = lane; k < J.Hh; k += 32) a = fmaf(hr[k], headW[k], a);
-    a = warp_sum(a) + __ldg(J.bh + po);
-    if (lane == 0) (J.qout + (long long)rep * J.rsQ)[row] = a;
+    if (w < nrows) {
+      const float bq = __ldg(J.bh + po);           // requested before the dot product, consumed after it
+      float a = 0.f;
+      for (int k = lane; k < J.Hh; k += 32) a = fmaf(hr[k], headW[k], a);
+      a = warp_sum(a) + bq;
+      if (lane == 0) (J.qout + (long long)rep * J.rsQ)[row] = a;
+    }
   } else if (FWD && J.head == CH_HEAD_POLICY) {
-    const int NO = 2 * K.act, H = J.Hh;
-    float e = policy_noise(K, A.pol, rep, row, lane);
-    float acc[kMaxHeadOut];
+    // (1) every warp: the head GEMV of its row -> sd[row][0..2A).  (2) ONE warp evaluates the tanh-Gaussian of all
+    // ROWS x A (row, action) pairs in parallel lanes: the transcendentals are evaluated in fp64, and a
+    // warp-wide fp64 instruction costs the same with 2 or 32 active lanes -- eight warps with two active lanes each
+    // queued ~5000 cycles on the FP64 pipe (measured), one warp with 16 lanes needs an eighth of that.
+    const int NO = 2 * K.act, H = J.Hh, Aa = K.act;
+    if (w < nrows) {
+      const float* __restrict__ bias = J.bh + po;
+      const float bl = lane < NO ? __ldg(bias + lane) : 0.f;      // bias j in lane j, requested before the GEMV
+      float acc[kMaxHeadOut];
 #pragma unroll
-    for (int j = 0; j < kMaxHeadOut; ++j) acc[j] = 0.f;
-    for (int k = lane; k < H; k += 32) {
-      const float hvv = hr[k];
+      for (int j = 0; j < kMaxHeadOut; ++j) acc[j] = 0.f;
+      for (int k = lane; k < H; k += 32) {
+        const float hvv = hr[k];
+#pragma unroll
+        for (int j = 0; j < kMaxHeadOut; ++j)
+          if (j < NO) acc[j] = fmaf(hvv, headW[j * CH_INP + k], acc[j]);
+      }
 #pragma unroll
       for (int j = 0; j < kMaxHeadOut; ++j)
-        if (j < NO) acc[j] = fmaf(hvv, headW[j * CH_INP + k], acc[j]);
+        if (j < NO) {
+          const float v = warp_sum(acc[j]) + __shfl_sync(0xffffffffu, bl, j);
+          if (lane == 0) sd[w * kMaxHeadOut + j] = v;
+        }
     }
-    const float* __restrict__ bias = J.bh + po;
-#pragma unroll
-    for (int j = 0; j < kMaxHeadOut; ++j)
-      if (j < NO) acc[j] = warp_sum(acc[j]) + __ldg(bias + j);
-    policy_finish(K, A.pol, rep, row, lane, acc, e);
+    __syncthreads();
+    CH_STAMP();                                    // (policy head) GEMVs done
+    if (w == 0) {
+      const PolicyHeadArgs& P = A.pol;
+      float* lp_s = part;                          // [ROWS][A] log-prob terms, [ROWS][A] log-std terms (the partial tiles are free now)
+      float* ls_s = part + ROWS * kMaxAct;
+      for (int e0 = 0; e0 < nrows * Aa; e0 += 32) {
+        const int e = e0 + lane;
+        if (e < nrows * Aa) {
+          const int m = e / Aa, j = e - m * Aa, r = row0 + m;
+          const float mu = sd[m * kMaxHeadOut + j], raw = sd[m * kMaxHeadOut + Aa + j];
+          const float eps = policy_noise(K, P, rep, r, j);
+          const PolicyPoint pp = policy_point(mu, raw, eps, K.action_scale);
+          lp_s[m * kMaxAct + j] = pp.logp_j;
+          ls_s[m * kMaxAct + j] = pp.logstd;
+          float* sv = P.psave + rep * P.rsSave + ((long long)r * Aa + j) * kSaveW;
+          sv[0] = pp.std; sv[1] = pp.diff; sv[2] = pp.t; sv[3] = pp.act; sv[4] = pp.jac; sv[5] = pp.eps; sv[6] = pp.mask;
+          sv[7] = pp.logp_j;
+          (P.act_out + rep * P.rsAct)[(long long)r * Aa + j] = pp.act;
+          float* pout = P.pout + rep * P.rsPout + (long long)r * NO;
+          pout[j] = mu;
+          pout[Aa + j] = raw;
+          if (r < K.B) (P.XT + rep * P.rsX)[(long long)r * K.ldx + K.in_w + j] = pp.act;
+          else (P.XP + rep * P.rsX)[(long long)(r - K.B) * K.ldx + K.in_w + j] = pp.act;
+        }
+      }
+      __syncwarp();
+      if (lane < nrows) {                          // sums over the actions in index order, like the per-row version
+        float tot = 0.f, tls = 0.f;
+        for (int j = 0; j < Aa; ++j) { tot += lp_s[lane * kMaxAct + j]; tls += ls_s[lane * kMaxAct + j]; }
+        (P.logp + rep * P.rsLogp)[row0 + lane] = tot;
+        (P.logstd_sum + rep * P.rsLogp)[row0 + lane] = tls;
+      }
+    }
   } else if (!FWD && J.head == CH_TAIL_DACTION) {
-    const int H0 = J.H0;
-    float acc[kMaxAct];
+    if (w < nrows) {
+      const int H0 = J.H0;
+      float acc[kMaxAct];
 #pragma unroll
-    for (int j = 0; j < kMaxAct; ++j) acc[j] = 0.f;
-    for (int k = lane; k < H0; k += 32) {
-      const float dv = hr[k];
+      for (int j = 0; j < kMaxAct; ++j) acc[j] = 0.f;
+      for (int k = lane; k < H0; k += 32) {
+        const float dv = hr[k];
 #pragma unroll
-      for (int j = 0; j < kMaxAct; ++j)
-        if (j < J.nact) acc[j] = fmaf(dv, w0a[k * kMaxAct + j], acc[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < kMaxAct; ++j)
-      if (j < J.nact) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
-      float* o = J.dx + (long long)rep * J.rsDx + (long long)row * J.lddx + J.col0;
+        for (int j = 0; j < kMaxAct; ++j)
+          if (j < J.nact) acc[j] = fmaf(dv, w0a[k * kMaxAct + j], acc[j]);
+      }
 #pragma unroll
       for (int j = 0; j < kMaxAct; ++j)
-        if (j < J.nact) o[j] = acc[j];
+        if (j < J.nact) acc[j] = warp_sum(acc[j]);
+      if (lane == 0) {
+        float* o = J.dx + (long long)rep * J.rsDx + (long long)row * J.lddx + J.col0;
+#pragma unroll
+        for (int j = 0; j < kMaxAct; ++j)
+          if (j < J.nact) o[j] = acc[j];
+      }
     }
   }
   CH_STAMP();                              // last: head / tail done

@@ -53,6 +53,10 @@ struct IngestOut {
   int* tid;
   Counters* cnt;
   long long rsXA, rsXQ, rsR, rsEps, rsXS;    // per-replica strides
+  // temperature of this step, alpha[t] = exp(log_alpha[t]) as update() snapshots it before anything moves
+  // (LL/learner.py:250, MS/learner.py:337): evaluated ONCE here (fp64, rounded once) for the layer-chained kernels
+  const float* log_alpha; long long rsP;     // parameter arena pointer
+  float* alpha; long long rsAlpha;           // [max(T,1)] per replica
 };
 
 B200_D void ingest_row(const StepConst& K, const IngestOut& O, int rep, int i, const float* s, const float* a,
@@ -95,6 +99,11 @@ B200_D void ingest_row(const StepConst& K, const IngestOut& O, int rep, int i, c
   }
 }
 
+B200_D void snapshot_alpha(const StepConst& K, const IngestOut& O, int rep, int t) {
+  if (O.alpha != nullptr && t < (K.T > 0 ? K.T : 1))
+    (O.alpha + rep * O.rsAlpha)[t] = (float)exp((double)(O.log_alpha + rep * O.rsP)[t]);
+}
+
 B200_D void bump_counters(Counters* cnt, int rep, double beta1, double beta2) {
   Counters* c = cnt + rep;
   c->v[0] += 1; c->v[1] += 1; c->v[2] += 1; c->v[3] += 1; c->v[4] += 1;
@@ -112,6 +121,7 @@ __global__ void ingest_split_kernel(StepConst K, IngestOut O, const float* __res
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
   const int B = K.B;
   if (blockIdx.x == 0 && threadIdx.x == 0) bump_counters(O.cnt, rep, K.beta1, K.beta2);
+  if (blockIdx.x == gridDim.x - 1) snapshot_alpha(K, O, rep, threadIdx.x);
   for (int i = blockIdx.x * wpb + warp; i < B; i += gridDim.x * wpb) {
     const long long ri = (long long)rep * B + i;
     ingest_row(K, O, rep, i, s + ri * K.obs, a + ri * K.act, r[ri], s2 + ri * K.obs, d[ri], lane, 32);
@@ -134,6 +144,7 @@ __global__ void ingest_rows_kernel(StepConst K, IngestOut O, const float* __rest
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, wpb = blockDim.x / 32;
   const int B = K.B;
   if (blockIdx.x == 0 && threadIdx.x == 0) bump_counters(O.cnt, rep, K.beta1, K.beta2);
+  if (blockIdx.x == gridDim.x - 1) snapshot_alpha(K, O, rep, threadIdx.x);
   for (int i = blockIdx.x * wpb + warp; i < B; i += gridDim.x * wpb) {
     const long long src = idx ? (long long)idx[rep * rs_idx + i] : (long long)i;
     const float* row = rows + rep * rs_rows + src * row_stride;
