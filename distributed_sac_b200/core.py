@@ -345,7 +345,9 @@ class SacCore:
         """Per-step intermediates (b200sac_debug_read): y, q1, ..., and the hidden activations "hA.<l>", "hQ.<l>", "hP.<l>",
         "hT.<l>", "mixH.<inst>.<l>" whose sign patterns are the ReLU masks the step used."""
         cap = self.cfg.batch * max(2 * self.cfg.act_dim, 1)
-        if name[0] == "h" or name.startswith("mixH"):
+        if name == "psave":
+            cap = 2 * self.cfg.batch * self.cfg.act_dim * 8
+        elif name[0] == "h" or name.startswith("mixH"):
             widest = max(list(self.cfg.actor_hidden) + list(self.cfg.critic_hidden) + [4 * ((w + 3) // 4) * self.cfg.num_encoders
                                                                                         for w in self.cfg.mix_hidden])
             cap = 2 * self.cfg.batch * widest

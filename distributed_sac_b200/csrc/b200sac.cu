@@ -315,6 +315,7 @@ struct b200sac {
   float* pub_h = nullptr;         // pinned host copy handed to the caller
   int64_t pub_cap = 0, pub_n = 0;
   bool pub_pending = false;
+  CUtensorMap* d_wmaps = nullptr; // layer-chained plan: 2-D maps of the weight-gradient operands, [R][maps per learner]
   CUtensorMap* d_cmaps = nullptr; // layer-chained plan: 2-D tensor maps of the forward weight matrices, [R][maps per learner]
   long long* chain_dbg = nullptr; // B200SAC_CHAIN_DBG=1: [plan launches][CH_DBG_SLOTS] clock64 timelines of the chain kernels
   float* split_d = nullptr;       // b200sac_step: handle-owned copy of the caller's minibatch arrays (stable graph pointers)
@@ -372,6 +373,7 @@ static int destroy_impl(b200sac* h) {
   cudaFree(h->split_d);
   cudaFree(h->chain_dbg);
   cudaFree(h->d_cmaps);
+  cudaFree(h->d_wmaps);
   if (h->pub_h) cudaFreeHost(h->pub_h);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->fork) cudaStreamDestroy(h->fork);
@@ -403,7 +405,7 @@ static EncodeTiledFn get_encode_tiled() {
 
 // 2-D fp32 row-major [outer][inner] (pitch in floats), box {32 floats = 128 B, box_outer rows}, SWIZZLE_128B, zero OOB fill
 static int make_map(CUtensorMap* tm, const float* ptr, long long inner, long long outer, long long pitch, int box_outer,
-                    bool mn_major = false) {
+                    bool mn_major = false, bool dense = false) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(B200SAC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -411,7 +413,7 @@ static int make_map(CUtensorMap* tm, const float* ptr, long long inner, long lon
   cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   dense ? CU_TENSOR_MAP_SWIZZLE_NONE : (mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200SAC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld pitch=%lld", (int)r, inner, outer, pitch);
   return 0;
@@ -491,6 +493,8 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
   rw.psave = h->psave.p + (long long)B * A * kSaveW; rw.rsSave = h->psave.rs;
   rw.dout_dbg = h->dout_dbg.p; rw.dact_dbg = h->dact_dbg.p; rw.rsDbg = h->dout_dbg.rs;
 
+  struct WMap { const float* p; long long rs; int ld, cols; };
+  std::vector<WMap> wmaps;                 // weight-gradient operands [B rows][cols] that get a tensor map
   struct FMap { int64_t off; int K, N, ld; };
   std::vector<FMap> fmaps;                 // forward weight matrices that need a tensor map (one per chained forward stage)
   auto new_chain = [&](const char* label, int early_weights = 1) {
@@ -579,7 +583,13 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
       J.A = Ap; J.rsA = rsA; J.lda = lda; J.B = Bp; J.rsB = rsB; J.ldb = ldb;
       J.C = Gp(offW); J.C2 = Gp(offB); J.ldc = ldc; J.Kout = Kout; J.Nin = Nin;
       J.tile0 = tiles; J.tn = (Nin + WG_T - 1) / WG_T;
+      J.shape = Kout <= 4 ? WG_KTHIN : (Nin <= 16 ? WG_NTHIN : WG_FULL);
       tiles += J.tn * ((Kout + WG_T - 1) / WG_T);
+      // operands a tensor map can address (16-byte row pitch and base) arrive by TMA, the others are staged by the threads
+      auto tmable = [&](const float* p_, long long rs_, int ld_) { return (ld_ % 4) == 0 && (((uintptr_t)p_) & 15) == 0 && (rs_ % 4) == 0; };
+      J.tmA_idx = J.tmB_idx = -1;
+      if (tmable(Ap, rsA, lda)) { J.tmA_idx = (int)wmaps.size(); wmaps.push_back(WMap{Ap, rsA, lda, Kout}); }
+      if (tmable(Bp, rsB, ldb)) { J.tmB_idx = (int)wmaps.size(); wmaps.push_back(WMap{Bp, rsB, ldb, Nin}); }
       return 0;
     };
     for (const WNet& n : nets) {
@@ -703,6 +713,27 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
               S.tm = h->d_cmaps + S.tm_idx;
               S.rsTm = n;
             }
+  }
+  {  // weight-gradient operand maps [R][n]: [B rows][cols] row-major, box {32 cols, 256 rows}, dense
+    const int n = (int)wmaps.size();
+    std::vector<CUtensorMap> maps((size_t)R * n);
+    for (int rep = 0; rep < R; ++rep)
+      for (int i = 0; i < n; ++i)
+        if (int rc = make_map(&maps[(size_t)rep * n + i], wmaps[i].p + (long long)rep * wmaps[i].rs, wmaps[i].cols, B, wmaps[i].ld, WG_ROWS,
+                              false, true))
+          return rc;
+    if (n > 0) {
+      CU(cudaMalloc(&h->d_wmaps, maps.size() * sizeof(CUtensorMap)));
+      CU(cudaMemcpy(h->d_wmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    }
+    for (auto& l : h->plan)
+      if (l.kind == L_WGRAD)
+        for (int j = 0; j < l.wg.njobs; ++j) {
+          WgradJob& J = l.wg.job[j];
+          J.tmA = J.tmA_idx >= 0 ? h->d_wmaps + J.tmA_idx : nullptr;
+          J.tmB = J.tmB_idx >= 0 ? h->d_wmaps + J.tmB_idx : nullptr;
+          J.rsTm = n;
+        }
   }
   CU(cudaFuncSetAttribute(chain_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
   CU(cudaFuncSetAttribute(chain_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
@@ -2504,6 +2535,7 @@ extern "C" int b200sac_debug_read(b200sac_t* h, const char* name, int32_t replic
   else if (nm == "qmin") { src = h->qmin.p + replica * h->qmin.rs; n = B; }
   else if (nm == "d_action") { src = h->dact_dbg.p + replica * h->dact_dbg.rs; n = (int64_t)B * A; }
   else if (nm == "d_head") { src = h->dout_dbg.p + replica * h->dout_dbg.rs; n = (int64_t)B * 2 * A; }
+  else if (nm == "psave") { src = h->psave.p + replica * h->psave.rs; n = (int64_t)2 * B * A * kSaveW; }   // [2B][A][8]: std, diff, tanh, act, jac, EPS, mask, logp_j
   else if (nm == "chain_dbg") {
     if (!h->chain_dbg) return fail(B200SAC_ERR_INVALID, "chain_dbg needs B200SAC_CHAIN_DBG=1 at create time");
     src = reinterpret_cast<const float*>(h->chain_dbg); n = 2 * CH_DBG_SLOTS * 16;     // int64 stamps viewed as float pairs

@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
 #define CH_STAMP() do { if (dbg != nullptr && dbg_i < CH_DBG_SLOTS) dbg[dbg_i++] = clock64(); } while (0)
   CH_STAMP();                              // 0: kernel entry
   extern __shared__ __align__(1024) float sm_raw[];
-  float* sm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));   // SWIZZLE_128B tiles: 1 KB aligned
+  // SWIZZLE_128B tiles want 1 KB alignment.  The offset is applied as POINTER arithmetic on the shared array: rounding the
+  // address through an integer makes every later access a generic LD/ST instead of LDS/STS (measured: 22 % of the stall
+  // samples of the first TMA version sat on LD.E.128)
+  float* sm = sm_raw + (((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u) >> 2);
   const ChainJob& J = A.job[blockIdx.y];
   const int rep = blockIdx.z;
   const int row0 = blockIdx.x * ROWS;
@@ -145,7 +148,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   float* part = w0a + CH_SM_W0A;
 
   // ---- weight pipeline: thread 0 issues chunk g into stage g % 3; the chunk lands on bars[g % 3] (phase (g / 3) & 1) -------
-  int is = 0, ic = 0, issued = 0;        // next chunk to issue: stage, chunk within the stage, running count
+  // Forward jobs whose input layer has K <= 32 (8 / 10 columns at LunarLander): that layer is evaluated DIRECTLY -- thread n
+  // holds row n of W0 in registers and does the K-long dot product for every row itself: no weight chunk, no split-K
+  // partials, no reduction (measured: ~2200 cycles of chunk wait + partial-tile epilogue for 80 FMAs per thread).
+  const bool direct0 = FWD && J.nstages > 1 && J.st[0].K <= CH_KC;
+  int is = direct0 ? 1 : 0, ic = 0, issued = 0;        // next chunk to issue: stage, chunk within the stage, running count
   auto issue_next = [&]() {
     if (tid == 0 && is < J.nstages) {
       const ChainStage& S = J.st[is];
@@ -308,7 +315,42 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   CH_STAMP();                              // 3: backward prologue done (forward: == 2)
   // ---- the dense stages ------------------------------------------------------------------------------------------------
   int g = 0;
-  for (int s = 0; s < J.nstages; ++s) {
+  if constexpr (FWD) {
+    if (direct0) {
+      const ChainStage& S = J.st[0];
+      const int N = S.N, K4 = (S.K + 3) & ~3;
+      float4 wr[CH_KC / 4];
+      float b0 = 0.f;
+      if (tid < N) {
+        const float4* __restrict__ wp = reinterpret_cast<const float4*>(S.W + po + (long long)tid * S.ldw);
+#pragma unroll
+        for (int q = 0; q < CH_KC / 4; ++q) wr[q] = (4 * q < K4) ? __ldg(wp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b0 = __ldg(S.bias + po + tid);
+      }
+      cp_async_wait<0>();
+      __syncthreads();                  // the input rows are in shared memory
+      if (tid < N) {
+        float* __restrict__ go = S.out ? S.out + (long long)rep * S.rsOut + (long long)row0 * S.ldo : nullptr;
+#pragma unroll
+        for (int m = 0; m < ROWS; ++m) {
+          float v = 0.f;
+#pragma unroll
+          for (int q = 0; q < CH_KC / 4; ++q)
+            if (4 * q < K4) {
+              const float4 x = *reinterpret_cast<const float4*>(In + m * CH_INP + 4 * q);
+              v = fmaf(x.x, wr[q].x, v); v = fmaf(x.y, wr[q].y, v); v = fmaf(x.z, wr[q].z, v); v = fmaf(x.w, wr[q].w, v);
+            }
+          v = fmaxf(v + b0, 0.f);
+          Out[m * CH_INP + tid] = v;
+          if (go && m < nrows) go[(long long)m * S.ldo + tid] = v;
+        }
+      }
+      __syncthreads();
+      CH_STAMP();                       // input layer done (direct)
+      float* t_ = In; In = Out; Out = t_;
+    }
+  }
+  for (int s = direct0 ? 1 : 0; s < J.nstages; ++s) {
     const ChainStage& S = J.st[s];
     const int N = S.N, K4 = (S.K + 3) & ~3;
     // epilogue operands of this thread's column, requested now
@@ -533,15 +575,22 @@ constexpr int WG_T = 32;
 constexpr int WG_ROWS = 256;               // batch rows staged per pass
 constexpr int WG_MAXJOBS = 20;
 constexpr int WG_THREADS = 256;
-constexpr size_t WG_SMEM_BYTES = (size_t)(2 * WG_ROWS * WG_T + 8 * WG_T * WG_T + 8 * WG_T) * sizeof(float);
+constexpr size_t WG_SMEM_BYTES = (size_t)(2 * WG_ROWS * WG_T + 8 * WG_T * WG_T + 8 * WG_T + 16) * sizeof(float) + 128;
+
+// lane mappings of a tile: FULL 32 k x 32 n (4 x 8 per lane); NTHIN for Nin <= 16 (input-layer weights: 32 k x 16 n,
+// 4 x 4 per lane -- half the FMAs); KTHIN for Kout <= 4 (head weights: 4 k x 32 n, 4 x 1 per lane -- an eighth)
+enum { WG_FULL = 0, WG_NTHIN = 1, WG_KTHIN = 2 };
 
 struct WgradJob {
   const float* A; const float* B;          // work-slab pointers (row 0)
   float* C; float* C2;                     // gradient arena (replica stride rsG); C2 may be null
+  const CUtensorMap* tmA; const CUtensorMap* tmB;   // 2-D maps [M rows][cols], box 32 x 256, dense; null -> staged by the threads
   long long rsA, rsB;
   int lda, ldb, ldc;
   int Kout, Nin;
   int tile0, tn;                           // first blockIdx.x of the job, tiles along Nin
+  int shape;
+  int tmA_idx, tmB_idx, rsTm;              // (host: indices into the map table; replica r at tm + r * rsTm)
 };
 struct WgradArgs {
   int njobs, M;
@@ -550,30 +599,24 @@ struct WgradArgs {
 };
 
 B200_D void wg_stage(float* __restrict__ dst, const float* __restrict__ src, int ld, int c0, int cmax, int m0, int M, int tid) {
-  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   for (int e = tid; e < WG_ROWS * (WG_T / 4); e += WG_THREADS) {
     const int mm = e >> 3, q = (e & 7) << 2;
     const int m = m0 + mm, c = c0 + q;
-    float* d = dst + mm * WG_T + q;
-    if (m < M && vec && c + 3 < cmax) {
-      cp_async16(d, src + (long long)m * ld + c);
-    } else {
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M) {
-        const float* p = src + (long long)m * ld + c;
-        if (c < cmax) x.x = __ldg(p);
-        if (c + 1 < cmax) x.y = __ldg(p + 1);
-        if (c + 2 < cmax) x.z = __ldg(p + 2);
-        if (c + 3 < cmax) x.w = __ldg(p + 3);
-      }
-      *reinterpret_cast<float4*>(d) = x;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < M) {
+      const float* p = src + (long long)m * ld + c;
+      if (c < cmax) x.x = __ldg(p);
+      if (c + 1 < cmax) x.y = __ldg(p + 1);
+      if (c + 2 < cmax) x.z = __ldg(p + 2);
+      if (c + 3 < cmax) x.w = __ldg(p + 3);
     }
+    *reinterpret_cast<float4*>(dst + mm * WG_T + q) = x;
   }
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_constant__ WgradArgs A) {
-  KStamp ks_;
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(128) float wsm_raw[];
+  float* sm = wsm_raw + (((128u - (smem_u32(wsm_raw) & 127u)) & 127u) >> 2);      // (pointer arithmetic keeps the shared address space)
   int ji = 0;
   for (int j = 1; j < A.njobs; ++j)
     if ((int)blockIdx.x >= A.job[j].tile0) ji = j;
@@ -589,6 +632,17 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
   float* Bs = As + WG_ROWS * WG_T;
   float* part = Bs + WG_ROWS * WG_T;
   float* bpart = part + 8 * WG_T * WG_T;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(bpart + 8 * WG_T);
+  const CUtensorMap* tmA = J.tmA ? J.tmA + (long long)rep * J.rsTm : nullptr;
+  const CUtensorMap* tmB = J.tmB ? J.tmB + (long long)rep * J.rsTm : nullptr;
+  if (tid == 0) {
+    if (tmA) asm volatile("prefetch.tensormap [%0];" ::"l"(tmA) : "memory");
+    if (tmB) asm volatile("prefetch.tensormap [%0];" ::"l"(tmB) : "memory");
+    mbar_init(smem_u32(bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  KStamp ks_;                              // the operands come from the launch right before this one
+  __syncthreads();
   const float* __restrict__ Ag = J.A + (long long)rep * J.rsA;
   const float* __restrict__ Bg = J.B + (long long)rep * J.rsB;
   const int M = A.M;
@@ -600,42 +654,89 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   float asum[4] = {0.f, 0.f, 0.f, 0.f};
 
-  for (int m0 = 0; m0 < M; m0 += WG_ROWS) {
+  int pass = 0;
+  for (int m0 = 0; m0 < M; m0 += WG_ROWS, ++pass) {
     if (m0 > 0) __syncthreads();
-    wg_stage(As, Ag, J.lda, k0, J.Kout, m0, M, tid);
-    wg_stage(Bs, Bg, J.ldb, n0, J.Nin, m0, M, tid);
-    cp_async_commit();
-    cp_async_wait<0>();
+    if (tid == 0 && (tmA || tmB)) {
+      mbar_expect_tx(smem_u32(bar), (uint32_t)((tmA ? 1 : 0) + (tmB ? 1 : 0)) * WG_ROWS * WG_T * 4u);
+      if (tmA) tma_load_2d(smem_u32(As), tmA, k0, m0, smem_u32(bar));
+      if (tmB) tma_load_2d(smem_u32(Bs), tmB, n0, m0, smem_u32(bar));
+    }
+    if (!tmA) wg_stage(As, Ag, J.lda, k0, J.Kout, m0, M, tid);
+    if (!tmB) wg_stage(Bs, Bg, J.ldb, n0, J.Nin, m0, M, tid);
+    if (tmA || tmB) mbar_wait(smem_u32(bar), (uint32_t)(pass & 1));
     __syncthreads();
     const int mcnt = (M - m0 < WG_ROWS) ? M - m0 : WG_ROWS;
     const int per = (mcnt + 7) >> 3;
     const int mb = w * per, me = (mb + per < mcnt) ? mb + per : mcnt;
+    if (J.shape == WG_FULL) {
 #pragma unroll 4
-    for (int m = mb; m < me; ++m) {
-      const float4 a = *reinterpret_cast<const float4*>(As + m * WG_T + 4 * ky);
-      const float4 b0 = *reinterpret_cast<const float4*>(Bs + m * WG_T + 8 * nx);
-      const float4 b1 = *reinterpret_cast<const float4*>(Bs + m * WG_T + 8 * nx + 4);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      for (int m = mb; m < me; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(As + m * WG_T + 4 * ky);
+        const float4 b0 = *reinterpret_cast<const float4*>(Bs + m * WG_T + 8 * nx);
+        const float4 b1 = *reinterpret_cast<const float4*>(Bs + m * WG_T + 8 * nx + 4);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        asum[i] += av[i];
+        for (int i = 0; i < 4; ++i) {
+          asum[i] += av[i];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+      }
+    } else if (J.shape == WG_NTHIN) {
+#pragma unroll 4
+      for (int m = mb; m < me; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(As + m * WG_T + 4 * ky);
+        const float4 b0 = *reinterpret_cast<const float4*>(Bs + m * WG_T + 4 * nx);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          asum[i] += av[i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int m = mb; m < me; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(As + m * WG_T);
+        const float b = Bs[m * WG_T + lane];
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          asum[i] += av[i];
+          acc[i][0] = fmaf(av[i], b, acc[i][0]);
+        }
       }
     }
   }
-  // partial tiles -> fixed-order sum
+  // partial tiles -> fixed-order sum.  Every mapping fills the part of the [32 k][32 n] tile that holds its valid outputs.
   {
     float* pw = part + w * (WG_T * WG_T);
+    if (J.shape == WG_FULL) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      *reinterpret_cast<float4*>(pw + (4 * ky + i) * WG_T + 8 * nx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      *reinterpret_cast<float4*>(pw + (4 * ky + i) * WG_T + 8 * nx + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-    }
-    if (nx == 0) {
+      for (int i = 0; i < 4; ++i) {
+        *reinterpret_cast<float4*>(pw + (4 * ky + i) * WG_T + 8 * nx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(pw + (4 * ky + i) * WG_T + 8 * nx + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+      if (nx == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) bpart[w * WG_T + 4 * ky + i] = asum[i];
+        for (int i = 0; i < 4; ++i) bpart[w * WG_T + 4 * ky + i] = asum[i];
+      }
+    } else if (J.shape == WG_NTHIN) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(pw + (4 * ky + i) * WG_T + 4 * nx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (nx == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bpart[w * WG_T + 4 * ky + i] = asum[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pw[i * WG_T + lane] = acc[i][0];
+      if (lane < 4) bpart[w * WG_T + lane] = lane == 0 ? asum[0] : (lane == 1 ? asum[1] : (lane == 2 ? asum[2] : asum[3]));
     }
   }
   __syncthreads();
@@ -644,10 +745,12 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
   for (int u = 0; u < 4; ++u) {
     const int o = tid + WG_THREADS * u;
     const int kk = o >> 5, nn = o & 31;
-    float v = 0.f;
+    if (k0 + kk < J.Kout && n0 + nn < J.Nin) {
+      float v = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) v += part[ww * (WG_T * WG_T) + o];
-    if (k0 + kk < J.Kout && n0 + nn < J.Nin) C[(long long)(k0 + kk) * J.ldc + n0 + nn] = v;
+      for (int ww = 0; ww < 8; ++ww) v += part[ww * (WG_T * WG_T) + o];
+      C[(long long)(k0 + kk) * J.ldc + n0 + nn] = v;
+    }
   }
   if (bn == 0 && J.C2 != nullptr && tid < WG_T && k0 + tid < J.Kout) {
     float v = 0.f;

@@ -198,7 +198,9 @@ int b200sac_publish_begin(b200sac_t* h, int32_t replica, int32_t n_ranges, const
 int b200sac_publish_wait(b200sac_t* h, const float** host_ptr, int64_t* n_floats);
 
 /* Debug / parity access to per-step intermediates of replica `replica`:
- * name in {"y","q1","q2","a_next","logp_next","a_cur","logp_cur","qmin","d_action","d_head","r","d"}, or a hidden
+ * name in {"y","q1","q2","a_next","logp_next","a_cur","logp_cur","qmin","d_action","d_head","r","d"}, "psave" ([2B][act][8]:
+ * what the policy head saved per (row, action) -- std, u-mu, tanh(u), action, Jacobian term, the NOISE it used, clamp mask,
+ * log-prob term), or a hidden
  * activation whose sign pattern is the ReLU mask the step used: "hA.<l>" [2B][H] (rows [s';s]), "hQ.<l>" / "hP.<l>" /
  * "hT.<l>" [2][B][H] (critic-update pass / actor pass / target pass; the layer-chained plan does not keep hT),
  * "mixH.<inst>.<l>" [K][rows][pitch4(H)] (CARE mixture encoders). */
