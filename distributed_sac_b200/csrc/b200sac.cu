@@ -519,9 +519,11 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
     // rows per CTA: every CTA streams the whole weight matrices whatever its row count, so fewer rows per CTA only pay
     // while the launch still fits the GPU: 8 rows when that already gives >= 96 CTAs, else 4 (twice the CTAs, half the math each)
     long long total = 0;
-    for (int j = 0; j < l.chain.njobs; ++j) total += (l.chain.job[j].rows + 7) / 8;
-    l.bn = (total * R >= 96) ? 8 : 4;             // (bn is reused as "rows per CTA" for chain launches)
-    if (const char* e = getenv("B200SAC_CHAIN_ROWS")) l.bn = atoi(e) == 4 ? 4 : 8;
+    for (int j = 0; j < l.chain.njobs; ++j) total += l.chain.job[j].rows;
+    l.bn = 8;                                      // (bn is reused as "rows per CTA" for chain launches)
+    for (int rows = 4; rows >= 2; rows >>= 1)      // the fewest rows per CTA whose launch still fits one wave of 148 CTAs
+      if ((total + rows - 1) / rows * R <= 148) l.bn = rows;
+    if (const char* e = getenv("B200SAC_CHAIN_ROWS")) { const int v = atoi(e); l.bn = (v == 2 || v == 4) ? v : 8; }
     int maxb = 1;
     for (int j = 0; j < l.chain.njobs; ++j) {
       const int nb = (l.chain.job[j].rows + l.bn - 1) / l.bn;
@@ -739,6 +741,8 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
   CU(cudaFuncSetAttribute(chain_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
   CU(cudaFuncSetAttribute(chain_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
   CU(cudaFuncSetAttribute(chain_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(chain_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(chain_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
   CU(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES));
   return 0;
 }
@@ -1459,9 +1463,12 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
         if (l.bn == 8) {
           if (f) launch_k(chain_kernel<true, 8>, l.grid, l.block, l.smem, s, a, h->K);
           else launch_k(chain_kernel<false, 8>, l.grid, l.block, l.smem, s, a, h->K);
-        } else {
+        } else if (l.bn == 4) {
           if (f) launch_k(chain_kernel<true, 4>, l.grid, l.block, l.smem, s, a, h->K);
           else launch_k(chain_kernel<false, 4>, l.grid, l.block, l.smem, s, a, h->K);
+        } else {
+          if (f) launch_k(chain_kernel<true, 2>, l.grid, l.block, l.smem, s, a, h->K);
+          else launch_k(chain_kernel<false, 2>, l.grid, l.block, l.smem, s, a, h->K);
         }
         break;
       }

@@ -226,21 +226,27 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     if (J.kind == CJ_BWD_ACTORQ && J.nact > 0) {   // action columns of the first-layer weights for the tail
       const float* __restrict__ W0 = J.W0 + po;
       const int H0 = J.H0;
-      for (int e = tid; e < H0 * J.nact; e += CH_THREADS) {
-        const int k = e / J.nact, j = e - k * J.nact;
-        w0a[k * kMaxAct + j] = __ldg(W0 + (long long)k * J.ldw0 + J.col0 + j);
+      for (int e = tid; e < H0 * kMaxAct; e += CH_THREADS) {
+        const int k = e >> 3, j = e & 7;
+        w0a[e] = j < J.nact ? __ldg(W0 + (long long)k * J.ldw0 + J.col0 + j) : 0.f;
       }
     }
+    // the step's temperatures (<= 64 tasks) are requested by the lanes up front; the row's alpha[t] then comes from a
+    // shuffle instead of a second, dependent round trip behind the task-id load
+    const float alpha_lo = (R.alpha + rep * R.rsAlpha)[lane < (K.T > 0 ? K.T : 1) ? lane : 0];
+    const float alpha_hi = (K.T > 32) ? (R.alpha + rep * R.rsAlpha)[lane + 32 < K.T ? lane + 32 : 0] : 0.f;
+    auto alpha_of = [&](int t) { const float lo = __shfl_sync(0xffffffffu, alpha_lo, t & 31), hi = __shfl_sync(0xffffffffu, alpha_hi, t & 31); return t < 32 ? lo : hi; };
     if (w < nrows) {
       if (J.kind == CJ_BWD_CRITIC) {
+        const int t_row = __shfl_sync(0xffffffffu, lane == 0 ? (R.tid + rep * R.rsR)[row] : 0, 0);
+        const float alpha_row = alpha_of(t_row);
         if (lane == 0) {
-          const int t = (R.tid + rep * R.rsR)[row];
           const float r = (R.r + rep * R.rsR)[row], d = (R.d + rep * R.rsR)[row];
           const float lp = (R.logp + rep * R.rsLogp)[row];
           const float* QT = R.qt + rep * 2 * R.rsY;
           const float* Q = R.q + rep * 2 * R.rsY;
           const float qt1 = QT[row], qt2 = QT[B + row], q1 = Q[row], q2 = Q[B + row];
-          const float alpha = (R.alpha + rep * R.rsAlpha)[t];
+          const float alpha = alpha_row;
           const float t1 = K.reward_scale * r;
           const float t2 = K.gamma * (1.f - d);
           const float t3 = fminf(qt1, qt2) - alpha * lp;
@@ -256,8 +262,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           }
         }
       } else if (J.kind == CJ_BWD_ACTORQ) {
+        const int t_row = __shfl_sync(0xffffffffu, lane == 0 ? (R.tid + rep * R.rsR)[row] : 0, 0);
+        const float alpha_row = alpha_of(t_row);
         if (lane == 0) {
-          const int t = (R.tid + rep * R.rsR)[row];
           const float lp = (R.logp + rep * R.rsLogp)[B + row];
           const float* QP = R.qp + rep * 2 * R.rsY;
           const float q1 = QP[row], q2 = QP[B + row];
@@ -269,18 +276,20 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           sd[w * kMaxHeadOut] = g;
           (R.dqa + rep * 2 * R.rsY)[J.net * B + row] = g;
           if (J.net == 0) {
-            const float alpha = (R.alpha + rep * R.rsAlpha)[t];
+            const float alpha = alpha_row;
             const float qm = fminf(q1, q2);
             (R.la + rep * R.rsY)[row] = -(qm - alpha * lp);
             (R.qmin + rep * R.rsY)[row] = qm;
           }
         }
       } else {                                     // CJ_BWD_POLICY: lane j < A owns action j
+        const int t_row = __shfl_sync(0xffffffffu, lane == 0 ? (R.tid + rep * R.rsR)[row] : 0, 0);
+        const float alpha_row = alpha_of(t_row);
         if (lane < Aa) {
           const float* __restrict__ sv = R.psave + rep * R.rsSave + ((long long)row * Aa + lane) * kSaveW;
           const float* __restrict__ dx0 = R.dxP + rep * R.rsDxRep + (long long)row * R.lddx + K.in_w + lane;
           const float da = dx0[0] + dx0[R.rsDxNet];
-          const float alpha = (R.alpha + rep * R.rsAlpha)[(R.tid + rep * R.rsR)[row]];
+          const float alpha = alpha_row;
           float dmu, dls;
           policy_dout_point(K, sv, da, alpha, dmu, dls);
           sd[w * kMaxHeadOut + lane] = dmu;
@@ -484,22 +493,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     const int NO = 2 * K.act, H = J.Hh, Aa = K.act;
     if (w < nrows) {
       const float* __restrict__ bias = J.bh + po;
-      const float bl = lane < NO ? __ldg(bias + lane) : 0.f;      // bias j in lane j, requested before the GEMV
-      float acc[kMaxHeadOut];
-#pragma unroll
-      for (int j = 0; j < kMaxHeadOut; ++j) acc[j] = 0.f;
-      for (int k = lane; k < H; k += 32) {
-        const float hvv = hr[k];
-#pragma unroll
-        for (int j = 0; j < kMaxHeadOut; ++j)
-          if (j < NO) acc[j] = fmaf(hvv, headW[j * CH_INP + k], acc[j]);
+      // head GEMV of this warp's row, compact on purpose (this code runs once per CTA, out of a cold instruction cache: an
+      // unrolled 16-output version took 3000-4500 cycles, measured).  The 32 lanes split into NOp groups of G lanes
+      // (NOp = NO rounded up to a power of two): lane (j, part) sums h[k] * W[j][k] over k = part (mod G), then a
+      // log2(G)-level butterfly inside the group; lane j * G holds output j.
+      int NOp = 1;
+      while (NOp < NO) NOp <<= 1;
+      const int G = 32 / NOp, jj = lane / G, part_ = lane - jj * G;
+      float accj = 0.f;
+      if (jj < NO) {
+        const float* __restrict__ wrow = headW + jj * CH_INP;
+#pragma unroll 4
+        for (int k = part_; k < H; k += G) accj = fmaf(hr[k], wrow[k], accj);
       }
-#pragma unroll
-      for (int j = 0; j < kMaxHeadOut; ++j)
-        if (j < NO) {
-          const float v = warp_sum(acc[j]) + __shfl_sync(0xffffffffu, bl, j);
-          if (lane == 0) sd[w * kMaxHeadOut + j] = v;
-        }
+      for (int o = G >> 1; o > 0; o >>= 1) accj += __shfl_xor_sync(0xffffffffu, accj, o);
+      if (jj < NO && part_ == 0) sd[w * kMaxHeadOut + jj] = accj + __ldg(bias + jj);
     }
     __syncthreads();
     CH_STAMP();                                    // (policy head) GEMVs done
@@ -541,15 +549,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       float acc[kMaxAct];
 #pragma unroll
       for (int j = 0; j < kMaxAct; ++j) acc[j] = 0.f;
-      for (int k = lane; k < H0; k += 32) {
+      for (int k = lane; k < H0; k += 32) {          // both float4 of the row's action weights are loaded before the FMAs
         const float dv = hr[k];
-#pragma unroll
-        for (int j = 0; j < kMaxAct; ++j)
-          if (j < J.nact) acc[j] = fmaf(dv, w0a[k * kMaxAct + j], acc[j]);
+        const float4 wa = *reinterpret_cast<const float4*>(w0a + k * kMaxAct);
+        const float4 wb = *reinterpret_cast<const float4*>(w0a + k * kMaxAct + 4);
+        acc[0] = fmaf(dv, wa.x, acc[0]); acc[1] = fmaf(dv, wa.y, acc[1]); acc[2] = fmaf(dv, wa.z, acc[2]); acc[3] = fmaf(dv, wa.w, acc[3]);
+        acc[4] = fmaf(dv, wb.x, acc[4]); acc[5] = fmaf(dv, wb.y, acc[5]); acc[6] = fmaf(dv, wb.z, acc[6]); acc[7] = fmaf(dv, wb.w, acc[7]);
       }
 #pragma unroll
-      for (int j = 0; j < kMaxAct; ++j)
-        if (j < J.nact) acc[j] = warp_sum(acc[j]);
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < kMaxAct; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      }
       if (lane == 0) {
         float* o = J.dx + (long long)rep * J.rsDx + (long long)row * J.lddx + J.col0;
 #pragma unroll

@@ -263,22 +263,29 @@ struct PolicyPoint {   // everything the backward needs for one (row, action)
   float std, diff, t, act, jac, eps, mask, logp_j, logstd;
 };
 
+// fp64-evaluated, once-rounded transcendentals as out-of-line functions: their bodies (70-150 instructions each) exist once
+// per kernel instead of once per call site.  The kernels that use them run each code path once per CTA, i.e. out of a cold
+// instruction cache (32 KB L1.5 against 70 KB kernels): straight-line code costs several cycles per instruction there.
+__device__ __noinline__ float exp_f64r(float x) { return (float)exp((double)x); }
+__device__ __noinline__ float tanh_f64r(float x) { return (float)tanh((double)x); }
+__device__ __noinline__ float log_f64r(float x) { return (float)log((double)x); }
+
 B200_D PolicyPoint policy_point(float mu, float raw, float eps, float k) {
   PolicyPoint p;
   const float ls = fminf(fmaxf(raw, -20.f), 2.f);          // torch.clamp(x, -20, 2)
   p.mask = (raw >= -20.f && raw <= 2.f) ? 1.f : 0.f;
-  p.std = (float)exp((double)ls);
+  p.std = exp_f64r(ls);
   p.eps = eps;
   const float u = mu + p.std * eps;                        // Normal.rsample: loc + eps * scale
-  p.t = (float)tanh((double)u);
+  p.t = tanh_f64r(u);
   p.act = k * p.t;
   p.diff = u - mu;                                         // as rounded, NOT std*eps
   const float var = p.std * p.std;
-  p.logstd = (float)log((double)p.std);
+  p.logstd = log_f64r(p.std);
   const float gauss = -(p.diff * p.diff) / (2.f * var) - p.logstd - 0.91893853320467274178f;
   const float q = p.act / k;
   p.jac = k * (1.f - q * q + 1e-6f);
-  p.logp_j = gauss - (float)log((double)p.jac);
+  p.logp_j = gauss - log_f64r(p.jac);
   return p;
 }
 
