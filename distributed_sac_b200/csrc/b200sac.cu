@@ -309,12 +309,14 @@ struct b200sac {
   int prefetch_slot = -1;         // host-ring step_sampled: minibatch already drawn, gathered and in flight (H2D)
   b200sac_replay* prefetch_rb = nullptr;
   // publication path (b200sac_publish_*): device snapshot -> pinned host, on its own stream
+  // two snapshot slots: the caller may build the published blob from snapshot k while snapshot k+1 (begun after the next
+  // step was enqueued) is still landing
   cudaStream_t pub = nullptr;
-  cudaEvent_t ev_pub_snap = nullptr, ev_pub_done = nullptr;
-  float* pub_d = nullptr;         // device snapshot (consistent: taken in stream order between two steps)
-  float* pub_h = nullptr;         // pinned host copy handed to the caller
-  int64_t pub_cap = 0, pub_n = 0;
-  bool pub_pending = false;
+  cudaEvent_t ev_pub_snap[2] = {nullptr, nullptr}, ev_pub_done[2] = {nullptr, nullptr};
+  float* pub_d[2] = {nullptr, nullptr};   // device snapshots (consistent: taken in stream order between two steps)
+  float* pub_h[2] = {nullptr, nullptr};   // pinned host copies handed to the caller
+  int64_t pub_cap = 0, pub_n[2] = {0, 0};
+  int pub_head = 0, pub_pending = 0;      // next slot to fill; snapshots begun and not yet collected (<= 2)
   CUtensorMap* d_wmaps = nullptr; // layer-chained plan: 2-D maps of the weight-gradient operands, [R][maps per learner]
   CUtensorMap* d_cmaps = nullptr; // layer-chained plan: 2-D tensor maps of the forward weight matrices, [R][maps per learner]
   long long* chain_dbg = nullptr; // B200SAC_CHAIN_DBG=1: [plan launches][CH_DBG_SLOTS] clock64 timelines of the chain kernels
@@ -367,14 +369,16 @@ static int destroy_impl(b200sac* h) {
   }
   if (h->loss_h) cudaFreeHost(h->loss_h);
   if (h->pub) { cudaStreamSynchronize(h->pub); cudaStreamDestroy(h->pub); }
-  if (h->ev_pub_snap) cudaEventDestroy(h->ev_pub_snap);
-  if (h->ev_pub_done) cudaEventDestroy(h->ev_pub_done);
-  cudaFree(h->pub_d);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_pub_snap[i]) cudaEventDestroy(h->ev_pub_snap[i]);
+    if (h->ev_pub_done[i]) cudaEventDestroy(h->ev_pub_done[i]);
+    cudaFree(h->pub_d[i]);
+    if (h->pub_h[i]) cudaFreeHost(h->pub_h[i]);
+  }
   cudaFree(h->split_d);
   cudaFree(h->chain_dbg);
   cudaFree(h->d_cmaps);
   cudaFree(h->d_wmaps);
-  if (h->pub_h) cudaFreeHost(h->pub_h);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->fork) cudaStreamDestroy(h->fork);
   if (h->ev_ingested) cudaEventDestroy(h->ev_ingested);
@@ -1860,44 +1864,55 @@ extern "C" int b200sac_publish_begin(b200sac_t* h, int32_t replica, int32_t n_ra
   CU(cudaSetDevice(h->device));
   if (!h->pub) {
     CU(cudaStreamCreateWithFlags(&h->pub, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&h->ev_pub_snap, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_pub_done, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      CU(cudaEventCreateWithFlags(&h->ev_pub_snap[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->ev_pub_done[i], cudaEventDisableTiming));
+    }
   }
-  if (h->pub_pending) CU(cudaEventSynchronize(h->ev_pub_done));     // an unread snapshot is simply superseded
+  if (h->pub_pending == 2) {            // both slots hold uncollected snapshots: the older one is superseded
+    CU(cudaEventSynchronize(h->ev_pub_done[h->pub_head]));
+    h->pub_pending = 1;
+  }
   if (total > h->pub_cap) {
     CU(cudaStreamSynchronize(h->pub));
-    cudaFree(h->pub_d); h->pub_d = nullptr;
-    if (h->pub_h) { cudaFreeHost(h->pub_h); h->pub_h = nullptr; }
-    CU(cudaMalloc(&h->pub_d, (size_t)total * sizeof(float)));
-    CU(cudaHostAlloc(&h->pub_h, (size_t)total * sizeof(float), cudaHostAllocDefault));
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(h->pub_d[i]); h->pub_d[i] = nullptr;
+      if (h->pub_h[i]) { cudaFreeHost(h->pub_h[i]); h->pub_h[i] = nullptr; }
+      CU(cudaMalloc(&h->pub_d[i], (size_t)total * sizeof(float)));
+      CU(cudaHostAlloc(&h->pub_h[i], (size_t)total * sizeof(float), cudaHostAllocDefault));
+    }
     h->pub_cap = total;
+    h->pub_pending = 0;
   }
+  const int slot = h->pub_head;
   StreamBridge sb(h, stream);
   if (int rc = sb.begin()) return rc;
   const float* base = h->params + (size_t)replica * h->L.arena;
   int64_t at = 0;
   for (int i = 0; i < n_ranges; ++i) {
-    CU(cudaMemcpyAsync(h->pub_d + at, base + offsets[i], (size_t)counts[i] * sizeof(float), cudaMemcpyDeviceToDevice, sb.run));
+    CU(cudaMemcpyAsync(h->pub_d[slot] + at, base + offsets[i], (size_t)counts[i] * sizeof(float), cudaMemcpyDeviceToDevice, sb.run));
     at += counts[i];
   }
-  CU(cudaEventRecord(h->ev_pub_snap, sb.run));
+  CU(cudaEventRecord(h->ev_pub_snap[slot], sb.run));
   if (int rc = sb.end()) return rc;
-  CU(cudaStreamWaitEvent(h->pub, h->ev_pub_snap, 0));
-  CU(cudaMemcpyAsync(h->pub_h, h->pub_d, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, h->pub));
-  CU(cudaEventRecord(h->ev_pub_done, h->pub));
-  h->pub_n = total;
-  h->pub_pending = true;
+  CU(cudaStreamWaitEvent(h->pub, h->ev_pub_snap[slot], 0));
+  CU(cudaMemcpyAsync(h->pub_h[slot], h->pub_d[slot], (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, h->pub));
+  CU(cudaEventRecord(h->ev_pub_done[slot], h->pub));
+  h->pub_n[slot] = total;
+  h->pub_head ^= 1;
+  h->pub_pending += 1;
   return 0;
 }
 
 extern "C" int b200sac_publish_wait(b200sac_t* h, const float** host_ptr, int64_t* n_floats) {
   if (!h || !host_ptr || !n_floats) return fail(B200SAC_ERR_INVALID, "null argument");
-  if (!h->pub_pending) return fail(B200SAC_ERR_STATE, "publish_wait without publish_begin");
+  if (h->pub_pending <= 0) return fail(B200SAC_ERR_STATE, "publish_wait without publish_begin");
   CU(cudaSetDevice(h->device));
-  CU(cudaEventSynchronize(h->ev_pub_done));
-  h->pub_pending = false;
-  *host_ptr = h->pub_h;
-  *n_floats = h->pub_n;
+  const int slot = (h->pub_head + 2 - h->pub_pending) & 1;      // the oldest snapshot not collected yet
+  CU(cudaEventSynchronize(h->ev_pub_done[slot]));
+  h->pub_pending -= 1;
+  *host_ptr = h->pub_h[slot];
+  *n_floats = h->pub_n[slot];
   return 0;
 }
 

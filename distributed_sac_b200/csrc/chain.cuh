@@ -173,31 +173,50 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       if (k0 + CH_KC >= K4) { ic = 0; ++is; } else { ++ic; }
     }
   };
-  if (tid == 0 && live) {
-    if constexpr (FWD) asm volatile("prefetch.tensormap [%0];" ::"l"(J.st[0].tm + (long long)rep * J.st[0].rsTm) : "memory");
+  // weights that do not depend on the launch right before this one: the head matrix (cp.async) and, for a directly
+  // evaluated input layer, this thread's row of W0 + its bias (registers)
+  float4 wr0[CH_KC / 4];
+  float b00 = 0.f;
+  auto request_weights = [&]() {
+    if (J.NO > 0) {
+      const float* __restrict__ Wh = J.Wh + po;
+      const int q4 = J.Hh >> 2;
+      for (int e = tid; e < J.NO * q4; e += CH_THREADS) {
+        const int j = e / q4, q = e - j * q4;
+        cp_async16(headW + j * CH_INP + 4 * q, Wh + (long long)j * J.Hh + 4 * q);
+      }
+    }
+    if constexpr (FWD) {
+      if (direct0 && tid < J.st[0].N) {
+        const ChainStage& S = J.st[0];
+        const int K4 = (S.K + 3) & ~3;
+        const float4* __restrict__ wp = reinterpret_cast<const float4*>(S.W + po + (long long)tid * S.ldw);
 #pragma unroll
-    for (int i = 0; i < CH_NSTAGE; ++i) mbar_init(smem_u32(bars + i), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (A.early_weights) { issue_next(); issue_next(); }
+        for (int q = 0; q < CH_KC / 4; ++q) wr0[q] = (4 * q < K4) ? __ldg(wp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b00 = __ldg(S.bias + po + tid);
+      }
+    }
+  };
+  if (live) {
+    if (tid == 0) {
+      if constexpr (FWD) asm volatile("prefetch.tensormap [%0];" ::"l"(J.st[0].tm + (long long)rep * J.st[0].rsTm) : "memory");
+#pragma unroll
+      for (int i = 0; i < CH_NSTAGE; ++i) mbar_init(smem_u32(bars + i), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (A.early_weights) { issue_next(); issue_next(); }
+    }
+    if (A.early_weights) request_weights();
   }
   KStamp ks_;
   CH_STAMP();                              // 1: predecessor complete (griddepcontrol.wait)
   if (!live) return;
   __syncthreads();                         // barriers initialised
-  if (!A.early_weights) { issue_next(); issue_next(); }
+  if (!A.early_weights) { issue_next(); issue_next(); request_weights(); }
 
   float* In = actA;
   float* Out = actB;
 
-  // ---- prologue: head weights and (forward) the input rows go out as the first cp.async group --------------------------
-  if (J.NO > 0) {
-    const float* __restrict__ Wh = J.Wh + po;
-    const int q4 = J.Hh >> 2;
-    for (int e = tid; e < J.NO * q4; e += CH_THREADS) {
-      const int j = e / q4, q = e - j * q4;
-      cp_async16(headW + j * CH_INP + 4 * q, Wh + (long long)j * J.Hh + 4 * q);
-    }
-  }
+  // ---- prologue: (forward) the input rows join the head weights in the cp.async group ------------------------------------
   if constexpr (FWD) {
     const float* __restrict__ X = J.X + (long long)rep * J.rsX + (long long)row0 * J.ldx;
     const int k4 = (J.K0 + 3) >> 2;
@@ -223,12 +242,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
 #pragma unroll
       for (int m = 0; m < ROWS; ++m) hv[m] = (tid < J.Hh && m < nrows) ? hl[(long long)m * J.ldh + tid] : 0.f;
     }
-    if (J.kind == CJ_BWD_ACTORQ && J.nact > 0) {   // action columns of the first-layer weights for the tail
+    // action columns of the first-layer weights for the tail: requested now (registers), parked in shared memory after
+    // the d(head output) phase -- the strided gather's latency hides behind it instead of heading the critical path
+    float w0r[CH_MAXW * kMaxAct / CH_THREADS];
+    const bool want_w0a = J.kind == CJ_BWD_ACTORQ && J.nact > 0;
+    if (want_w0a) {
       const float* __restrict__ W0 = J.W0 + po;
-      const int H0 = J.H0;
-      for (int e = tid; e < H0 * kMaxAct; e += CH_THREADS) {
-        const int k = e >> 3, j = e & 7;
-        w0a[e] = j < J.nact ? __ldg(W0 + (long long)k * J.ldw0 + J.col0 + j) : 0.f;
+#pragma unroll
+      for (int i = 0; i < CH_MAXW * kMaxAct / CH_THREADS; ++i) {
+        const int e = tid + i * CH_THREADS, k = e >> 3, j = e & 7;
+        w0r[i] = (k < J.H0 && j < J.nact) ? __ldg(W0 + (long long)k * J.ldw0 + J.col0 + j) : 0.f;
       }
     }
     // the step's temperatures (<= 64 tasks) are requested by the lanes up front; the row's alpha[t] then comes from a
@@ -318,6 +341,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         In[m * CH_INP + tid] = v;
       }
     }
+    if (want_w0a) {
+#pragma unroll
+      for (int i = 0; i < CH_MAXW * kMaxAct / CH_THREADS; ++i) w0a[tid + i * CH_THREADS] = w0r[i];
+    }
     __syncthreads();                               // In (and the staged action columns) visible to every warp
   }
 
@@ -328,14 +355,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     if (direct0) {
       const ChainStage& S = J.st[0];
       const int N = S.N, K4 = (S.K + 3) & ~3;
-      float4 wr[CH_KC / 4];
-      float b0 = 0.f;
-      if (tid < N) {
-        const float4* __restrict__ wp = reinterpret_cast<const float4*>(S.W + po + (long long)tid * S.ldw);
-#pragma unroll
-        for (int q = 0; q < CH_KC / 4; ++q) wr[q] = (4 * q < K4) ? __ldg(wp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        b0 = __ldg(S.bias + po + tid);
-      }
+      const float4 (&wr)[CH_KC / 4] = wr0;          // this thread's row of W0, requested in the prologue
+      const float b0 = b00;
       cp_async_wait<0>();
       __syncthreads();                  // the input rows are in shared memory
       if (tid < N) {

@@ -177,7 +177,9 @@ class _BaseLearner:
         """Start an asynchronous snapshot of the published modules (b200sac_publish_begin): a device-side copy in
         stream order after the steps enqueued so far, then D2H into pinned memory on a private stream."""
         self._pub_maps = [(net, self._key_map(net)) for net in self._published]
-        self.core.publish_begin({canon for _, m in self._pub_maps for canon in m.values()})
+        # (+ the temperature: the logger's alpha then comes from the same consistent snapshot, not from a second,
+        #  stream-ordered read that would wait for whatever step is running by then)
+        self.core.publish_begin({canon for _, m in self._pub_maps for canon in m.values()} | {"log_alpha"})
 
     def publish_wait(self):
         named = self.core.publish_wait()
@@ -197,7 +199,9 @@ class _BaseLearner:
         blocking=True: take the snapshot now (get_parameters semantics); else collect the one started by publish_begin()."""
         if blocking:
             self.publish_begin()
-        views = self.core.publish_views()
+        return self._blob_from_views(self.core.publish_views())
+
+    def _blob_from_views(self, views):
         tpl = getattr(self, "_blob_tpl", None)
         if tpl is None:
             rng = np.random.default_rng(12345)
@@ -317,12 +321,12 @@ class _BaseLearner:
             self.alpha = ck["alpha"].detach().reshape(-1).clone()
 
     # ---- Redis-facing loop (LL/learner.py:191-201,278-316) -------------------------------------
-    def write(self, update_iteration, critic_loss, actor_loss, entropy=None):
+    def write(self, update_iteration, critic_loss, actor_loss, entropy=None, log_alpha=None):
         self.server.rpush("critic_loss", _pickle.dumps((update_iteration, critic_loss)))
         self.server.rpush("actor_loss", _pickle.dumps((update_iteration, actor_loss)))
         if entropy is not None:
             self.server.rpush("entropy", _pickle.dumps((update_iteration, entropy)))
-        alphas = self.log_alpha.exp().numpy()
+        alphas = np.exp(np.array(log_alpha, dtype=np.float32)) if log_alpha is not None else self.log_alpha.exp().numpy()
         self.server.rpush("alpha", _pickle.dumps((update_iteration, alphas)))
 
     def run(self, max_updates=None):
@@ -331,24 +335,34 @@ class _BaseLearner:
         self.wait_until_memoryReady()
         self.my_print("######################### Start train #########################")
         self.soft_update(None, None, 1.0)           # copy parameters to target
+        # Pipelined like this: while the GPU runs step k+1 (enqueued together with its snapshot), the host turns snapshot k
+        # into the published blob and talks to Redis -- the reference does the same things strictly one after the other
+        # (learner.py:296-316).  Two snapshot slots in the library make that safe.
         done = 0
-        for update_iteration in itertools.count():
-            if update_iteration % self.update_delay != 0:
-                continue
-            self.memory.enqueue_step(self.core)        # update(), split so the snapshot's D2H overlaps the loss read
-            self.publish_begin()
-            res = self._loss_tuple(self.core.read_losses(1)[0])
-            self.server.set("update_iteration", _pickle.dumps(update_iteration))
-            self.server.set("parameters", self.parameters_blob())
+        iters = (i for i in itertools.count() if i % self.update_delay == 0)
+        update_iteration = next(iters)
+        self.memory.enqueue_step(self.core)            # update(), split so that everything below overlaps the GPU
+        self.publish_begin()
+        while True:
+            cur = update_iteration
+            res = self._loss_tuple(self.core.read_losses(1)[0])        # step `cur` has finished
+            views = self.core.publish_views()                            # ... and so has its snapshot
+            last = max_updates is not None and done + 1 >= max_updates
+            if cur % self.save_period == 0:
+                self.save_checkpoint(cur)              # before step cur+1 is enqueued: the arena is the state after `cur`
+            if not last:
+                update_iteration = next(iters)
+                self.memory.enqueue_step(self.core)
+                self.publish_begin()
+            self.server.set("update_iteration", _pickle.dumps(cur))
+            self.server.set("parameters", self._blob_from_views(views))
             if self.write_mode:
-                self.write(update_iteration, *res)
-                if update_iteration % self.print_period == 0:
+                self.write(cur, *res, log_alpha=views.get("log_alpha"))
+                if cur % self.print_period == 0:
                     self.my_print("[Learner] Update_iteration: {0:<6} \t | actor_loss : {1:5.3f} \t | critic_loss : {2:5.3f}".format(
-                        update_iteration, res[1], res[0]))
-            if update_iteration % self.save_period == 0:
-                self.save_checkpoint(update_iteration)
+                        cur, res[1], res[0]))
             done += 1
-            if max_updates is not None and done >= max_updates:
+            if last:
                 return done
 
 

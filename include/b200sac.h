@@ -191,8 +191,10 @@ int b200sac_act(b200sac_t* h, int32_t replica, int32_t n, const float* obs, cons
  * publish_begin enqueues, in stream order, a consistent device snapshot of `n_ranges` ranges
  * [offsets[i], offsets[i]+counts[i]) of replica `replica`'s parameter arena (offsets from b200sac_layout)
  * and starts its copy to pinned host memory on a private stream; it does not block, and steps enqueued
- * afterwards overlap the copy.  publish_wait blocks until that copy has landed and returns the packed
- * ranges; the pointer is owned by the handle and valid until the next publish_begin. */
+ * afterwards overlap the copy.  publish_wait blocks until the OLDEST uncollected snapshot has landed and returns its
+ * packed ranges.  Two snapshot slots: publish_begin may be called again before the previous snapshot is collected (the
+ * caller then turns snapshot k into the published blob while step k+1 runs and snapshot k+1 lands); the pointer stays
+ * valid until the second publish_begin after the one that produced it.  A third begin without a wait supersedes the oldest. */
 int b200sac_publish_begin(b200sac_t* h, int32_t replica, int32_t n_ranges, const int64_t* offsets, const int64_t* counts,
                           void* stream);
 int b200sac_publish_wait(b200sac_t* h, const float** host_ptr, int64_t* n_floats);
