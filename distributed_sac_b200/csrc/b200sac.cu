@@ -26,6 +26,7 @@
 #include "sac_kernels.cuh"
 #include "care_kernels.cuh"
 #include "chain.cuh"
+#include "chain2.cuh"
 
 using namespace bsac;
 
@@ -214,7 +215,7 @@ struct Buf {           // [R][n] fp32 (or int32) slab slice
   long long rs = 0;    // replica stride in floats
 };
 
-enum LaunchKind { L_POLICY_DOUT, L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_THIN, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM, L_CHAIN, L_WGRAD };
+enum LaunchKind { L_POLICY_DOUT, L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_THIN, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM, L_CHAIN, L_WGRAD, L_CHAIN2 };
 
 struct Launch {
   LaunchKind kind;
@@ -239,6 +240,7 @@ struct Launch {
   HeadBwdArgs hb;
   AdamArgs ad;
   ChainArgs chain;
+  Chain2Args chain2;
   WgradArgs wg;
   const char* label = nullptr;
 };
@@ -638,23 +640,83 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
     h->use_eps_buf_idx = (int)h->plan.size();
     finish_chain(l);
   }
-  // ---- B: target critics over (s', a') -------------------------------------------------------------------------------
-  {
-    Launch l = new_chain("chain_fwd{qt1,qt2}");
-    l.chain.njobs = 2;
+  // Twin forward + backward in one clustered launch (chain2.cuh) when the critic is shallow enough for its stage tables
+  const bool pair = Lc <= C2_MAXL && getenv("B200SAC_NO_CLUSTER") == nullptr;
+  auto pair_launch = [&](const char* label, int kind, int early, const std::vector<LayerOff>* fnet /* [2] */, const float* X, long long rsX,
+                         const std::vector<Buf>* fstore, const Buf& qf, const std::vector<Buf>& acts, const std::vector<Buf>* dstore,
+                         bool tail) {
+    Launch l;
+    l.kind = L_CHAIN2;
+    l.label = label;
+    memset(&l.chain2, 0, sizeof(l.chain2));
+    Chain2Args& P = l.chain2;
+    P.kind = kind; P.rsP = rsP; P.rw = rw;
+    P.early_weights = (early && getenv("B200SAC_NO_EARLY_WEIGHTS") == nullptr) ? 1 : 0;
     for (int net = 0; net < 2; ++net) {
-      ChainJob& J = l.chain.job[net];
-      fwd_job(J, L.qt[net], Lc, h->XT.p, h->XT.rs, h->K.ldx, h->K.xw, B, nullptr, net, B);
-      J.head = CH_HEAD_SCALAR; J.qout = h->qt.p + (long long)net * B; J.rsQ = h->qt.rs;
+      Chain2Job& J = P.job[net];
+      J.rows = B; J.nfwd = Lc; J.nbwd = Lc - 1; J.net = net;
+      J.X = X; J.rsX = rsX; J.ldx = h->K.ldx; J.K0 = h->K.xw;
+      for (int lyr = 0; lyr < Lc; ++lyr) {
+        const LayerOff& lo = fnet[net][lyr];
+        ChainStage& S = J.fst[lyr];
+        S.W = W(lo.w); S.bias = W(lo.b); S.ldw = lo.ld; S.K = lo.in; S.N = lo.out;
+        S.tm_idx = (int)fmaps.size();
+        fmaps.push_back(FMap{lo.w, lo.in, lo.out, lo.ld});
+        if (fstore) { S.out = (*fstore)[lyr].p + (long long)net * B * lo.out; S.rsOut = (*fstore)[lyr].rs; S.ldo = lo.out; }
+      }
+      const LayerOff& fh = fnet[net][Lc];
+      J.Whf = W(fh.w); J.bhf = W(fh.b); J.Hhf = fh.in;
+      J.qf_out = qf.p + (long long)net * B; J.rsQf = qf.rs;
+      // backward through the LOCAL twin
+      const std::vector<LayerOff>& bn = L.q[net];
+      const int Hl = bn[Lc - 1].out;
+      J.hlast = acts[Lc - 1].p + (long long)net * B * Hl; J.rsHlast = acts[Lc - 1].rs; J.ldh = Hl;
+      if (dstore) { J.dylast = (*dstore)[Lc - 1].p + (long long)net * B * Hl; J.rsDy = (*dstore)[Lc - 1].rs; J.lddy = Hl; }
+      J.Whb = W(bn[Lc].w); J.Hhb = bn[Lc].in;
+      for (int sidx = 0; sidx + 1 < Lc; ++sidx) {
+        const int lyr = Lc - 1 - sidx;
+        const LayerOff& lo = bn[lyr];
+        ChainStage& S = J.bst[sidx];
+        S.W = W(lo.w); S.ldw = lo.ld; S.K = lo.out; S.N = lo.in;
+        S.mask = acts[lyr - 1].p + (long long)net * B * lo.in; S.rsMask = acts[lyr - 1].rs; S.ldmask = lo.in;
+        if (dstore) { S.out = (*dstore)[lyr - 1].p + (long long)net * B * lo.in; S.rsOut = (*dstore)[lyr - 1].rs; S.ldo = lo.in; }
+      }
+      if (tail) {
+        const LayerOff& lo = bn[0];
+        J.W0 = W(lo.w); J.ldw0 = lo.ld; J.col0 = h->K.in_w; J.nact = A; J.H0 = lo.out;
+        J.dx = h->dxP.p + (long long)net * B * h->K.ldx; J.rsDx = h->dxP.rs; J.lddx = h->K.ldx;
+      }
     }
-    finish_chain(l);
-  }
-  // ---- C: critic backward, weight gradients, Adam + Polyak -------------------------------------------------------------
-  {
+    if (h->chain_dbg && h->plan.size() < 16) P.dbg = h->chain_dbg + h->plan.size() * CH_DBG_SLOTS;
+    l.bn = 8;
+    for (int rows = 4; rows >= 2; rows >>= 1)
+      if ((long long)2 * ((B + rows - 1) / rows) * R <= 148) l.bn = rows;
+    if (const char* e = getenv("B200SAC_CHAIN_ROWS")) { const int v = atoi(e); l.bn = (v == 2 || v == 4) ? v : 8; }
+    l.grid = dim3((B + l.bn - 1) / l.bn, 2, R);
+    l.block = dim3(CH_THREADS);
+    l.smem = C2_SMEM_BYTES;
+    h->plan.push_back(l);
+  };
+  // ---- B + C: target critics over (s', a'), TD target, critic backward (one clustered launch), weight gradients, Adam ----
+  if (pair) {
+    pair_launch("chain2{qt->y->bwd q}", C2_CRITIC, 1, L.qt, h->XT.p, h->XT.rs, nullptr, h->qt, h->hQ, &h->dhQ, false);
+  } else {
+    {
+      Launch l = new_chain("chain_fwd{qt1,qt2}");
+      l.chain.njobs = 2;
+      for (int net = 0; net < 2; ++net) {
+        ChainJob& J = l.chain.job[net];
+        fwd_job(J, L.qt[net], Lc, h->XT.p, h->XT.rs, h->K.ldx, h->K.xw, B, nullptr, net, B);
+        J.head = CH_HEAD_SCALAR; J.qout = h->qt.p + (long long)net * B; J.rsQ = h->qt.rs;
+      }
+      finish_chain(l);
+    }
     Launch l = new_chain("chain_bwd{q1,q2}");
     l.chain.njobs = 2;
     for (int net = 0; net < 2; ++net) bwd_job(l.chain.job[net], CJ_BWD_CRITIC, L.q[net], Lc, B, h->hQ, 0, &h->dhQ, net);
     finish_chain(l);
+  }
+  {
     std::vector<WNet> nets;
     for (int net = 0; net < 2; ++net)
       nets.push_back(WNet{&L.q[net], Lc, &h->dhQ, &h->hQ, 0, h->XQ.p, h->XQ.rs, h->K.ldx, h->dq.p + (long long)net * B, h->dq.rs, 1, net});
@@ -663,26 +725,31 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
   }
   // ---- D: actor pass through the updated critics ------------------------------------------------------------------------
   {
-    // (the launch right before this one is the critic Adam: no weight request before the dependency wait)
-    Launch l = new_chain("chain_fwd{q1,q2}(s,a~)", 0);
-    l.chain.njobs = 2;
-    for (int net = 0; net < 2; ++net) {
-      ChainJob& J = l.chain.job[net];
-      fwd_job(J, L.q[net], Lc, h->XP.p, h->XP.rs, h->K.ldx, h->K.xw, B, &h->hP, net, B);
-      J.head = CH_HEAD_SCALAR; J.qout = h->qp.p + (long long)net * B; J.rsQ = h->qp.rs;
+    if (pair) {
+      // (the launch right before this one is the critic Adam: no weight request before the dependency wait)
+      pair_launch("chain2{q(s,a~)->min->bwd->d(action)}", C2_ACTORQ, 0, L.q, h->XP.p, h->XP.rs, &h->hP, h->qp, h->hP, nullptr, true);
+    } else {
+      // (the launch right before this one is the critic Adam: no weight request before the dependency wait)
+      Launch l = new_chain("chain_fwd{q1,q2}(s,a~)", 0);
+      l.chain.njobs = 2;
+      for (int net = 0; net < 2; ++net) {
+        ChainJob& J = l.chain.job[net];
+        fwd_job(J, L.q[net], Lc, h->XP.p, h->XP.rs, h->K.ldx, h->K.xw, B, &h->hP, net, B);
+        J.head = CH_HEAD_SCALAR; J.qout = h->qp.p + (long long)net * B; J.rsQ = h->qp.rs;
+      }
+      finish_chain(l);
+      Launch l2 = new_chain("chain_bwd{q1,q2}->d(action)");
+      l2.chain.njobs = 2;
+      for (int net = 0; net < 2; ++net) {
+        ChainJob& J = l2.chain.job[net];
+        bwd_job(J, CJ_BWD_ACTORQ, L.q[net], Lc, B, h->hP, 0, nullptr, net);
+        const LayerOff& lo = L.q[net][0];
+        J.head = CH_TAIL_DACTION;
+        J.W0 = W(lo.w); J.ldw0 = lo.ld; J.col0 = h->K.in_w; J.nact = A; J.H0 = lo.out;
+        J.dx = h->dxP.p + (long long)net * B * h->K.ldx; J.rsDx = h->dxP.rs; J.lddx = h->K.ldx;
+      }
+      finish_chain(l2);
     }
-    finish_chain(l);
-    Launch l2 = new_chain("chain_bwd{q1,q2}->d(action)");
-    l2.chain.njobs = 2;
-    for (int net = 0; net < 2; ++net) {
-      ChainJob& J = l2.chain.job[net];
-      bwd_job(J, CJ_BWD_ACTORQ, L.q[net], Lc, B, h->hP, 0, nullptr, net);
-      const LayerOff& lo = L.q[net][0];
-      J.head = CH_TAIL_DACTION;
-      J.W0 = W(lo.w); J.ldw0 = lo.ld; J.col0 = h->K.in_w; J.nact = A; J.H0 = lo.out;
-      J.dx = h->dxP.p + (long long)net * B * h->K.ldx; J.rsDx = h->dxP.rs; J.lddx = h->K.ldx;
-    }
-    finish_chain(l2);
     // actor loss / entropy / temperature gradient + its Adam step need only what D produced (the step's alpha is the
     // snapshot taken at ingest): they run on the fork stream beside the policy backward instead of trailing the actor Adam
     adam(1, 2);
@@ -710,7 +777,7 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
           return rc;
     CU(cudaMalloc(&h->d_cmaps, maps.size() * sizeof(CUtensorMap)));
     CU(cudaMemcpy(h->d_cmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-    for (auto& l : h->plan)
+    for (auto& l : h->plan) {
       if (l.kind == L_CHAIN)
         for (int j = 0; j < l.chain.njobs; ++j)
           if (l.chain.job[j].kind == CJ_FWD)
@@ -719,7 +786,18 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
               S.tm = h->d_cmaps + S.tm_idx;
               S.rsTm = n;
             }
+      if (l.kind == L_CHAIN2)
+        for (int j = 0; j < 2; ++j)
+          for (int st = 0; st < l.chain2.job[j].nfwd; ++st) {
+            ChainStage& S = l.chain2.job[j].fst[st];
+            S.tm = h->d_cmaps + S.tm_idx;
+            S.rsTm = n;
+          }
+    }
   }
+  CU(cudaFuncSetAttribute(chain2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(chain2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(chain2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2_SMEM_BYTES));
   {  // weight-gradient operand maps [R][n]: [B rows][cols] row-major, box {32 cols, 256 rows}, dense
     const int n = (int)wmaps.size();
     std::vector<CUtensorMap> maps((size_t)R * n);
@@ -1396,6 +1474,23 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// the same with a thread-block cluster of (1, 2, 1): the two CTAs with equal blockIdx.x / z are co-scheduled and can read
+// each other's shared memory
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pair_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* evs = nullptr, bool allow_fork = false) {
   bool fork_pending = false;
   for (size_t i = 0; i < h->plan.size(); ++i) {
@@ -1478,6 +1573,11 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
       }
       case L_WGRAD:
         launch_k(wgrad_kernel, l.grid, l.block, l.smem, s, l.wg);
+        break;
+      case L_CHAIN2:
+        if (l.bn == 8) launch_pair_k(chain2_kernel<8>, l.grid, l.block, l.smem, s, l.chain2, h->K);
+        else if (l.bn == 4) launch_pair_k(chain2_kernel<4>, l.grid, l.block, l.smem, s, l.chain2, h->K);
+        else launch_pair_k(chain2_kernel<2>, l.grid, l.block, l.smem, s, l.chain2, h->K);
         break;
     }
     if (forked) {
@@ -2181,6 +2281,7 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
     case L_AQHEADS: return "actor_q_heads";
     case L_HEADBWD: return (l.hb.policy_mode || l.hb.NO > 1) ? "head_bwd(policy)" : "head_bwd(q)";
     case L_CHAIN:
+    case L_CHAIN2:
     case L_WGRAD: return l.label ? l.label : "chain";
     case L_ADAM:
       if (l.ad.which == 1 && l.branch == 1) return "alpha+losses(forked)";
