@@ -577,12 +577,22 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
   // weight-gradient launch of a group of networks
   struct WNet { const std::vector<LayerOff>* net; int nh; const std::vector<Buf>* dstore; const std::vector<Buf>* acts; long long act_row_off;
                 const float* X; long long rsX; int ldx; const float* dout; long long rsDout; int lddout; int net_idx; };
-  auto wgrad_launch = [&](const std::vector<WNet>& nets, const char* label) -> int {
+  const bool fuse_adam = getenv("B200SAC_NO_FUSED_ADAM") == nullptr;
+  auto wgrad_launch = [&](const std::vector<WNet>& nets, const char* label, int which) -> int {
     Launch l;
     l.kind = L_WGRAD;
     l.label = label;
     memset(&l.wg, 0, sizeof(l.wg));
     l.wg.M = B; l.wg.rsG = rsG;
+    if (fuse_adam) {                             // the CTA that reduces a gradient tile applies Adam (+ Polyak) to it
+      WgradAdam& O = l.wg.adam;
+      O.enabled = 1; O.which = which;
+      O.params = h->params; O.m = h->adam_m; O.v = h->adam_v; O.grads = h->grads;
+      O.rsP = rsP; O.rsM = rsG;
+      O.target_delta = which == 0 ? L.target_delta : 0;
+      O.lr = which == 0 ? c.lr_critic : c.lr_actor;
+      O.cnt = h->cnt;
+    }
     int tiles = 0;
     auto add = [&](const float* Ap, long long rsA, int lda, const float* Bp, long long rsB, int ldb, int64_t offW, int ldc, int64_t offB,
                    int Kout, int Nin) -> int {
@@ -720,8 +730,8 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
     std::vector<WNet> nets;
     for (int net = 0; net < 2; ++net)
       nets.push_back(WNet{&L.q[net], Lc, &h->dhQ, &h->hQ, 0, h->XQ.p, h->XQ.rs, h->K.ldx, h->dq.p + (long long)net * B, h->dq.rs, 1, net});
-    if (int rc = wgrad_launch(nets, "wgrad{q1,q2}")) return rc;
-    adam(0, 0);
+    if (int rc = wgrad_launch(nets, fuse_adam ? "wgrad+adam+polyak{q1,q2}" : "wgrad{q1,q2}", 0)) return rc;
+    if (!fuse_adam) adam(0, 0);
   }
   // ---- D: actor pass through the updated critics ------------------------------------------------------------------------
   {
@@ -752,7 +762,7 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
     }
     // actor loss / entropy / temperature gradient + its Adam step need only what D produced (the step's alpha is the
     // snapshot taken at ingest): they run on the fork stream beside the policy backward instead of trailing the actor Adam
-    adam(1, 2);
+    adam(1, fuse_adam ? 3 : 2);
   }
   // ---- E: policy backward, weight gradients, Adam + temperature ------------------------------------------------------------
   {
@@ -763,8 +773,8 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
     std::vector<WNet> nets;
     nets.push_back(WNet{&L.actor, La, &h->dhA, &h->hA, (long long)B, h->XA.p + (long long)B * h->K.ldxa, h->XA.rs, h->K.ldxa,
                         h->dout_dbg.p, h->dout_dbg.rs, 2 * A, 0});
-    if (int rc = wgrad_launch(nets, "wgrad{actor}")) return rc;
-    adam(1, 1);
+    if (int rc = wgrad_launch(nets, fuse_adam ? "wgrad+adam{actor}" : "wgrad{actor}", 1)) return rc;
+    if (!fuse_adam) adam(1, 1);
   }
   (void)Hc; (void)Ha;
   {  // tensor maps [R][n]: W [N][K] row-major (pitch ld), box {32 k, N rows}, SWIZZLE_128B, OOB k zero-filled
@@ -1093,7 +1103,8 @@ static int build_plan(b200sac* h) {
     P.logstd_sum = h->logstd.p;
     P.cnt = h->cnt;
   }
-  // mode 0: parameter update + the tail job (last CTA); 1: parameter update only; 2: the tail job alone, on the fork stream
+  // mode 0: parameter update + the tail job (last CTA); 1: parameter update only; 2 / 3: the tail job alone, on the fork
+  // stream (3: + the critic-loss reduction, for plans whose critic Adam is fused into the weight-gradient launch)
   auto adam = [&](int which, int mode) {
     Launch l;
     l.kind = L_ADAM;
@@ -1112,6 +1123,7 @@ static int build_plan(b200sac* h) {
     P.cnt = h->cnt;
     P.tail = which == 0 ? TAIL_CRITIC_LOSS : (which == 1 ? TAIL_ALPHA_AND_LOSSES : TAIL_NONE);
     if (mode == 1) P.tail = TAIL_NONE;
+    if (mode == 3) P.tail = TAIL_ALL;              // forked tail that also reduces the critic loss (no critic Adam launch)
     P.lq = h->lq.p; P.la = h->la.p; P.rsY = h->y.rs;
     P.logp_cur = h->logp.p + B; P.logstd_sum = h->logstd.p + B; P.rsLogp = h->logp.rs;
     P.tid = (const int*)h->tid.p; P.rsR = h->r.rs;
@@ -1124,7 +1136,7 @@ static int build_plan(b200sac* h) {
     l.grid = dim3(nb + (P.tail != TAIL_NONE ? 1 : 0), R);
     l.block = dim3(256);
     l.join = true;                 // every gradient of the slice must have landed, including the forked weight gradients
-    if (mode == 2) { l.grid = dim3(1, R); l.join = false; l.branch = 1; }
+    if (mode == 2 || mode == 3) { l.grid = dim3(1, R); l.join = false; l.branch = 1; }
     h->plan.push_back(l);
   };
   if (h->fused) {
@@ -1572,7 +1584,7 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
         break;
       }
       case L_WGRAD:
-        launch_k(wgrad_kernel, l.grid, l.block, l.smem, s, l.wg);
+        launch_k(wgrad_kernel, l.grid, l.block, l.smem, s, l.wg, h->K);
         break;
       case L_CHAIN2:
         if (l.bn == 8) launch_pair_k(chain2_kernel<8>, l.grid, l.block, l.smem, s, l.chain2, h->K);

@@ -624,9 +624,22 @@ struct WgradJob {
   int shape;
   int tmA_idx, tmB_idx, rsTm;              // (host: indices into the map table; replica r at tm + r * rsTm)
 };
+// Optional Adam (+ Polyak) applied by the CTA that just reduced a gradient tile: the gradient value is final the moment the
+// tile's fixed-order sum is done, so the separate optimizer launch (one more kernel boundary + a cold pass over p/m/v) is
+// unnecessary.  Same element-wise math as adam_kernel (adam_one, torch _single_tensor_adam).
+struct WgradAdam {
+  int enabled, which;                      // which: Adam step-counter slot (0 critic, 1 actor)
+  float* params; float* m; float* v;       // arenas; an element's index = its offset in the gradient arena
+  const float* grads;                      // gradient arena base (to turn C pointers into offsets)
+  long long rsP, rsM;
+  long long target_delta;                  // != 0: params[i + target_delta] is the Polyak target of element i
+  double lr;
+  const Counters* cnt;
+};
 struct WgradArgs {
   int njobs, M;
   long long rsG;
+  WgradAdam adam;
   WgradJob job[WG_MAXJOBS];
 };
 
@@ -646,7 +659,7 @@ B200_D void wg_stage(float* __restrict__ dst, const float* __restrict__ src, int
   }
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_constant__ WgradArgs A) {
+__global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_constant__ WgradArgs A, StepConst K) {
   extern __shared__ __align__(128) float wsm_raw[];
   float* sm = wsm_raw + (((128u - (smem_u32(wsm_raw) & 127u)) & 127u) >> 2);      // (pointer arithmetic keeps the shared address space)
   int ji = 0;
@@ -773,6 +786,20 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
   }
   __syncthreads();
   float* __restrict__ C = J.C + (long long)rep * A.rsG;
+  // fused optimizer step: bias corrections once per CTA (doubles), then adam_one per element like adam_kernel
+  const WgradAdam& O = A.adam;
+  float step_size = 0.f, bc2_sqrt = 1.f;
+  if (O.enabled) adam_scalars(O.lr, O.cnt[rep].b1p[O.which], O.cnt[rep].b2p[O.which], step_size, bc2_sqrt);
+  const float w1 = (float)(1.0 - K.beta1), b2 = (float)K.beta2, omb2 = (float)(1.0 - K.beta2), eps = (float)K.adam_eps;
+  auto apply = [&](long long gi, float g) {          // gi: index inside the trainable arena
+    float* pp = O.params + rep * O.rsP + gi;
+    float* mp = O.m + rep * O.rsM + gi;
+    float* vp = O.v + rep * O.rsM + gi;
+    float pv = *pp, mv = *mp, vv = *vp;
+    adam_one(pv, mv, vv, g, w1, b2, omb2, step_size, bc2_sqrt, eps);
+    *pp = pv; *mp = mv; *vp = vv;
+    if (O.target_delta != 0) pp[O.target_delta] = K.tau * pv + K.one_minus_tau * pp[O.target_delta];
+  };
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int o = tid + WG_THREADS * u;
@@ -781,7 +808,9 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
       float v = 0.f;
 #pragma unroll
       for (int ww = 0; ww < 8; ++ww) v += part[ww * (WG_T * WG_T) + o];
-      C[(long long)(k0 + kk) * J.ldc + n0 + nn] = v;
+      const long long ci = (long long)(k0 + kk) * J.ldc + n0 + nn;
+      C[ci] = v;
+      if (O.enabled) apply((J.C - O.grads) + ci, v);
     }
   }
   if (bn == 0 && J.C2 != nullptr && tid < WG_T && k0 + tid < J.Kout) {
@@ -789,6 +818,7 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
 #pragma unroll
     for (int ww = 0; ww < 8; ++ww) v += bpart[ww * WG_T + tid];
     (J.C2 + (long long)rep * A.rsG)[k0 + tid] = v;
+    if (O.enabled) apply((J.C2 - O.grads) + k0 + tid, v);
   }
 }
 

@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
 // write here is exactly equivalent to the reference's end-of-step soft_update.
 // The extra last CTA runs a "tail job": scalar reductions that must be deterministic.
 // ------------------------------------------------------------------------------------------
-enum { TAIL_NONE = 0, TAIL_CRITIC_LOSS = 1, TAIL_ALPHA_AND_LOSSES = 2 };
+enum { TAIL_NONE = 0, TAIL_CRITIC_LOSS = 1, TAIL_ALPHA_AND_LOSSES = 2, TAIL_ALL = 3 };   // ALL = critic loss + actor loss / entropy / temperature
 
 struct AdamArgs {
   float* p; float* m; float* v; const float* g;     // slice bases (replica 0)
@@ -811,12 +811,12 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
   const long long slot = (P.cnt[rep].v[3] - 1) % kLossSlots;
   float* L = P.losses + ((long long)slot * P.R + rep) * 4;
   float* LH = P.losses_host + ((long long)slot * P.R + rep) * 4;
-  if (P.tail == TAIL_CRITIC_LOSS) {
+  if (P.tail == TAIL_CRITIC_LOSS || P.tail == TAIL_ALL) {
     float s = 0.f, dummy;
     for (int i = tid; i < B; i += 256) s += (P.lq + rep * P.rsY)[i];
     block_sum2(s, 0.f, s, dummy);
     if (tid == 0) { L[0] = s * K.c_loss; LH[0] = L[0]; }
-    return;
+    if (P.tail == TAIL_CRITIC_LOSS) return;
   }
   // TAIL_ALPHA_AND_LOSSES: actor loss, entropy, temperature gradient + its Adam step
   {
