@@ -226,6 +226,56 @@ class SacCore:
         flat = np.ctypeslib.as_array(ptr, shape=(n.value,))       # view of the pinned buffer; _unpack copies out of it
         return {name: self._unpack(name, flat, at) for name, at in self._pub_where.items()}
 
+    # ---- blob publication (b200sac_blob_*): the published byte string is assembled on the device -------------------
+    def tensor_shape(self, name):
+        """Shape of tensor `name` as the reference's state_dict holds it."""
+        off, rows, _cols, _t, _o, pitch = self.table[name]
+        return tuple(self._view(name, np.broadcast_to(np.float32(0), (off + rows * pitch,)), off).shape)
+
+    def blob_index_map(self, name) -> np.ndarray:
+        """Arena index of every element of tensor `name`, in the reference's shape and C order (pitch padding and the
+        CARE mixture transposition are resolved here, once)."""
+        off, rows, _cols, _t, _o, pitch = self.table[name]
+        idx = np.arange(off + rows * pitch, dtype=np.int64)
+        return np.ascontiguousarray(self._view(name, idx, off)).reshape(-1)
+
+    def blob_template(self, image: bytes, slots, extra=(), replica=0):
+        """Register the byte image.  slots: [(tensor name, byte offset of its payload inside `image`)]; extra: tensor names
+        whose floats are appended BEHIND the image bytes (4-byte aligned; e.g. log_alpha for the logger) and returned by
+        blob_wait() as numpy arrays."""
+        src, dst = [], []
+        for name, at in slots:
+            m = self.blob_index_map(name)
+            src.append(m)
+            dst.append(at + 4 * np.arange(m.size, dtype=np.int64))
+        total = (len(image) + 3) & ~3
+        self._blob_extra = []
+        for name in extra:
+            m = self.blob_index_map(name)
+            src.append(m)
+            dst.append(total + 4 * np.arange(m.size, dtype=np.int64))
+            self._blob_extra.append((name, total, m.size))
+            total += 4 * m.size
+        src = np.ascontiguousarray(np.concatenate(src), dtype=np.int32)
+        dst = np.ascontiguousarray(np.concatenate(dst), dtype=np.int32)
+        img = np.zeros(total, dtype=np.uint8)
+        img[:len(image)] = np.frombuffer(image, dtype=np.uint8)
+        _lib.check(self.lib.b200sac_blob_template(self._h, replica, C.c_void_p(img.ctypes.data), total, src.size,
+                                                  C.c_void_p(src.ctypes.data), C.c_void_p(dst.ctypes.data)))
+        self._blob_len = len(image)
+
+    def blob_begin(self):
+        _lib.check(self.lib.b200sac_blob_begin(self._h, _stream()))
+
+    def blob_wait(self):
+        """(published bytes, {extra tensor name: float32 array}) of the oldest blob begun and not yet collected."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.b200sac_blob_wait(self._h, C.byref(ptr), C.byref(n)))
+        blob = C.string_at(ptr.value, self._blob_len)
+        extra = {name: np.ctypeslib.as_array(C.cast(ptr.value + at, C.POINTER(C.c_float)), shape=(cnt,)).copy()
+                 for name, at, cnt in self._blob_extra}
+        return blob, extra
+
     def get_named(self, which=_lib.PARAMS, replica=0) -> Dict[str, torch.Tensor]:
         flat = self.export_arena(which, replica).numpy()
         return {name: self._unpack(name, flat, d[0]) for name, d in self.table.items() if which == _lib.PARAMS or d[3]}

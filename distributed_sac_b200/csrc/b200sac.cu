@@ -319,6 +319,15 @@ struct b200sac {
   float* pub_h[2] = {nullptr, nullptr};   // pinned host copies handed to the caller
   int64_t pub_cap = 0, pub_n[2] = {0, 0};
   int pub_head = 0, pub_pending = 0;      // next slot to fill; snapshots begun and not yet collected (<= 2)
+  // blob publication (b200sac_blob_*): the published byte string is assembled ON THE DEVICE (constant bytes + float payloads
+  // gathered from the arena by a kernel) and crosses PCIe as one copy; the host never touches individual tensors
+  uint8_t* blob_d[2] = {nullptr, nullptr};
+  uint8_t* blob_h[2] = {nullptr, nullptr};
+  int* blob_src = nullptr;                // [blob_nf] arena index of payload float j
+  int* blob_dst = nullptr;                // [blob_nf] byte offset of payload float j inside the image
+  int64_t blob_bytes = 0, blob_nf = 0;
+  int blob_replica = 0, blob_head = 0, blob_pending = 0;
+  cudaEvent_t ev_blob_snap[2] = {nullptr, nullptr}, ev_blob_done[2] = {nullptr, nullptr};
   CUtensorMap* d_wmaps = nullptr; // layer-chained plan: 2-D maps of the weight-gradient operands, [R][maps per learner]
   CUtensorMap* d_cmaps = nullptr; // layer-chained plan: 2-D tensor maps of the forward weight matrices, [R][maps per learner]
   long long* chain_dbg = nullptr; // B200SAC_CHAIN_DBG=1: [plan launches][CH_DBG_SLOTS] clock64 timelines of the chain kernels
@@ -376,7 +385,13 @@ static int destroy_impl(b200sac* h) {
     if (h->ev_pub_done[i]) cudaEventDestroy(h->ev_pub_done[i]);
     cudaFree(h->pub_d[i]);
     if (h->pub_h[i]) cudaFreeHost(h->pub_h[i]);
+    if (h->ev_blob_snap[i]) cudaEventDestroy(h->ev_blob_snap[i]);
+    if (h->ev_blob_done[i]) cudaEventDestroy(h->ev_blob_done[i]);
+    cudaFree(h->blob_d[i]);
+    if (h->blob_h[i]) cudaFreeHost(h->blob_h[i]);
   }
+  cudaFree(h->blob_src);
+  cudaFree(h->blob_dst);
   cudaFree(h->split_d);
   cudaFree(h->chain_dbg);
   cudaFree(h->d_cmaps);
@@ -2025,6 +2040,95 @@ extern "C" int b200sac_publish_wait(b200sac_t* h, const float** host_ptr, int64_
   h->pub_pending -= 1;
   *host_ptr = h->pub_h[slot];
   *n_floats = h->pub_n[slot];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Blob publication.  What Learner.run() stores in Redis after every update is ONE byte string: _pickle.dumps of
+// {'actor': state_dict} (LunarLander_Distributed_SAC/src/learner.py:272-276,298-299).  Its shape never changes, so the
+// caller hands over the byte image once (b200sac_blob_template: constant pickle bytes + where every payload float sits and
+// which arena element it is -- pitch padding and the CARE [k][out][in] -> [k][in][out] transposition are just index maps);
+// per publication a kernel, in stream order between two steps, gathers the floats into a device copy of the image, one
+// D2H copy on the private stream brings it to pinned memory, and the host's only work is handing the bytes on.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) blob_pack_kernel(const float* __restrict__ params, const int* __restrict__ src,
+                                                        const int* __restrict__ dst, uint8_t* __restrict__ img, int n) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t v = __float_as_uint(params[src[j]]);
+  uint8_t* o = img + dst[j];
+  if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(o) = v;
+  } else {                                  // pickle payloads start at arbitrary byte offsets
+    o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); o[3] = (uint8_t)(v >> 24);
+  }
+}
+
+extern "C" int b200sac_blob_template(b200sac_t* h, int32_t replica, const uint8_t* image, int64_t image_bytes, int64_t n_floats,
+                                     const int32_t* src_index, const int32_t* dst_byte) {
+  if (!h || !image || image_bytes <= 0 || n_floats <= 0 || !src_index || !dst_byte) return fail(B200SAC_ERR_INVALID, "bad argument");
+  if (replica < 0 || replica >= h->R) return fail(B200SAC_ERR_INVALID, "replica %d out of range", replica);
+  if (n_floats > 0x7fffffffLL || image_bytes > 0x7fffffffLL) return fail(B200SAC_ERR_INVALID, "image too large");
+  for (int64_t j = 0; j < n_floats; ++j) {
+    if (src_index[j] < 0 || src_index[j] >= h->L.arena) return fail(B200SAC_ERR_INVALID, "payload float %lld reads arena index %d outside [0, %lld)", (long long)j, src_index[j], (long long)h->L.arena);
+    if (dst_byte[j] < 0 || (int64_t)dst_byte[j] + 4 > image_bytes) return fail(B200SAC_ERR_INVALID, "payload float %lld lands outside the image", (long long)j);
+  }
+  CU(cudaSetDevice(h->device));
+  if (!h->pub) CU(cudaStreamCreateWithFlags(&h->pub, cudaStreamNonBlocking));
+  CU(cudaStreamSynchronize(h->pub));
+  for (int i = 0; i < 2; ++i) {
+    if (!h->ev_blob_snap[i]) CU(cudaEventCreateWithFlags(&h->ev_blob_snap[i], cudaEventDisableTiming));
+    if (!h->ev_blob_done[i]) CU(cudaEventCreateWithFlags(&h->ev_blob_done[i], cudaEventDisableTiming));
+    cudaFree(h->blob_d[i]); h->blob_d[i] = nullptr;
+    if (h->blob_h[i]) { cudaFreeHost(h->blob_h[i]); h->blob_h[i] = nullptr; }
+    CU(cudaMalloc(&h->blob_d[i], (size_t)image_bytes));
+    CU(cudaHostAlloc(&h->blob_h[i], (size_t)image_bytes, cudaHostAllocDefault));
+    CU(cudaMemcpy(h->blob_d[i], image, (size_t)image_bytes, cudaMemcpyHostToDevice));
+  }
+  cudaFree(h->blob_src); cudaFree(h->blob_dst); h->blob_src = h->blob_dst = nullptr;
+  CU(cudaMalloc(&h->blob_src, (size_t)n_floats * sizeof(int)));
+  CU(cudaMalloc(&h->blob_dst, (size_t)n_floats * sizeof(int)));
+  CU(cudaMemcpy(h->blob_src, src_index, (size_t)n_floats * sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->blob_dst, dst_byte, (size_t)n_floats * sizeof(int), cudaMemcpyHostToDevice));
+  h->blob_bytes = image_bytes; h->blob_nf = n_floats; h->blob_replica = replica;
+  h->blob_head = 0; h->blob_pending = 0;
+  return 0;
+}
+
+extern "C" int b200sac_blob_begin(b200sac_t* h, void* stream) {
+  if (!h) return fail(B200SAC_ERR_INVALID, "null handle");
+  if (h->blob_nf <= 0) return fail(B200SAC_ERR_STATE, "blob_begin without blob_template");
+  CU(cudaSetDevice(h->device));
+  if (h->blob_pending == 2) {           // both images hold uncollected blobs: the older one is superseded
+    CU(cudaEventSynchronize(h->ev_blob_done[h->blob_head]));
+    h->blob_pending = 1;
+  }
+  const int slot = h->blob_head;
+  StreamBridge sb(h, stream);
+  if (int rc = sb.begin()) return rc;
+  // (slot reuse: the D2H of the blob begun two calls ago was collected or superseded above, so image `slot` is idle)
+  const float* base = h->params + (size_t)h->blob_replica * h->L.arena;
+  blob_pack_kernel<<<(unsigned)((h->blob_nf + 255) / 256), 256, 0, sb.run>>>(base, h->blob_src, h->blob_dst, h->blob_d[slot], (int)h->blob_nf);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev_blob_snap[slot], sb.run));
+  if (int rc = sb.end()) return rc;
+  CU(cudaStreamWaitEvent(h->pub, h->ev_blob_snap[slot], 0));
+  CU(cudaMemcpyAsync(h->blob_h[slot], h->blob_d[slot], (size_t)h->blob_bytes, cudaMemcpyDeviceToHost, h->pub));
+  CU(cudaEventRecord(h->ev_blob_done[slot], h->pub));
+  h->blob_head ^= 1;
+  h->blob_pending += 1;
+  return 0;
+}
+
+extern "C" int b200sac_blob_wait(b200sac_t* h, const uint8_t** host_ptr, int64_t* n_bytes) {
+  if (!h || !host_ptr || !n_bytes) return fail(B200SAC_ERR_INVALID, "null argument");
+  if (h->blob_pending <= 0) return fail(B200SAC_ERR_STATE, "blob_wait without blob_begin");
+  CU(cudaSetDevice(h->device));
+  const int slot = (h->blob_head + 2 - h->blob_pending) & 1;    // the oldest blob not collected yet
+  CU(cudaEventSynchronize(h->ev_blob_done[slot]));
+  h->blob_pending -= 1;
+  *host_ptr = h->blob_h[slot];
+  *n_bytes = h->blob_bytes;
   return 0;
 }
 

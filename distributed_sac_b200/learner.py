@@ -190,18 +190,42 @@ class _BaseLearner:
         self.publish_begin()
         return self.publish_wait()
 
-    def parameters_blob(self, blocking=False):
+    def parameters_blob(self, blocking=True):
         """The bytes Learner.run() stores under the Redis key 'parameters' (LL/learner.py:298-299): _pickle.dumps of
         {'actor': state_dict_on_cpu[, ...]} with the reference's key names -- what Player.pull_parameters unpickles
-        (LL/player.py:75-85).  pickle.dumps of a dict of torch tensors costs ~0.3 ms per call (one torch.save per
-        storage); the shapes never change, so the pickle stream is built ONCE from tensors of the same shapes and every
-        later call only copies the fresh float data from the pinned snapshot over the tensors' payload bytes.
-        blocking=True: take the snapshot now (get_parameters semantics); else collect the one started by publish_begin()."""
+        (LL/player.py:75-85).  The shapes never change, so the pickle stream is built ONCE (from tensors of the same shapes)
+        and handed to the library as a byte image with the positions of the float payloads (b200sac_blob_template); per
+        publication a kernel gathers the current floats into a device copy of the image and ONE D2H copy brings the finished
+        byte string to pinned memory -- the host never touches a tensor.
+        blocking=True: publish now (get_parameters + dumps semantics); False: collect the blob started by blob_begin()."""
+        self._ensure_blob()
         if blocking:
-            self.publish_begin()
-        return self._blob_from_views(self.core.publish_views())
+            self.core.blob_begin()
+        return self.core.blob_wait()[0]
+
+    def _ensure_blob(self):
+        if getattr(self, "_blob_ready", False):
+            return
+        self._pub_maps = [(net, self._key_map(net)) for net in self._published]
+        rng = np.random.default_rng(12345)
+        fake = {net: {ref: torch.from_numpy(rng.random(self.core.tensor_shape(canon), dtype=np.float32) + 1.0) for ref, canon in m.items()}
+                for net, m in self._pub_maps}
+        blob = _pickle.dumps(fake)
+        slots = []
+        for net, m in self._pub_maps:
+            for ref, canon in m.items():
+                payload = fake[net][ref].numpy().tobytes()
+                at = blob.find(payload)
+                if at < 0 or blob.find(payload, at + 1) >= 0:
+                    raise RuntimeError(f"cannot locate the payload of {net}.{ref} in the pickle stream")
+                slots.append((canon, at))
+        # (+ the temperature behind the image: the logger's alpha then comes from the same consistent snapshot)
+        self.core.blob_template(blob, slots, extra=("log_alpha",))
+        self._blob_ready = True
 
     def _blob_from_views(self, views):
+        """Host-side variant (snapshot views -> bytes patched into the pickle template); kept for callers of
+        publish_begin()/core.publish_views()."""
         tpl = getattr(self, "_blob_tpl", None)
         if tpl is None:
             rng = np.random.default_rng(12345)
@@ -335,29 +359,30 @@ class _BaseLearner:
         self.wait_until_memoryReady()
         self.my_print("######################### Start train #########################")
         self.soft_update(None, None, 1.0)           # copy parameters to target
-        # Pipelined like this: while the GPU runs step k+1 (enqueued together with its snapshot), the host turns snapshot k
-        # into the published blob and talks to Redis -- the reference does the same things strictly one after the other
-        # (learner.py:296-316).  Two snapshot slots in the library make that safe.
+        # Pipelined like this: while the GPU runs step k+1 (enqueued together with the assembly of its blob), the host hands
+        # blob k to Redis -- the reference does the same things strictly one after the other (learner.py:296-316).  Two
+        # blob images in the library make that safe.
         done = 0
         iters = (i for i in itertools.count() if i % self.update_delay == 0)
         update_iteration = next(iters)
-        self.memory.enqueue_step(self.core)            # update(), split so that everything below overlaps the GPU
-        self.publish_begin()
+        core = self.core
+        self.memory.enqueue_step(core)                 # update(), split so that everything below overlaps the GPU
+        core.blob_begin()
         while True:
             cur = update_iteration
-            res = self._loss_tuple(self.core.read_losses(1)[0])        # step `cur` has finished
-            views = self.core.publish_views()                            # ... and so has its snapshot
+            res = self._loss_tuple(core.read_losses(1)[0])             # step `cur` has finished
             last = max_updates is not None and done + 1 >= max_updates
             if cur % self.save_period == 0:
                 self.save_checkpoint(cur)              # before step cur+1 is enqueued: the arena is the state after `cur`
-            if not last:
+            if not last:                               # the GPU goes on with step cur+1 while blob `cur` is still crossing PCIe
                 update_iteration = next(iters)
-                self.memory.enqueue_step(self.core)
-                self.publish_begin()
+                self.memory.enqueue_step(core)
+                core.blob_begin()
+            blob, extra = core.blob_wait()             # the OLDEST uncollected blob = the one of step `cur`
             self.server.set("update_iteration", _pickle.dumps(cur))
-            self.server.set("parameters", self._blob_from_views(views))
+            self.server.set("parameters", blob)
             if self.write_mode:
-                self.write(cur, *res, log_alpha=views.get("log_alpha"))
+                self.write(cur, *res, log_alpha=extra["log_alpha"])
                 if cur % self.print_period == 0:
                     self.my_print("[Learner] Update_iteration: {0:<6} \t | actor_loss : {1:5.3f} \t | critic_loss : {2:5.3f}".format(
                         cur, res[1], res[0]))

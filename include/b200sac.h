@@ -199,6 +199,20 @@ int b200sac_publish_begin(b200sac_t* h, int32_t replica, int32_t n_ranges, const
                           void* stream);
 int b200sac_publish_wait(b200sac_t* h, const float** host_ptr, int64_t* n_floats);
 
+/* Blob publication: the byte string Learner.run() stores under the Redis key 'parameters' after every update
+ * (LunarLander_Distributed_SAC/src/learner.py:298-299: _pickle.dumps({'actor': state_dict}); read back by
+ * Player.pull_parameters, player.py:75-85) assembled on the device.  blob_template: `image` = the constant bytes of the
+ * string (any values in the payload positions); payload float j (j < n_floats) is the 4 bytes at dst_byte[j] and holds
+ * element src_index[j] of replica `replica`'s parameter arena (b200sac_layout offsets; pitch padding / transposed views
+ * are expressed through the index map).  blob_begin enqueues, in stream order, the gather of all payload floats into a
+ * device copy of the image and starts ONE D2H copy of it on a private stream; it does not block and later steps overlap
+ * the copy.  blob_wait blocks until the OLDEST uncollected blob has landed in pinned memory and returns it (valid until
+ * the second blob_begin after the one that produced it; two image slots, as for publish_begin/wait). */
+int b200sac_blob_template(b200sac_t* h, int32_t replica, const uint8_t* image, int64_t image_bytes, int64_t n_floats,
+                          const int32_t* src_index, const int32_t* dst_byte);
+int b200sac_blob_begin(b200sac_t* h, void* stream);
+int b200sac_blob_wait(b200sac_t* h, const uint8_t** host_ptr, int64_t* n_bytes);
+
 /* Debug / parity access to per-step intermediates of replica `replica`:
  * name in {"y","q1","q2","a_next","logp_next","a_cur","logp_cur","qmin","d_action","d_head","r","d"}, "psave" ([2B][act][8]:
  * what the policy head saved per (row, action) -- std, u-mu, tanh(u), action, Jacobian term, the NOISE it used, clamp mask,

@@ -5,7 +5,10 @@ from distributed_sac_b200 import _lib
 lib = C.CDLL(_lib.LIB_PATH)
 lib.b200sac_tc_gemm_timeline.argtypes = [C.c_int32] * 4 + [C.c_void_p]
 torch.cuda.init(); torch.zeros(1, device="cuda")
-for mode, M, N, K in [(0, 256, 256, 256), (2, 256, 256, 256)]:
+shapes = [(0, 256, 256, 256), (2, 256, 256, 256)]
+if len(sys.argv) > 1:      # e.g. 0,4096,400,400 1,2048,400,400 (mode,M,N,K); B200SAC_TC_BN picks the tile width
+    shapes = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]]
+for mode, M, N, K in shapes:
     out = (C.c_longlong * 96)()
     rc = lib.b200sac_tc_gemm_timeline(mode, M, N, K, out)
     t = list(out); t0 = t[0]

@@ -112,6 +112,12 @@ def test_run_loop_with_redis_stub(cuda, tmp_path):
     params = pickle.loads(lrn.server.get("parameters"))
     assert params["actor"]["mu_log_std_layer.weight"].shape == (4, 256)
     assert lrn.server.llen("critic_loss") == 7 and lrn.server.llen("alpha") == 7
+    # the last published blob (assembled on the device, b200sac_blob_*) is the actor after the last update, and the logged
+    # temperature is the one of the same snapshot
+    final = lrn._module_state_dict("actor")
+    assert all(torch.equal(params["actor"][k], final[k]) for k in final)
+    it, alphas = pickle.loads(lrn.server.pipeline().lrange("alpha", 6, 6).execute()[0][0])
+    assert it == 18 and np.allclose(alphas, lrn.log_alpha.exp().numpy(), rtol=1e-6)
     lrn.memory.stop()
 
 
@@ -208,9 +214,13 @@ def test_publication_snapshot_is_consistent_and_async(cuda, tmp_path):
     assert set(fast) == set(full) and all(torch.equal(fast[k], full[k]) and fast[k].is_contiguous() for k in full)
     assert torch.equal(lrn.log_alpha, lrn.core.get_named()["log_alpha"])          # small-range read == arena export
     lrn.publish_begin()                                          # snapshot after step 3 ...
-    lrn.core.step_sampled(lrn.memory.ring, 40)                   # ... while 40 more steps are enqueued behind it
+    lrn.core.blob_begin()                                        # ... and the device-assembled blob of the same state ...
+    lrn.core.step_sampled(lrn.memory.ring, 40)                   # ... while 40 more steps are enqueued behind them
     snap = lrn.publish_wait()["actor"]
     assert all(torch.equal(snap[k], full[k]) for k in full)
+    blob3, extra3 = lrn.core.blob_wait()
+    snap_b = pickle.loads(blob3)["actor"]
+    assert all(torch.equal(snap_b[k], full[k]) for k in full)
     twin.core.step_sampled(twin.memory.ring, 40)                 # same seed, same ring: replicas stay bit-identical
     after, ref = lrn.get_parameters()["actor"], twin.get_parameters()["actor"]
     assert all(torch.equal(after[k], ref[k]) for k in ref)

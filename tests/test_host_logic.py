@@ -132,39 +132,86 @@ def test_publication_ranges_and_unpack_without_a_gpu():
     assert w0[5] >= w0[2] and w0[5] % 4 == 0                       # padded pitch of the first layer is hidden from the caller
 
 
-def test_parameters_blob_template_patching_round_trips():
-    """Learner.parameters_blob(): the pickle stream is built once from tensors of the published shapes and later calls only
-    overwrite the tensors' payload bytes -- unpickling must give exactly what a plain pickle.dumps of the state_dict gives."""
+class BlobStubLib:
+    """CPU stand-in for b200sac_blob_*: emulates the device gather (payload float j = arena[src[j]] -> image bytes at dst[j])."""
+
+    def __init__(self, arena):
+        self.arena = arena
+
+    def b200sac_blob_template(self, h, replica, image, image_bytes, n_floats, src, dst):
+        import ctypes as C
+        import numpy as np
+        self.image = np.ctypeslib.as_array(C.cast(image, C.POINTER(C.c_uint8)), shape=(image_bytes,)).copy()
+        self.src = np.ctypeslib.as_array(C.cast(src, C.POINTER(C.c_int32)), shape=(n_floats,)).copy()
+        self.dst = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_int32)), shape=(n_floats,)).copy()
+        return 0
+
+    def b200sac_blob_begin(self, h, stream):
+        import numpy as np
+        out = self.image.copy()
+        vals = np.ascontiguousarray(self.arena[self.src], dtype=np.float32).view(np.uint8).reshape(-1, 4)
+        for b in range(4):
+            out[self.dst + b] = vals[:, b]
+        self.out = out
+        return 0
+
+    def b200sac_blob_wait(self, h, ptr, n):
+        import ctypes as C
+        C.cast(ptr, C.POINTER(C.c_void_p))[0] = self.out.ctypes.data
+        C.cast(n, C.POINTER(C.c_int64))[0] = self.out.size
+        return 0
+
+
+def test_parameters_blob_device_image_round_trips():
+    """Learner.parameters_blob(): the pickle stream is built once from tensors of the published shapes and registered as a byte
+    image + index maps (core.blob_template); a publication only gathers arena floats into the payload positions.  With the
+    gather emulated on the CPU, unpickling must give exactly what a plain pickle.dumps of the state_dict gives -- through the
+    padded first-layer pitch and the CARE (K,in,out) mixture layout."""
     import pickle
     import numpy as np
     import torch
+    import distributed_sac_b200.core as core_mod
+    from distributed_sac_b200 import names
+    from distributed_sac_b200.core import CoreConfig, SacCore, layout
     from distributed_sac_b200.learner import _BaseLearner
 
-    class FakeCore:
-        def __init__(self): self.views = {}
-        def publish_views(self): return self.views
-
-    lrn = _BaseLearner.__new__(_BaseLearner)
-    lrn.core = FakeCore()
-    shapes = {"actor.0.weight": (256, 8), "actor.0.bias": (256,), "actor.1.weight": (256, 256), "actor.1.bias": (256,),
-              "actor.2.weight": (4, 256), "actor.2.bias": (4,)}
-    km = {"layer_intermediate.0.weight": "actor.0.weight", "layer_intermediate.0.bias": "actor.0.bias",
-          "layer_intermediate.1.weight": "actor.1.weight", "layer_intermediate.1.bias": "actor.1.bias",
-          "mu_log_std_layer.weight": "actor.2.weight", "mu_log_std_layer.bias": "actor.2.bias"}
-    lrn._pub_maps = [("actor", km)]
+    cfg = CoreConfig(state_dim=39, act_dim=4, actor_hidden=[16, 12], critic_hidden=[16, 12], batch=60, num_tasks=10, care=True,
+                     num_encoders=3, mix_hidden=[8], mix_out=6, ctx_in=20, ctx_hidden=[7], ctx_out=5)
+    table, arena, _trainable = layout(cfg)
     rng = np.random.default_rng(0)
-    for rnd in range(3):
-        # a non-contiguous view for the first-layer weight (padded row pitch in the arena), zeros for the biases
-        padded = rng.standard_normal((256, 12)).astype(np.float32)
-        lrn.core.views = {k: (np.zeros(sh, np.float32) if "bias" in k and rnd == 0 else rng.standard_normal(sh).astype(np.float32))
-                          for k, sh in shapes.items()}
-        lrn.core.views["actor.0.weight"] = padded[:, :8]
-        blob = lrn.parameters_blob()
-        got = pickle.loads(blob)
-        assert set(got) == {"actor"} and set(got["actor"]) == set(km)
-        for ref, canon in km.items():
-            t = got["actor"][ref]
-            assert isinstance(t, torch.Tensor) and t.dtype == torch.float32 and tuple(t.shape) == shapes[canon]
-            assert np.array_equal(t.numpy(), np.asarray(lrn.core.views[canon]))
-        plain = pickle.loads(pickle.dumps({"actor": {ref: torch.from_numpy(np.ascontiguousarray(lrn.core.views[c_])) for ref, c_ in km.items()}}))
-        assert all(torch.equal(plain["actor"][k], got["actor"][k]) for k in km)
+    flat = rng.standard_normal(arena).astype(np.float32)
+    core = object.__new__(SacCore)
+    core.lib, core._h, core.cfg, core.table = BlobStubLib(flat), None, cfg, table
+    lrn = _BaseLearner.__new__(_BaseLearner)
+    lrn.core = core
+    lrn._published = ("actor", "cse")
+    km = {"actor": {f"ref.{n}": n for n in table if n.startswith("actor.")},
+          "cse": {f"ref.{n}": n for n in table if n.startswith("cse.")}}
+    lrn._key_map = lambda net: km[net]
+    real_stream = core_mod._stream
+    core_mod._stream = lambda: None
+    try:
+        for rnd in range(3):
+            flat[:] = rng.standard_normal(arena).astype(np.float32)
+            if rnd == 1:
+                flat[:] = 0.0                                       # all-zero payloads must not confuse the template
+            blob = lrn.parameters_blob(blocking=True)
+            got = pickle.loads(blob)
+            assert set(got) == {"actor", "cse"}
+            for net, m in km.items():
+                assert set(got[net]) == set(m)
+                for ref, canon in m.items():
+                    off, rows, cols, _tr, _opt, pitch = table[canon]
+                    want = core._view(canon, flat, off)
+                    t = got[net][ref]
+                    assert isinstance(t, torch.Tensor) and t.dtype == torch.float32 and tuple(t.shape) == want.shape, (canon, t.shape, want.shape)
+                    assert np.array_equal(t.numpy(), want), canon
+            plain = pickle.loads(pickle.dumps({net: {ref: torch.from_numpy(np.ascontiguousarray(core._view(c_, flat, table[c_][0])))
+                                                     for ref, c_ in m.items()} for net, m in km.items()}))
+            assert all(torch.equal(plain[net][k], got[net][k]) for net in km for k in km[net])
+            _blob, extra = core.blob_wait()                          # (the stub keeps the last image) the logger's temperature
+            assert np.array_equal(extra["log_alpha"], flat[table["log_alpha"][0]:table["log_alpha"][0] + table["log_alpha"][1]])
+    finally:
+        core_mod._stream = real_stream
+    mixw = [n for n in table if ".mix." in n and n.endswith(".W")]
+    assert mixw and table["actor.0.weight"][5] > table["actor.0.weight"][2]      # both layout twists were exercised

@@ -3,7 +3,7 @@ and the host-side wire formats against the UNMODIFIED reference, live.
 
 * oracle/sac_port.py / care_port.py reproduce the reference learner's update() step for step (the committed fixtures under
   tests/golden/ are frozen outputs of the same comparison; this test re-derives them from the code in front of us);
-* the bytes Learner.run() publishes (Learner.parameters_blob: a pickle stream built once and patched per call) load into
+* the bytes Learner.run() publishes (Learner.parameters_blob: a pickle stream built once whose float payloads the library gathers from the arena) load into
   the reference's own Actor via load_state_dict -- what Player.pull_parameters does (LL/player.py:75-85);
 * a checkpoint written by the drop-in learner's save path (reference-written fixtures round-tripped on the GPU side, see
   tests/test_gpu_checkpoint.py) has the key set the reference's load_checkpoint() reads."""
@@ -65,13 +65,29 @@ def test_published_blob_loads_into_the_reference_actor():
     km = names.actor_key_map("LL", 3)
     sd = lrn.actor.state_dict()
 
-    class FakeCore:
-        def publish_views(self_inner):
-            return {canon: sd[ref].detach().numpy() for ref, canon in km.items()}
-
+    # stand-in core: the arena of a LunarLander learner filled with the live reference Actor's state; the device gather of
+    # b200sac_blob_* is emulated on the CPU (tests/test_host_logic.py::BlobStubLib)
+    import numpy as np
+    import distributed_sac_b200.core as core_mod
+    from distributed_sac_b200.core import CoreConfig, SacCore, layout
+    from test_host_logic import BlobStubLib
+    cfg = CoreConfig(batch=64)
+    table, arena, _tr = layout(cfg)
+    flat = np.zeros(arena, np.float32)
+    core = object.__new__(SacCore)
+    core.lib, core._h, core.cfg, core.table = BlobStubLib(flat), None, cfg, table
+    for ref, canon in km.items():
+        off, rows, cols, _t, _o, pitch = table[canon]
+        flat[off:off + rows * pitch].reshape(rows, pitch)[:, :cols] = sd[ref].detach().numpy().reshape(rows, cols)
     shim = _BaseLearner.__new__(_BaseLearner)
-    shim.core, shim._pub_maps = FakeCore(), [("actor", km)]
-    blob = shim.parameters_blob()
+    shim.core = core
+    shim._key_map = lambda net: km
+    real_stream = core_mod._stream
+    core_mod._stream = lambda: None
+    try:
+        blob = shim.parameters_blob()
+    finally:
+        core_mod._stream = real_stream
     params = pickle.loads(blob)                                   # Player.pull_parameters: _pickle.loads(server.get('parameters'))
     other, _ = rh.make_learner("LL", dict(batch_size=64), seed=99)
     assert not torch.equal(other.actor.state_dict()["mu_log_std_layer.weight"], sd["mu_log_std_layer.weight"])
