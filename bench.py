@@ -492,6 +492,7 @@ class Bench:
                         lrn.save_checkpoint = lambda idx: None
                         lrn.my_print = lambda content: None
                         lrn.update_delay = 1
+                        lrn.start_memory_len = -1                    # the ring was filled directly (per-task sub-rings hold HOST_RING / T rows)
                         lrn.run(max_updates=16)
                         t0 = time.perf_counter()
                         done = lrn.run(max_updates=Kp)

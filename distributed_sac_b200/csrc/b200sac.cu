@@ -446,6 +446,61 @@ static bool tc_eligible(const GemmProb& p) {
   return p.M >= 32 && p.N >= 32 && p.K >= 32;
 }
 
+// Tile variants of the tcgen05 GEMM (gemm_tc.cuh): 128x64 paired, 128x128 unpaired / paired (N = 256 MMAs), 128x160.
+typedef void (*TcKernel)(const TcProb*);
+static bool tc_pair128() { const char* e = getenv("B200SAC_TC_PAIR128"); return !(e && e[0] == '0'); }
+static TcKernel tc_kernel(int bn) {
+  if (bn == 160) return gemm_tc_kernel<160, false>;
+  if (bn == 128) return tc_pair128() ? (TcKernel)gemm_tc_kernel<128, true> : (TcKernel)gemm_tc_kernel<128, false>;
+  return gemm_tc_kernel<64, true>;
+}
+static size_t tc_smem(int bn) {
+  return bn == 160 ? TcCfg<160, false>::kSmemBytes : (bn == 128 ? TcCfg<128, false>::kSmemBytes : TcCfg<64, true>::kSmemBytes);
+}
+static cudaError_t tc_set_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, true>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, true>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<160, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<160, false>::kSmemBytes);
+  return e;
+}
+// Modelled cycles of one launch group with `bn`-wide tiles (measured constants, scripts/tc_timeline.py): a tile costs a
+// ~2.5k-cycle prologue, 4 k steps per 32-wide k chunk at 210 (64, paired) / 276 (128, paired) / 315 (128) / 366 (160)
+// cycles of MMA issue each, and ~1.5k cycles of epilogue per pair of 32-column blocks; tiles beyond 148 x R wait for a
+// second wave.  The plan builder takes the cheapest width.
+static double tc_group_cost(const std::vector<GemmProb>& v, int bn, int R) {
+  long long tiles = 0;
+  int nk = 1;
+  for (auto& p : v) {
+    tiles += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + bn - 1) / bn);
+    nk = std::max(nk, (p.K + TC_BK - 1) / TC_BK);
+  }
+  const double kstep = bn == 64 ? 210.0 : (bn == 160 ? 366.0 : (tc_pair128() ? 276.0 : 315.0));
+  const double tile = 2500.0 + nk * 4 * kstep + 1500.0 * ((bn / 32 + 1) / 2);
+  const long long waves = (tiles * R + 147) / 148;
+  return (double)waves * tile;
+}
+static int tc_pick_bn(const std::vector<GemmProb>& v, int R) {
+  if (const char* e = getenv("B200SAC_TC_BN")) { const int b = atoi(e); return b == 128 ? 128 : (b == 160 ? 160 : 64); }
+  int maxN = 0;
+  for (auto& p : v) maxN = std::max(maxN, p.N);
+  if (getenv("B200SAC_TC_OLDRULE")) {             // round-1 rule: 128 when the group still fills most of the GPU with 128x128 tiles
+    long long c128 = 0;
+    for (auto& p : v) c128 += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + 127) / 128);
+    return (maxN >= 256 && c128 * R >= 96) ? 128 : 64;
+  }
+  const bool no160 = getenv("B200SAC_TC_NO160") != nullptr;
+  int best = 64;
+  double cost = tc_group_cost(v, 64, R);
+  for (int bn : {128, 160}) {
+    if (bn == 160 && no160) continue;
+    if (maxN < 2 * bn - 64) continue;             // a lone, mostly empty wide tile is never better than 64-wide ones
+    const double c = tc_group_cost(v, bn, R);
+    if (c < cost) { cost = c; best = bn; }
+  }
+  return best;
+}
+
 constexpr int kSplitK = 4, kSplitKMin = 512;     // weight gradients with K >= 512 rows are computed in 4 K slices
 
 static int make_tc_prob(const GemmProb& p, int rep, TcProb& t, int bn = 64) {
@@ -900,28 +955,36 @@ static int build_plan(b200sac* h) {
         }
       }
     };
-    // tcgen05 tiles hold one CTA per SM: take the finest split whose launch still fits one wave of 148 CTAs (a second
-    // wave costs more than the shorter k loop saves); the FFMA engine (several CTAs per SM) always takes the finest.
-    auto tc_ctas = [&](const std::vector<GemmProb>& v) {
-      long long c128 = 0, c64 = 0;
-      int maxN = 0;
-      for (auto& p : v) {
-        if (!tc_eligible(p)) continue;
-        c128 += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + 127) / 128);
-        c64 += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + 63) / 64);
-        maxN = p.N > maxN ? p.N : maxN;
-      }
-      return ((maxN >= 256 && c128 * R >= 96) ? c128 : c64) * R;
+    // tcgen05 tiles hold one CTA per SM: take the split factor (and with it the tile width) whose launch is cheapest under
+    // tc_group_cost's model -- a finer split shortens the k loop but a second wave of CTAs costs a whole tile time; the FFMA
+    // engine (several CTAs per SM) always takes the finest.
+    auto tc_only = [&](const std::vector<GemmProb>& v) {
+      std::vector<GemmProb> o;
+      for (auto& p : v) if (tc_eligible(p)) o.push_back(p);
+      return o;
     };
     std::vector<GemmProb> ps;
     {
       int S = kSplitK;
-      if (c.precision == 1)
-        for (; S > 1; S >>= 1) {
+      if (c.precision == 1) {
+        double best = 1e300;
+        for (int s_ = kSplitK; s_ >= 1; s_ >>= 1) {
           std::vector<GemmProb> trial;
-          expand(S, trial);
-          if (tc_ctas(trial) <= 148) break;
+          expand(s_, trial);
+          const std::vector<GemmProb> o = tc_only(trial);
+          if (o.empty()) { S = s_; break; }
+          if (getenv("B200SAC_TC_OLDRULE")) {          // round-1 rule: the finest split that fits one wave
+            const int bn = tc_pick_bn(o, R);
+            long long ct = 0;
+            for (auto& p : o) ct += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + bn - 1) / bn);
+            S = s_;
+            if (ct * R <= 148) break;
+            continue;
+          }
+          const double cost = tc_group_cost(o, tc_pick_bn(o, R), R);
+          if (cost < best) { best = cost; S = s_; }
         }
+      }
       expand(S, ps);
     }
     if (c.precision == 1) {
@@ -931,17 +994,20 @@ static int build_plan(b200sac* h) {
         Launch l;
         int maxM = 0, maxN = 0;
         for (auto& p : tc) { maxM = p.M > maxM ? p.M : maxM; maxN = p.N > maxN ? p.N : maxN; }
-        // tile width: 128 when the group still fills most of the GPU with 128x128 tiles, else 64
-        long long ctas128 = 0;
-        for (auto& p : tc) ctas128 += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + 127) / 128);
-        int bn = (maxN >= 256 && ctas128 * R >= 96) ? 128 : 64;
-        if (const char* e = getenv("B200SAC_TC_BN")) bn = atoi(e) == 128 ? 128 : 64;
+        const int bn = tc_pick_bn(tc, R);          // tile width: the cheapest of 64 / 128 / 160 under tc_group_cost's model
+        if (getenv("B200SAC_PLAN_DBG")) {
+          long long tiles = 0;
+          for (auto& p : tc) tiles += (long long)((p.M + TC_BM - 1) / TC_BM) * ((p.N + bn - 1) / bn);
+          fprintf(stderr, "[plan] launch %zu: tcgen05 bn=%d problems=%zu tiles=%lld:", h->plan.size(), bn, tc.size(), tiles);
+          for (auto& p : tc) fprintf(stderr, " %s%dx%dx%d", p.mode == GEMM_FWD ? "F" : (p.mode == GEMM_DGRAD ? "D" : "W"), p.M, p.N, p.K);
+          fprintf(stderr, "\n");
+        }
         l.kind = L_GEMM_TC;
         l.branch = cur_branch;
         l.bn = bn;
         l.grid = dim3((maxN + bn - 1) / bn, (maxM + TC_BM - 1) / TC_BM, (unsigned)(tc.size() * R));
         l.block = dim3(TC_THREADS);
-        l.smem = bn == 128 ? TcCfg<128>::kSmemBytes : TcCfg<64>::kSmemBytes;
+        l.smem = tc_smem(bn);
         l.G = (int)tc.size();
         l.tprobs = (const TcProb*)(uintptr_t)h->h_tprobs.size();
         l.probs = (const GemmProb*)(uintptr_t)h->h_probs.size();   // keep the SIMT descriptors too (labels)
@@ -1466,8 +1532,7 @@ static int build_plan(b200sac* h) {
   if (!h->h_tprobs.empty()) {
     CU(cudaMalloc(&h->d_tprobs, h->h_tprobs.size() * sizeof(TcProb)));
     CU(cudaMemcpy(h->d_tprobs, h->h_tprobs.data(), h->h_tprobs.size() * sizeof(TcProb), cudaMemcpyHostToDevice));
-    CU(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes));
-    CU(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
+    CU(tc_set_attrs());
   }
   if (!h->h_probs.empty()) {
     CU(cudaMalloc(&h->d_probs, h->h_probs.size() * sizeof(GemmProb)));
@@ -1561,8 +1626,7 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
         launch_k(gemm_thin_kernel, l.grid, l.block, 0, s, l.grp);
         break;
       case L_GEMM_TC:
-        if (l.bn == 128) launch_k(gemm_tc_kernel<128>, l.grid, l.block, l.smem, s, l.tprobs);
-        else launch_k(gemm_tc_kernel<64>, l.grid, l.block, l.smem, s, l.tprobs);
+        launch_k(tc_kernel(l.bn), l.grid, l.block, l.smem, s, l.tprobs);
         break;
       case L_POLICY: {
         PolicyHeadArgs P = l.pol;
@@ -2490,17 +2554,15 @@ static int tc_gemm_test_impl(int32_t mode, int32_t M, int32_t N, int32_t K, cons
   p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldmask = ldmask; p.mode = mode; p.relu = relu;
   if (!tc_eligible(p)) return fail(B200SAC_ERR_INVALID, "problem not eligible for the tcgen05 path (need 16-B aligned operands, lda/ldb %% 4 == 0, M,N,K >= 32)");
   int bn = 64;
-  if (const char* e = getenv("B200SAC_TC_BN")) bn = atoi(e) == 128 ? 128 : 64;
+  if (const char* e = getenv("B200SAC_TC_BN")) { const int b = atoi(e); bn = b == 128 ? 128 : (b == 160 ? 160 : 64); }
   TcProb t;
   if (int rc = make_tc_prob(p, 0, t, bn)) return rc;
   TcProb* d = nullptr;
   CU(cudaMalloc(&d, sizeof(TcProb)));
   CU(cudaMemcpy(d, &t, sizeof(TcProb), cudaMemcpyHostToDevice));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
+  CU(tc_set_attrs());
   dim3 grid((N + bn - 1) / bn, (M + TC_BM - 1) / TC_BM, 1);
-  if (bn == 128) gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::kSmemBytes, (cudaStream_t)stream>>>(d);
-  else gemm_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::kSmemBytes, (cudaStream_t)stream>>>(d);
+  tc_kernel(bn)<<<grid, TC_THREADS, tc_smem(bn), (cudaStream_t)stream>>>(d);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(d);
@@ -2520,20 +2582,16 @@ extern "C" int b200sac_tc_gemm_timeline(int32_t mode, int32_t M, int32_t N, int3
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.mode = mode;
   p.lda = mode == GEMM_WGRAD ? M : K; p.ldb = mode == GEMM_FWD ? K : N; p.ldc = N;
   int bn = 64;
-  if (const char* e = getenv("B200SAC_TC_BN")) bn = atoi(e) == 128 ? 128 : 64;
+  if (const char* e = getenv("B200SAC_TC_BN")) { const int b = atoi(e); bn = b == 128 ? 128 : (b == 160 ? 160 : 64); }
   TcProb t;
   if (int rc = make_tc_prob(p, 0, t, bn)) return rc;
   t.dbg = dbg;
   TcProb* d = nullptr;
   CU(cudaMalloc(&d, sizeof(TcProb)));
   CU(cudaMemcpy(d, &t, sizeof(TcProb), cudaMemcpyHostToDevice));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
+  CU(tc_set_attrs());
   dim3 grid((N + bn - 1) / bn, (M + TC_BM - 1) / TC_BM, 1);
-  for (int it = 0; it < 3; ++it) {
-    if (bn == 128) gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::kSmemBytes>>>(d);
-    else gemm_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::kSmemBytes>>>(d);
-  }
+  for (int it = 0; it < 3; ++it) tc_kernel(bn)<<<grid, TC_THREADS, tc_smem(bn)>>>(d);
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out96, dbg, 96 * 8, cudaMemcpyDeviceToHost));
   cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(dbg); cudaFree(d);
@@ -2772,6 +2830,8 @@ extern "C" int b200sac_debug_read(b200sac_t* h, const char* name, int32_t replic
   else if (nm == "r") { src = h->r.p + replica * h->r.rs; n = B; }
   else if (nm == "d") { src = h->d.p + replica * h->d.rs; n = B; }
   else if (nm == "qmin") { src = h->qmin.p + replica * h->qmin.rs; n = B; }
+  else if (nm == "q_pi") { src = h->qp.p + replica * 2 * h->y.rs; n = 2 * B; }        // [2][B]: Q1, Q2 at (s, a~) (actor pass)
+  else if (nm == "dq_pi") { src = h->dqa.p + replica * 2 * h->y.rs; n = 2 * B; }      // [2][B]: d(actor loss)/dQk -- the min routing
   else if (nm == "d_action") { src = h->dact_dbg.p + replica * h->dact_dbg.rs; n = (int64_t)B * A; }
   else if (nm == "d_head") { src = h->dout_dbg.p + replica * h->dout_dbg.rs; n = (int64_t)B * 2 * A; }
   else if (nm == "psave") { src = h->psave.p + replica * h->psave.rs; n = (int64_t)2 * B * A * kSaveW; }   // [2B][A][8]: std, diff, tanh, act, jac, EPS, mask, logp_j

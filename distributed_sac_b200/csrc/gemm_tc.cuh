@@ -37,26 +37,31 @@ namespace bsac {
 
 constexpr int TC_BM = 128, TC_BK = 32;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                  // 16 KiB
-constexpr int TC_THREADS = 192;
-constexpr int TC_SPLIT_THREADS = 128;
+constexpr int TC_SPLIT_THREADS = 256;                          // warps 2-9: splitter, then epilogue (two warps per TMEM lane quarter)
+constexpr int TC_THREADS = 64 + TC_SPLIT_THREADS;
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_BSUM_BYTES = 16 * TC_BM * 4;                  // [16 partials][128 m] fp32
 
-// Two tile widths: 128x64 (many CTAs: latency-critical small problems) and 128x128 (the 400-wide shapes:
-// an N=128 MMA amortises the A-operand shared-memory reads over twice the columns).
-template <int BN>
+// Tile widths: 128x64 (many CTAs: latency-critical small problems), 128x128 (the 400-wide shapes: an N=128 MMA amortises
+// the A-operand shared-memory reads over twice the columns) and 128x160 (400 = 3 x 160 - 80: launch groups whose 128-wide
+// tiling needs a second wave of CTAs but whose 160-wide tiling fits one, e.g. 5120 rows x 400 columns = 160 vs 120 tiles).
+template <int BN, bool PAIRED = (BN == 64)>
 struct TcCfg {
   static constexpr int kBN = BN;
-  static constexpr int kBBytes = BN * TC_BK * 4;                           // 8 / 16 KiB
-  static constexpr int kStageBytes = 2 * (TC_A_BYTES + kBBytes);           // hi + lo of both operands: 48 / 64 KiB
+  static constexpr int kBBytes = BN * TC_BK * 4;                           // 8 / 16 / 20 KiB
+  static constexpr int kStageBytes = 2 * (TC_A_BYTES + kBBytes);           // hi + lo of both operands: 48 / 64 / 72 KiB
   static constexpr int kStages = BN == 64 ? 4 : 3;
-  // BN = 64: "paired" accumulators [main_i | cross_i] (2*BN columns each, 4 pairs) fed by ONE N=128 MMA per k step
-  // whose B operand spans the hi tile and the lo tile behind it (A_hi * [B_hi ; B_lo]) plus one N=64 MMA
-  // (A_lo * B_hi -> cross_i): 2 instead of 3 tcgen05.mma per k step, and an MMA costs ~105 cycles whatever its N <= 128
-  // (measured, scripts/micro/mma_rate.cu).  BN = 128 keeps 3 mains + 1 shared cross accumulator (an N=256 MMA costs 171).
-  static constexpr bool kPaired = BN == 64;
-  static constexpr int kNMain = BN == 64 ? 4 : 3;                          // TMEM: 4 * 128 | (3 + 1) * 128 = 512 columns
+  // PAIRED: accumulators [main_i | cross_i] (2*BN columns each) fed by ONE N=2*BN MMA per k step whose B operand spans the
+  // hi tile and the lo tile behind it (A_hi * [B_hi ; B_lo]) plus one N=BN MMA (A_lo * B_hi -> cross_i): 2 instead of 3
+  // tcgen05.mma per k step.  An MMA costs ~105 cycles whatever its N <= 128 and ~171 at N = 256 (measured,
+  // scripts/micro/mma_rate.cu): 210 instead of 315 cycles per k step at BN = 64, 276 instead of 315 at BN = 128.
+  // Unpaired: kNMain rotating main accumulators + 1 shared cross accumulator.
+  static constexpr bool kPaired = PAIRED;
+  static constexpr int kNMain = PAIRED ? (512 / (2 * BN)) : (BN == 128 ? 3 : 2);   // TMEM: 4*128 | 2*256 | (3+1)*128 | (2+1)*160 columns
   static constexpr int kSmemBytes = kStages * kStageBytes + TC_BSUM_BYTES + 256 + 1024;   // + barriers + align slack
+  static_assert(PAIRED ? (2 * BN * kNMain <= TC_TMEM_COLS && 2 * BN <= 256) : (BN * (kNMain + 1) <= TC_TMEM_COLS), "TMEM columns");
+  static_assert(kSmemBytes <= 232448, "shared memory");
+  static_assert(BN % 32 == 0 && kBBytes % (16 * TC_SPLIT_THREADS) == 0, "tile width");
 };
 constexpr int TC_BN = 64;            // default tile width (descriptor-eligibility bounds, tests)
 constexpr int TC_SMEM_BYTES = TcCfg<64>::kSmemBytes;
@@ -187,9 +192,9 @@ B200_D uint32_t tc_instr_desc(int a_mn, int b_mn, int bn) {
          ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, bool PAIRED>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __restrict__ probs) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PAIRED>;
   constexpr int TC_BN = BN, TC_B_BYTES = Cfg::kBBytes, TC_STAGE_BYTES = Cfg::kStageBytes, TC_STAGES = Cfg::kStages,
                 TC_NMAIN = Cfg::kNMain;
   KStamp ks_;
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
     }
   } else {
     // =============================== splitter, then epilogue ===============================
-    const int t = threadIdx.x - 64;       // 0..127
+    const int t = threadIdx.x - 64;       // 0..255
     const bool want_bsum = (P->mode == GEMM_WGRAD) && (P->C2 != nullptr) && (blockIdx.x == 0);
     float bs[4][4];
 #pragma unroll
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
         lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
       };
-      constexpr int NA = TC_A_BYTES / 16 / TC_SPLIT_THREADS, NB = TC_B_BYTES / 16 / TC_SPLIT_THREADS;   // 8, 4
+      constexpr int NA = TC_A_BYTES / 16 / TC_SPLIT_THREADS, NB = TC_B_BYTES / 16 / TC_SPLIT_THREADS;   // 4; 2 | 4 | 5
       float4 va[NA], vb[NB];
 #pragma unroll
       for (int i = 0; i < NA; ++i) va[i] = aH[t + i * TC_SPLIT_THREADS];   // all loads first
@@ -354,8 +359,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         float4 lo;
         split(va[i], lo);
         aL[t + i * TC_SPLIT_THREADS] = lo;
-        if (want_bsum) {   // MN-major A tile: [g = idx/256][k = (idx%256)/8][slot = idx%8], 32-B chunk (slot/2) ^= (k&3)
-          bs[i >> 1][0] += va[i].x; bs[i >> 1][1] += va[i].y; bs[i >> 1][2] += va[i].z; bs[i >> 1][3] += va[i].w;
+        if (want_bsum) {   // MN-major A tile: [g = idx/256][k = (idx%256)/8][slot = idx%8], 32-B chunk (slot/2) ^= (k&3); idx = t + 256 i
+          bs[i][0] += va[i].x; bs[i][1] += va[i].y; bs[i][2] += va[i].z; bs[i][3] += va[i].w;
         }
       }
 #pragma unroll
@@ -370,16 +375,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
     }
 
     if (want_bsum) {
-      // thread t saw, for every g, physical 16-B slot t%8 of rows k = t/8 and 16 + t/8; SW128_BASE32B
-      // XORs the 32-B chunk index (slot/2) with k&3, so its logical 4-float m-vector is:
-      const int j = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1), r = t >> 3;   // r = 0..15: 16 partials per column
+      // thread t saw, for every g, physical 16-B slot t%8 of row k = t/8; SW128_BASE32B XORs the 32-B chunk index (slot/2)
+      // with k&3, so its logical 4-float m-vector is j below.  32 partials per column (one per k row of a chunk), folded in
+      // two ordered passes into 16 slots, then summed in slot order: a fixed order, bit-reproducible.
+      const int j = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1), r = t >> 3;   // r = 0..31
+      if (r < 16) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+        for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bsum_g[r * TC_BM + g * 32 + j * 4 + q] = bs[g][q];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int q = 0; q < 4; ++q) bsum_g[r * TC_BM + g * 32 + j * 4 + q] = bs[g][q];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (r >= 16) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bsum_g[(r - 16) * TC_BM + g * 32 + j * 4 + q] += bs[g][q];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int m = m0 + t;
-      if (m < M) {
+      if (t < TC_BM && m < M) {
         float ssum = 0.f;
 #pragma unroll
         for (int rr = 0; rr < 16; ++rr) ssum += bsum_g[rr * TC_BM + t];
@@ -389,6 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
 
     // ---- epilogue: TMEM -> registers -> global ----
     const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
+    const int cg = (warp - 2) >> 2;                           // two warps per quarter: even / odd 32-column blocks
     const int mode = P->mode, relu = P->relu, ldc = P->ldc;
     const float* __restrict__ bias = P->bias;
     const float* __restrict__ mask = P->mask;
@@ -400,16 +416,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
     const int rsub = lane >> 3, c4 = (lane & 7) << 2;
     const bool vec_c = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
     const bool vec_m = mask && ((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);
-    float4 bvs[TC_BN / 32];                                   // this lane's bias quad per block, requested while the MMAs still run
+    constexpr int NBLK = (TC_BN / 32 + 1) / 2;                // 32-column blocks per warp (block c = 2 ci + cg)
+    float4 bvs[NBLK];                                         // this lane's bias quad per block, requested while the MMAs still run
 #pragma unroll
-    for (int c = 0; c < TC_BN / 32; ++c) {
-      const int n = n0 + c * 32 + c4;
-      bvs[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ci = 0; ci < NBLK; ++ci) {
+      const int n = n0 + (2 * ci + cg) * 32 + c4;
+      bvs[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (mode == GEMM_FWD && bias) {
-        if (n < N) bvs[c].x = __ldg(bias + n);
-        if (n + 1 < N) bvs[c].y = __ldg(bias + n + 1);
-        if (n + 2 < N) bvs[c].z = __ldg(bias + n + 2);
-        if (n + 3 < N) bvs[c].w = __ldg(bias + n + 3);
+        if (n < N) bvs[ci].x = __ldg(bias + n);
+        if (n + 1 < N) bvs[ci].y = __ldg(bias + n + 1);
+        if (n + 2 < N) bvs[ci].z = __ldg(bias + n + 2);
+        if (n + 3 < N) bvs[ci].w = __ldg(bias + n + 3);
       }
     }
     mbar_wait(accum_bar, 0);
@@ -420,7 +437,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
     // 32x32 block through a padded smem scratch so that global stores / mask loads are row-contiguous.
     float* scratch = reinterpret_cast<float*>(gbase) + (warp - 2) * (32 * 33);
 #pragma unroll
-    for (int c = 0; c < TC_BN / 32; ++c) {
+    for (int ci = 0; ci < NBLK; ++ci) {
+      const int c = 2 * ci + cg;
+      if (c >= TC_BN / 32) break;
       uint32_t v[32], w[32];
       float4 mkv[8];                                          // ReLU' mask quads of this lane's 8 output rows, in flight during the TMEM loads
       if (mode == GEMM_DGRAD && mask) {
@@ -449,7 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         tc_ld32_nowait(lane_addr, v);
         tc_ld32_nowait(lane_addr + (uint32_t)TC_BN, w);
         tc_ld_wait();
-        if (t == 0 && c == 0) TC_STAMP(85);
+        if (t == 0 && ci == 0) TC_STAMP(85);
         for (int mi = 1; mi < nmain; ++mi) {
           uint32_t v2[32], w2[32];
           tc_ld32_nowait(lane_addr + acc_stride * (uint32_t)mi, v2);
@@ -465,7 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         tc_ld32_nowait(lane_addr, v);                         // main[0]
         tc_ld32_nowait(lane_addr + (uint32_t)(TC_BN * TC_NMAIN), w);   // cross terms
         tc_ld_wait();
-        if (t == 0 && c == 0) TC_STAMP(85);
+        if (t == 0 && ci == 0) TC_STAMP(85);
         for (int mi = 1; mi < nmain; ++mi) {
           uint32_t v2[32];
           tc_ld32(lane_addr + acc_stride * (uint32_t)mi, v2);
@@ -473,13 +492,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
           for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
         }
       }
-      if (t == 0 && c == 0) TC_STAMP(86);
+      if (t == 0 && ci == 0) TC_STAMP(86);
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) scratch[lane * 33 + jj] = __uint_as_float(v[jj]) + __uint_as_float(w[jj]);
       __syncwarp();
-      if (t == 0 && c == 0) TC_STAMP(87);
+      if (t == 0 && ci == 0) TC_STAMP(87);
       const int n = n0 + c * 32 + c4;                         // first of this lane's four output columns
-      const float4 bv = bvs[c];
+      const float4 bv = bvs[ci];
       const int mrow0 = m0 + q * 32;
       float4 xo[8];
 #pragma unroll
@@ -517,7 +536,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         }
       }
       __syncwarp();
-      if (t == 0 && c == 0) TC_STAMP(88);
+      if (t == 0 && ci == 0) TC_STAMP(88);
     }
   }
 

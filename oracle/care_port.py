@@ -249,7 +249,7 @@ class CarePortLearner:
         std = torch.exp(log_std)
         u = mu + std * eps
         k = spec.action_scale
-        act = k * torch.tanh(u)
+        act = k * sp.tanh_tagged(u, None if tag is None else f"tanh:{tag}")
         gauss = -((u - mu) ** 2) / (2 * std ** 2) - std.log() - math.log(math.sqrt(2 * math.pi))
         logp = (gauss - torch.log(k * (1 - (act / k) ** 2 + 1e-6))).sum(-1, keepdim=True)
         return act, logp, torch.log(std)
@@ -284,7 +284,7 @@ class CarePortLearner:
 
         a_cur, logp, log_std = self._policy("ase", z.detach(), s, eps_cur, True, "cur")
         q1n, q2n = self._q("cse", "q1", "q2", z.detach(), s, a_cur, detach=True, tag="pi")
-        qmin = torch.min(q1n, q2n)
+        qmin = sp.min_tagged(q1n, q2n, "route:pi")
         pi_loss = torch.mean(-(qmin - alpha * logp)) / div
         pi_loss.backward()
         self.opt_actor.step()

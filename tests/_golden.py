@@ -143,6 +143,13 @@ def cuda_relu_masks(core, spec, replica=0, care=False):
         hP = core.debug(f"hP.{l}", replica).reshape(2, B, H) > 0
         for net in range(2):
             masks[f"q{net + 1}:cur:{l}"], masks[f"q{net + 1}:pi:{l}"] = hQ[net], hP[net]
+    # saturated tanh: the policy head's own tanh(u) per (row, action) -- value + derivative forced into the oracle, which then
+    # has to agree with it to the parity tolerance (sac_port.tanh_tagged; psave = [2B][A][8], entry 2 = tanh(u))
+    t = core.debug("psave", replica).reshape(2 * B, spec.act_dim, 8)[:, :, 2]
+    masks["tanh:next"], masks["tanh:cur"] = t[:B].clone(), t[B:].clone()
+    # the other discontinuity of the step: which twin min(Q1, Q2)(s, a~) routes the actor gradient to (tag "route:pi",
+    # True = Q1).  Handled like a ReLU bit: forced into the oracle, and a differing bit must sit on |Q1 - Q2| ~ 0
+    masks["route:pi"] = (core.debug("dq_pi", replica).reshape(2, B)[0] != 0).reshape(B, 1)
     if care:
         K = spec.num_encoders
         for l, H in enumerate(spec.mix_hidden):
@@ -155,6 +162,27 @@ def cuda_relu_masks(core, spec, replica=0, care=False):
     return masks
 
 
+def check_forced(tape, forced, what=""):
+    """Every forced bit that differs from the oracle's own decision must sit on a numerically-zero pre-activation (a ReLU
+    kink / a tie of min(Q1,Q2)); every forced tanh value must agree with the oracle's own to the parity tolerance.
+    Returns {tag: differing bits}."""
+    flips = {}
+    for tag, m in forced.items():
+        z = tape.z[tag]
+        if tag.startswith("tanh:"):
+            worst = float((z - m.reshape(z.shape)).abs().max())
+            assert worst <= REL, f"{what}tanh(u) of {tag} differs by {worst:.3e} > {REL}"
+            continue
+        diff = (z > 0) != m
+        n = int(diff.sum())
+        if n:
+            tol = REL * max(1.0, float(z.abs().mean()))
+            worst = float(z[diff].abs().max())
+            assert worst <= tol, f"{what}mask bit of {tag} differs at |z| = {worst:.3e} > {tol:.3e}: not a ReLU kink"
+            flips[tag] = n
+    return flips
+
+
 def kink_checked_step(core, port, spec, batch, e1, e2, replica=0, care=False, step_cuda=None):
     """One step of `core` (from the port's state) and of `port` with the CUDA masks forced; returns (port outputs,
     {tag: flipped bits}).  Raises AssertionError if a flipped bit is not a kink."""
@@ -163,16 +191,7 @@ def kink_checked_step(core, port, spec, batch, e1, e2, replica=0, care=False, st
     forced = cuda_relu_masks(core, spec, replica, care)
     with sp.ReluTape(forced) as tape:
         out = (port.update if care else port.update_SAC)(*batch, e1, e2)
-    flips = {}
-    for tag, m in forced.items():
-        z = tape.z[tag]
-        diff = (z > 0) != m
-        n = int(diff.sum())
-        if n:
-            tol = REL * max(1.0, float(z.abs().mean()))
-            worst = float(z[diff].abs().max())
-            assert worst <= tol, f"mask bit of {tag} differs at |z| = {worst:.3e} > {tol:.3e}: not a ReLU kink"
-            flips[tag] = n
+    flips = check_forced(tape, forced)
     return out, flips
 
 
@@ -192,7 +211,7 @@ def check_port_state(core, port, replica=0, tol=REL):
             errs += [rel_l2(gm[k], st["m"][k]), rel_l2(gv[k], st["v"][k])]
         if max(errs) > tol:
             bad.append((k, errs))
-    assert not bad, f"state differs beyond {tol} with the CUDA masks forced into the oracle: {bad[:6]}"
+    assert not bad, f"state differs beyond {tol} with the CUDA masks forced into the oracle: {[(k, [float(f"{e:.1e}") for e in es]) for k, es in bad]}"
 
 
 # ---------------------------------------------------------------------------------------------------------------

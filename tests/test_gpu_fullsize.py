@@ -15,7 +15,7 @@ import pytest
 import torch
 
 import sac_port as sp
-from _golden import (FULL_CARE_CASES, FULL_CASES, REL, FullCase, care_core_config, check_port_state, core_config,
+from _golden import (check_forced, FULL_CARE_CASES, FULL_CASES, REL, FullCase, care_core_config, check_port_state, core_config,
                      cuda_relu_masks, rel_l2, rel_scalar)
 
 pytestmark = pytest.mark.gpu
@@ -72,15 +72,7 @@ def test_chain_matches_reference_fixture_at_full_size(cuda, name, precision):
         # which is why the fixture comparison above stops at the first proven kink and this one never does)
         assert rel_scalar(float(L[0]), o["critic_loss"]) <= REL, ("critic_loss vs port with forced masks", i, float(L[0]), o["critic_loss"])
         assert rel_scalar(float(L[1]), o["actor_loss"]) <= REL, ("actor_loss vs port with forced masks", i, float(L[1]), o["actor_loss"])
-        for tag, m in forced.items():
-            z = tape.z[tag]
-            diff = (z > 0) != m
-            n = int(diff.sum())
-            if n:
-                tol = REL * max(1.0, float(z.abs().mean()))
-                worst = float(z[diff].abs().max())
-                assert worst <= tol, f"step {i}: mask bit of {tag} differs at |z| = {worst:.3e} > {tol:.3e}: not a ReLU kink"
-                total_flips += n
+        total_flips += sum(check_forced(tape, forced, f"step {i}: ").values())
     check_port_state(core, port)                       # strict 1e-4: CUDA chain == port chain with the same masks
     assert tuple(core.get_steps()) == tuple(int(x) for x in c.step_out)
     if total_flips == 0:                               # no kink anywhere in the chain: the reference's own numbers, directly

@@ -7,16 +7,20 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[64, 128], ids=["tile128x64", "tile128x128"])
+@pytest.fixture(scope="module", params=[(64, 1), (128, 1), (128, 0), (160, 1)],
+                ids=["tile128x64", "tile128x128-paired", "tile128x128", "tile128x160"])
 def lib(request):
-    """Both tile widths of the kernel (the step picks per launch group; B200SAC_TC_BN forces one)."""
+    """Every tile variant of the kernel (the step picks per launch group by a cost model; B200SAC_TC_BN forces a width,
+    B200SAC_TC_PAIR128=0 the unpaired 128-wide flavour)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import os
     from distributed_sac_b200 import _lib
-    os.environ["B200SAC_TC_BN"] = str(request.param)
+    os.environ["B200SAC_TC_BN"] = str(request.param[0])
+    os.environ["B200SAC_TC_PAIR128"] = str(request.param[1])
     yield _lib.load()
     os.environ.pop("B200SAC_TC_BN", None)
+    os.environ.pop("B200SAC_TC_PAIR128", None)
 
 
 def _p(t):
@@ -38,7 +42,7 @@ def rel(a, b):
 
 # fp32-class accuracy: 3xTF32 drops only lo*lo (~2^-22 relative per product); the tensor core's
 # truncating fp32 accumulation adds a bias ~ (#MMAs per accumulator) * 2^-24 (rotating accumulators: up to 4 pairs for
-# 64-wide tiles, 3 mains + 1 cross for 128-wide ones)
+# 64-wide tiles, 2 pairs or 3 mains + 1 cross for 128-wide ones, 2 mains + 1 cross for 160-wide ones)
 TOL = 5e-6
 
 SHAPES = [(256, 256, 256), (512, 256, 256), (128, 64, 32), (1024, 400, 400), (1280, 400, 400), (200, 72, 40),
