@@ -702,6 +702,7 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
     l.grid = dim3(tiles, R);
     l.block = dim3(WG_THREADS);
     l.smem = WG_SMEM_BYTES;
+    if (h->chain_dbg && h->plan.size() < 16) l.wg.dbg = h->chain_dbg + h->plan.size() * CH_DBG_SLOTS;
     h->plan.push_back(l);
     return 0;
   };

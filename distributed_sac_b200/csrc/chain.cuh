@@ -639,6 +639,7 @@ struct WgradAdam {
 struct WgradArgs {
   int njobs, M;
   long long rsG;
+  long long* dbg;                          // optional clock64() timeline of CTA (0,0) (B200SAC_CHAIN_DBG=1)
   WgradAdam adam;
   WgradJob job[WG_MAXJOBS];
 };
@@ -660,6 +661,10 @@ B200_D void wg_stage(float* __restrict__ dst, const float* __restrict__ src, int
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_constant__ WgradArgs A, StepConst K) {
+  long long* const dbg = (A.dbg != nullptr && (blockIdx.x | blockIdx.y) == 0 && threadIdx.x == 0) ? A.dbg : nullptr;
+  int dbg_i = 0;
+#define WG_STAMP() do { if (dbg != nullptr && dbg_i < CH_DBG_SLOTS) dbg[dbg_i++] = clock64(); } while (0)
+  WG_STAMP();                              // 0: entry
   extern __shared__ __align__(128) float wsm_raw[];
   float* sm = wsm_raw + (((128u - (smem_u32(wsm_raw) & 127u)) & 127u) >> 2);      // (pointer arithmetic keeps the shared address space)
   int ji = 0;
@@ -687,7 +692,13 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   KStamp ks_;                              // the operands come from the launch right before this one
+  WG_STAMP();                              // 1: predecessor complete
   __syncthreads();
+  // bias corrections of the fused optimizer step (two counter loads, an fp64 division and square root): evaluated now, while
+  // the operand tiles are in flight, instead of heading the epilogue
+  const WgradAdam& O = A.adam;
+  float step_size = 0.f, bc2_sqrt = 1.f;
+  if (O.enabled) adam_scalars(O.lr, O.cnt[rep].b1p[O.which], O.cnt[rep].b2p[O.which], step_size, bc2_sqrt);
   const float* __restrict__ Ag = J.A + (long long)rep * J.rsA;
   const float* __restrict__ Bg = J.B + (long long)rep * J.rsB;
   const int M = A.M;
@@ -711,6 +722,7 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
     if (!tmB) wg_stage(Bs, Bg, J.ldb, n0, J.Nin, m0, M, tid);
     if (tmA || tmB) mbar_wait(smem_u32(bar), (uint32_t)(pass & 1));
     __syncthreads();
+    WG_STAMP();                            // per pass: operands landed
     const int mcnt = (M - m0 < WG_ROWS) ? M - m0 : WG_ROWS;
     const int per = (mcnt + 7) >> 3;
     const int mb = w * per, me = (mb + per < mcnt) ? mb + per : mcnt;
@@ -757,6 +769,7 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
       }
     }
   }
+  WG_STAMP();                              // accumulation done
   // partial tiles -> fixed-order sum.  Every mapping fills the part of the [32 k][32 n] tile that holds its valid outputs.
   {
     float* pw = part + w * (WG_T * WG_T);
@@ -785,41 +798,80 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const __grid_const
     }
   }
   __syncthreads();
+  WG_STAMP();                              // partial tiles visible
   float* __restrict__ C = J.C + (long long)rep * A.rsG;
-  // fused optimizer step: bias corrections once per CTA (doubles), then adam_one per element like adam_kernel
-  const WgradAdam& O = A.adam;
-  float step_size = 0.f, bc2_sqrt = 1.f;
-  if (O.enabled) adam_scalars(O.lr, O.cnt[rep].b1p[O.which], O.cnt[rep].b2p[O.which], step_size, bc2_sqrt);
+  // fused optimizer step: adam_one per element like adam_kernel
   const float w1 = (float)(1.0 - K.beta1), b2 = (float)K.beta2, omb2 = (float)(1.0 - K.beta2), eps = (float)K.adam_eps;
-  auto apply = [&](long long gi, float g) {          // gi: index inside the trainable arena
-    float* pp = O.params + rep * O.rsP + gi;
-    float* mp = O.m + rep * O.rsM + gi;
-    float* vp = O.v + rep * O.rsM + gi;
-    float pv = *pp, mv = *mp, vv = *vp;
-    adam_one(pv, mv, vv, g, w1, b2, omb2, step_size, bc2_sqrt, eps);
-    *pp = pv; *mp = mv; *vp = vv;
-    if (O.target_delta != 0) pp[O.target_delta] = K.tau * pv + K.one_minus_tau * pp[O.target_delta];
-  };
+  // One thread = four consecutive columns of one row of the tile (128-bit accesses; row pitches, tile origins and tensor
+  // offsets are multiples of 4 floats by construction of the arena -- pad columns of a thin first layer see zero gradients
+  // and stay zero).  Every operand of the optimizer step is REQUESTED before the first dependent instruction: the (p, m, v
+  // [, target]) quadruples used to be sequential global round trips between stores -- 9.1k of the 19.3k cycles of the critic
+  // launch -- and the code is kept compact on purpose: it runs once per CTA out of a cold instruction cache (measured with
+  // scripts/chain_timeline.py: 4x-unrolled scalar version 5.3k cycles).
+  const bool has_t = O.enabled && O.target_delta != 0;
+  const int kk = tid >> 3, nn4 = (tid & 7) << 2;
+  const bool okq = k0 + kk < J.Kout && n0 + nn4 < J.Nin;
+  const long long ci = (long long)(k0 + kk) * J.ldc + n0 + nn4;
+  const long long gi = (J.C - O.grads) + ci;
+  float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = p4, v4 = p4, t4 = p4;
+  if (okq && O.enabled) {
+    const float* pp = O.params + rep * O.rsP + gi;
+    p4 = *reinterpret_cast<const float4*>(pp);
+    m4 = *reinterpret_cast<const float4*>(O.m + rep * O.rsM + gi);
+    v4 = *reinterpret_cast<const float4*>(O.v + rep * O.rsM + gi);
+    if (has_t) t4 = *reinterpret_cast<const float4*>(pp + O.target_delta);
+  }
+  const bool bias_thread = bn == 0 && J.C2 != nullptr && tid < WG_T && k0 + tid < J.Kout;
+  float bp = 0.f, bm = 0.f, bv_ = 0.f, bt = 0.f;
+  const long long bgi = bias_thread ? (J.C2 - O.grads) + k0 + tid : 0;
+  if (bias_thread && O.enabled) {
+    const float* pp = O.params + rep * O.rsP + bgi;
+    bp = *pp;
+    bm = (O.m + rep * O.rsM)[bgi];
+    bv_ = (O.v + rep * O.rsM)[bgi];
+    if (has_t) bt = pp[O.target_delta];
+  }
+  float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int o = tid + WG_THREADS * u;
-    const int kk = o >> 5, nn = o & 31;
-    if (k0 + kk < J.Kout && n0 + nn < J.Nin) {
-      float v = 0.f;
-#pragma unroll
-      for (int ww = 0; ww < 8; ++ww) v += part[ww * (WG_T * WG_T) + o];
-      const long long ci = (long long)(k0 + kk) * J.ldc + n0 + nn;
-      C[ci] = v;
-      if (O.enabled) apply((J.C - O.grads) + ci, v);
+  for (int ww = 0; ww < 8; ++ww) {           // fixed order: warp 0's partial first
+    const float4 q = *reinterpret_cast<const float4*>(part + ww * (WG_T * WG_T) + kk * WG_T + nn4);
+    g4.x += q.x; g4.y += q.y; g4.z += q.z; g4.w += q.w;
+  }
+  WG_STAMP();                              // partial tiles summed (optimizer operands still in flight)
+  if (okq) {
+    *reinterpret_cast<float4*>(C + ci) = g4;
+    if (O.enabled) {
+      adam_one(p4.x, m4.x, v4.x, g4.x, w1, b2, omb2, step_size, bc2_sqrt, eps);
+      adam_one(p4.y, m4.y, v4.y, g4.y, w1, b2, omb2, step_size, bc2_sqrt, eps);
+      adam_one(p4.z, m4.z, v4.z, g4.z, w1, b2, omb2, step_size, bc2_sqrt, eps);
+      adam_one(p4.w, m4.w, v4.w, g4.w, w1, b2, omb2, step_size, bc2_sqrt, eps);
+      float* pp = O.params + rep * O.rsP + gi;
+      *reinterpret_cast<float4*>(pp) = p4;
+      *reinterpret_cast<float4*>(O.m + rep * O.rsM + gi) = m4;
+      *reinterpret_cast<float4*>(O.v + rep * O.rsM + gi) = v4;
+      if (has_t)
+        *reinterpret_cast<float4*>(pp + O.target_delta) =
+            make_float4(K.tau * p4.x + K.one_minus_tau * t4.x, K.tau * p4.y + K.one_minus_tau * t4.y,
+                        K.tau * p4.z + K.one_minus_tau * t4.z, K.tau * p4.w + K.one_minus_tau * t4.w);
     }
   }
-  if (bn == 0 && J.C2 != nullptr && tid < WG_T && k0 + tid < J.Kout) {
+  if (bias_thread) {
     float v = 0.f;
 #pragma unroll
     for (int ww = 0; ww < 8; ++ww) v += bpart[ww * WG_T + tid];
     (J.C2 + (long long)rep * A.rsG)[k0 + tid] = v;
-    if (O.enabled) apply((J.C2 - O.grads) + k0 + tid, v);
+    if (O.enabled) {
+      adam_one(bp, bm, bv_, v, w1, b2, omb2, step_size, bc2_sqrt, eps);
+      float* pp = O.params + rep * O.rsP + bgi;
+      *pp = bp;
+      (O.m + rep * O.rsM)[bgi] = bm;
+      (O.v + rep * O.rsM)[bgi] = bv_;
+      if (has_t) pp[O.target_delta] = K.tau * bp + K.one_minus_tau * bt;
+    }
   }
+  WG_STAMP();                              // reduction + optimizer step done
+  if (dbg != nullptr) dbg[CH_DBG_SLOTS - 1] = dbg_i;
+#undef WG_STAMP
 }
 
 }  // namespace bsac
