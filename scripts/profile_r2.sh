@@ -9,11 +9,11 @@ TAG=${1:-r2}
 OUT=gpurun_out
 mkdir -p $OUT
 B="python bench.py --no-cpu --ring 65536 --e2e-steps 2 --configs none"
-ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 66 --csv --log-file $OUT/${TAG}_launches_LL_chain.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 220 -c 55 --csv --log-file $OUT/${TAG}_launches_LL_chain.csv \
     $B --workload LL --precision 0 --steps 20 --warmup 5 > $OUT/ncu_ll.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 87 --csv --log-file $OUT/${TAG}_launches_VS_tc.csv \
     $B --workload VS --precision 1 --steps 20 --warmup 5 > $OUT/ncu_vs.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none -s 200 -c 66 --csv \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none -s 220 -c 55 --csv \
     --log-file $OUT/${TAG}_traffic_LL_chain.csv $B --workload LL --precision 0 --steps 20 --warmup 5 > $OUT/ncu_tr_ll.log 2>&1
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none -s 200 -c 87 --csv \
     --log-file $OUT/${TAG}_traffic_VS_tc.csv $B --workload VS --precision 1 --steps 20 --warmup 5 > $OUT/ncu_tr_vs.log 2>&1
