@@ -525,6 +525,11 @@ static int make_tc_prob(const GemmProb& p, int rep, TcProb& t, int bn = 64) {
     if (int rc = make_map(&t.tmA, A, p.M, p.K, p.lda, TC_BK, true)) return rc;
     if (int rc = make_map(&t.tmB, B, p.N, p.K, p.ldb, TC_BK, true)) return rc;
   }
+  // output map for the bulk-store epilogue: [M][N] fp32, row pitch ldc, boxes of 32 x 32
+  if ((p.ldc % 4) == 0 && (((uintptr_t)t.C) & 15) == 0 && getenv("B200SAC_TC_NO_TMA_STORE") == nullptr) {
+    if (int rc = make_map(&t.tmC, t.C, p.N, p.M, p.ldc, 32)) return rc;
+    t.c_tma = 1;
+  }
   return 0;
 }
 

@@ -69,6 +69,7 @@ constexpr int TC_SMEM_BYTES = TcCfg<64>::kSmemBytes;
 struct alignas(128) TcProb {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmC;     // output [M][N] row-major, box 32 x 32, SWIZZLE_128B (valid when c_tma != 0)
   const float* bias;
   const float* mask;
   float* C;
@@ -77,7 +78,7 @@ struct alignas(128) TcProb {
   int ldc, ldmask;
   int mode, relu;
   int a_mn, b_mn;
-  int pad[1];
+  int c_tma;           // 1: the epilogue stores its 32 x 32 blocks with cp.async.bulk.tensor (ldc % 4 == 0, 16-B aligned C)
   long long* dbg;      // optional clock64() timeline of CTA (0,0) (b200sac_tc_gemm_timeline)
 };
 
@@ -120,6 +121,12 @@ B200_D void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uin
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+B200_D void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+B200_D void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+B200_D void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 B200_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 B200_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 B200_D void tc_commit(uint32_t bar) {
@@ -279,9 +286,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
     if (lane == 0) {
       const uint32_t idesc = tc_instr_desc(a_mn, b_mn, TC_BN);
       const int nmain = tc_nmain(nk, TC_NMAIN);          // chunk kc accumulates into main[(kc * nmain) / nk]
+      // (kept free of run-time divisions: this single thread's scalar work between two chunks is on the critical path --
+      //  ~300 cycles per chunk with the divisions, measured with scripts/tc_timeline.py)
+      int mi = 0, acc_pos = 0, acc_lim = nk, s = 0;
+      uint32_t ph = 0;
       for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kc / TC_STAGES) & 1u;
+        bool new_main = kc == 0;
+        if (acc_pos >= acc_lim) { ++mi; acc_lim += nk; new_main = true; }     // mi == (kc * nmain) / nk
+        acc_pos += nmain;
         mbar_wait(ready_bar(s), ph);
         if (kc < 16) TC_STAMP(50 + 2 * kc);
         tc_fence_after();
@@ -291,8 +303,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         const uint64_t dA0 = tc_smem_desc(st, a_mn ? 4096u : 16u, a_mn ? 512u : 1024u, a_mn ? 1u : 2u);
         const uint64_t dB0 = tc_smem_desc(st + 2 * TC_A_BYTES, b_mn ? 4096u : 16u, b_mn ? 512u : 1024u, b_mn ? 1u : 2u);
         const uint64_t stepA = a_mn ? (1024u >> 4) : (32u >> 4), stepB = b_mn ? (1024u >> 4) : (32u >> 4);
-        const int mi = (kc * nmain) / nk;
-        const bool new_main = (kc == 0) || (((kc - 1) * nmain) / nk != mi);
         if (Cfg::kPaired) {
           const uint32_t d_pair = tmem_base + (uint32_t)(2 * TC_BN * mi);       // [main_mi | cross_mi]
           const uint32_t idesc2 = tc_instr_desc(a_mn, b_mn, 2 * TC_BN);
@@ -316,6 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         }
         tc_commit(empty_bar(s));          // smem stage reusable once these MMAs have read it
         if (kc < 16) TC_STAMP(51 + 2 * kc);
+        if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
       }
       tc_commit(accum_bar);               // accumulator complete
     }
@@ -416,6 +427,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
     const int rsub = lane >> 3, c4 = (lane & 7) << 2;
     const bool vec_c = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
     const bool vec_m = mask && ((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+    // Output path: the 32 x 32 block of a warp goes to shared memory in the thread = row layout tcgen05.ld delivers (8 swizzled
+    // 128-bit stores per thread, conflict-free) and leaves as ONE cp.async.bulk.tensor store that clips ragged edges itself --
+    // instead of a transposition through padded shared memory + 8 row stores per lane (1.5 k of the ~2 k cycles of a block,
+    // measured).  Falls back to the row-store path when C cannot have a tensor map (ldc % 4 != 0) or the mask is unaligned.
+    const bool use_tma = P->c_tma != 0 && (!(P->mode == GEMM_DGRAD && P->mask) || (((P->ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(P->mask) & 15) == 0)));
     constexpr int NBLK = (TC_BN / 32 + 1) / 2;                // 32-column blocks per warp (block c = 2 ci + cg)
     float4 bvs[NBLK];                                         // this lane's bias quad per block, requested while the MMAs still run
 #pragma unroll
@@ -428,6 +444,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         if (n + 2 < N) bvs[ci].z = __ldg(bias + n + 2);
         if (n + 3 < N) bvs[ci].w = __ldg(bias + n + 3);
       }
+    }
+    float bcol[NBLK];                                         // thread = row layout: lane j holds the bias of column j of the block
+#pragma unroll
+    for (int ci = 0; ci < NBLK; ++ci) {
+      const int n = n0 + (2 * ci + cg) * 32 + lane;
+      bcol[ci] = (use_tma && mode == GEMM_FWD && bias && n < N) ? __ldg(bias + n) : 0.f;
     }
     mbar_wait(accum_bar, 0);
     if (t == 0) TC_STAMP(82);
@@ -442,7 +464,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
       if (c >= TC_BN / 32) break;
       uint32_t v[32], w[32];
       float4 mkv[8];                                          // ReLU' mask quads of this lane's 8 output rows, in flight during the TMEM loads
-      if (mode == GEMM_DGRAD && mask) {
+      if (use_tma && mode == GEMM_DGRAD && mask) {            // thread = row: the 8 column quads of this thread's own row
+        const int m_ = m0 + q * 32 + lane;
+        const float* __restrict__ mp_ = mask + (long long)m_ * ldmask + n0 + c * 32;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int n_ = n0 + c * 32 + 4 * u;
+          float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (m_ < M) {
+            if (n_ + 3 < N) {
+              mk = __ldg(reinterpret_cast<const float4*>(mp_ + 4 * u));
+            } else {
+              if (n_ < N) mk.x = ldg_f32(mp_ + 4 * u);
+              if (n_ + 1 < N) mk.y = ldg_f32(mp_ + 4 * u + 1);
+              if (n_ + 2 < N) mk.z = ldg_f32(mp_ + 4 * u + 2);
+              if (n_ + 3 < N) mk.w = ldg_f32(mp_ + 4 * u + 3);
+            }
+          }
+          mkv[u] = mk;
+        }
+      } else if (mode == GEMM_DGRAD && mask) {
         const int n_ = n0 + c * 32 + c4;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -493,6 +534,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
         }
       }
       if (t == 0 && ci == 0) TC_STAMP(86);
+      if (use_tma) {
+        float x[32];
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) x[jj] = __uint_as_float(v[jj]) + __uint_as_float(w[jj]);
+        if (mode == GEMM_FWD) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            x[jj] += __shfl_sync(0xffffffffu, bcol[ci], jj);
+            if (relu) x[jj] = fmaxf(x[jj], 0.f);
+          }
+        } else if (mode == GEMM_DGRAD && mask) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            x[4 * u] = mkv[u].x > 0.f ? x[4 * u] : 0.f; x[4 * u + 1] = mkv[u].y > 0.f ? x[4 * u + 1] : 0.f;
+            x[4 * u + 2] = mkv[u].z > 0.f ? x[4 * u + 2] : 0.f; x[4 * u + 3] = mkv[u].w > 0.f ? x[4 * u + 3] : 0.f;
+          }
+        }
+        // two 4-KB staging tiles per warp (the pipeline stages are free); a third block (160-wide tiles) waits for the first
+        uint8_t* stg = gbase + (size_t)(warp - 2) * 8192 + (size_t)(ci & 1) * 4096;
+        if (ci >= 2) { if (lane == 0) tma_store_wait_read(); __syncwarp(); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)                           // SWIZZLE_128B: 16-B chunk u of row r sits at chunk u ^ (r & 7)
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (t == 0 && ci == 0) TC_STAMP(87);
+        if (lane == 0 && m0 + q * 32 < M && n0 + c * 32 < N) {
+          tma_store_2d(&P->tmC, smem_u32(stg), n0 + c * 32, m0 + q * 32);
+          tma_store_commit();
+        }
+        if (t == 0 && ci == 0) TC_STAMP(88);
+        continue;
+      }
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) scratch[lane * 33 + jj] = __uint_as_float(v[jj]) + __uint_as_float(w[jj]);
       __syncwarp();
@@ -538,6 +612,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcProb* __
       __syncwarp();
       if (t == 0 && ci == 0) TC_STAMP(88);
     }
+    if (use_tma && lane == 0) tma_store_wait_read();          // the staging tiles must outlive the bulk reads
   }
 
   if (threadIdx.x == 64) TC_STAMP(83);
