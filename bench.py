@@ -539,7 +539,10 @@ def roofline_block(b, leg, workload, R, traffic=None, traffic_src=None):
                                                      (top[0] == "gemm_tc" and "tcgen05" in n) or
                                                      (top[0] == "gemm_ffma" and n.startswith("gemm_") and "tcgen05" not in n))},
         "per_launch_us_in_graph": [[n, round(t, 2)] for n, t in tl],
-        "note": "latency-bound: %d dependent launches per step; params + Adam state stay L2-resident between steps" % leg["launches_per_step"],
+        "note": ("neither roof binds: the step runs out of L2 (`traffic` = measured DRAM bytes per step with the caches left alone vs "
+                 "`algorithmic_bytes_per_step`) as %d dependent launches; what bounds it is the per-SM TMA request cadence inside the "
+                 "chained / tcgen05 kernels (~675 cycles per bulk request, ~105 cycles per tf32 MMA) and the kernel boundaries "
+                 "(DESIGN.md 4, profiles/README.md)") % leg["launches_per_step"],
     }
 
 
