@@ -215,7 +215,7 @@ struct Buf {           // [R][n] fp32 (or int32) slab slice
   long long rs = 0;    // replica stride in floats
 };
 
-enum LaunchKind { L_POLICY_DOUT, L_CARE_TAB, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_THIN, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM, L_CHAIN, L_WGRAD, L_CHAIN2 };
+enum LaunchKind { L_POLICY_DOUT, L_CARE_TAB, L_CARE_MIXFWD, L_CARE_MIX, L_CARE_MIXBWD, L_CARE_TABRED, L_CARE_TABWG, L_GEMM_BIG, L_GEMM_SMALL, L_GEMM_THIN, L_GEMM_TC, L_POLICY, L_CHEADS, L_AQHEADS, L_HEADBWD, L_ADAM, L_CHAIN, L_WGRAD, L_CHAIN2 };
 
 struct Launch {
   LaunchKind kind;
@@ -231,6 +231,7 @@ struct Launch {
   PolicyDoutArgs pdo;
   CareTabArgs ctab;
   CareMixArgs cmix;
+  CareMixFwdArgs cmf;
   CareMixBwdArgs cmixb;
   CareTabReduceArgs ctred;
   CareTabWgradArgs ctwg;
@@ -1132,12 +1133,59 @@ static int build_plan(b200sac* h) {
     l.block = dim3(256);
     h->plan.push_back(l);
   };
+  // mixture layers + attention mix of up to three encoder instances in ONE launch (care_mixfwd_kernel: all mixture weights of
+  // an instance resident in shared memory); falls back to the grouped-GEMM path when the weights do not fit
+  struct EncJob { int inst, xs_row0, rows; float* d1; long long rs1; int ld1; float* d2; long long rs2; int ld2; int off2; };
+  auto care_encode = [&](std::vector<EncJob> jobs) {
+    CareMixFwdArgs A;
+    memset(&A, 0, sizeof(A));
+    A.njobs = (int)jobs.size(); A.nl = nmix; A.K = Kenc; A.B = B;
+    A.params = h->params; A.rsP = rsP;
+    A.XS = h->XS.p; A.rsXS = h->XS.rs; A.ldx = h->K.obs;
+    A.tid = (const int*)h->tid.p; A.rsR = h->r.rs;
+    A.row_w = h->care_row_w; A.off_att = h->care_off_att; A.off_ctx = h->care_off_ctx; A.mo = c.mix_out; A.co = c.ctx_out;
+    bool ok = nmix >= 1 && nmix <= CMF_MAXL && (int)jobs.size() <= CMF_MAXJOBS && getenv("B200SAC_NO_CARE_FUSED") == nullptr;
+    for (int l = 0; ok && l < nmix; ++l) {
+      A.w_off[l] = L.mix[l].w; A.b_off[l] = L.mix[l].b; A.in[l] = L.mix[l].in; A.out[l] = L.mix[l].out;
+      A.maxw = std::max(A.maxw, L.mix[l].out);
+    }
+    int cta = 0;
+    for (size_t i = 0; ok && i < jobs.size(); ++i) {
+      const EncJob& e = jobs[i];
+      CareMixFwdJob& J = A.job[i];
+      const int rows_buf = e.inst == 0 ? 2 * B : B;
+      J.inst_delta = e.inst == 1 ? L.target_delta : 0;
+      J.rows = e.rows; J.xs_row0 = e.xs_row0; J.out_row0 = e.inst == 0 ? e.xs_row0 : 0; J.rows_buf = rows_buf;
+      J.cta0 = cta; cta += (e.rows + CMF_ROWS - 1) / CMF_ROWS;
+      J.tab = h->careTab[e.inst].p; J.rsTab = h->careTab[e.inst].rs;
+      for (int l = 0; l < nmix; ++l) {
+        const Buf& ob = (l == nmix - 1) ? h->mixZ[e.inst] : h->mixH[e.inst][l];
+        J.H[l] = ob.p; J.rsH[l] = ob.rs;
+      }
+      J.dst1 = e.d1; J.rsD1 = e.rs1; J.ld1 = e.ld1; J.dst2 = e.d2; J.rsD2 = e.rs2; J.ld2 = e.ld2; J.row_off2 = e.off2;
+    }
+    const size_t smem = ok ? care_mixfwd_smem_floats(A) * sizeof(float) : 0;
+    if (ok && smem <= 225 * 1024 &&
+        cudaFuncSetAttribute(care_mixfwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) == cudaSuccess) {
+      Launch l;
+      l.kind = L_CARE_MIXFWD;
+      l.cmf = A;
+      l.grid = dim3(cta, R);
+      l.block = dim3(CMF_THREADS);
+      l.smem = smem;
+      h->plan.push_back(l);
+      return;
+    }
+    std::vector<std::tuple<int, int, int>> mj;
+    for (auto& e : jobs) mj.push_back(std::make_tuple(e.inst, e.xs_row0, e.rows));
+    care_mixture_fwd(mj);
+    for (auto& e : jobs) care_mix(e.inst, e.rows, e.d1, e.rs1, e.ld1, e.d2, e.rs2, e.ld2, e.off2);
+  };
   if (c.care) {
     // encoded states of [s'; s] with the critic's (== actor's, tied) encoder and of s' with the target's
     care_tables({0, 1});
-    care_mixture_fwd({std::make_tuple(0, 0, 2 * B), std::make_tuple(1, 0, B)});
-    care_mix(0, 2 * B, h->XA.p, h->XA.rs, h->K.ldxa, h->XQ.p, h->XQ.rs, h->K.ldx, B);
-    care_mix(1, B, h->XT.p, h->XT.rs, h->K.ldx, nullptr, 0, 0, 0);
+    care_encode({EncJob{0, 0, 2 * B, h->XA.p, h->XA.rs, h->K.ldxa, h->XQ.p, h->XQ.rs, h->K.ldx, B},
+                 EncJob{1, 0, B, h->XT.p, h->XT.rs, h->K.ldx, nullptr, 0, 0, 0}});
   }
 
   auto fwd = [&](const float* Ain, long long rsA, int M, const LayerOff& lo, bool target_or_local_params, float* out,
@@ -1468,8 +1516,7 @@ static int build_plan(b200sac* h) {
   adam(0, 0);
   if (c.care) {          // encoded states of s with the UPDATED critic encoder for the actor pass (learner.py:336-341)
     care_tables({2});
-    care_mixture_fwd({std::make_tuple(2, B, B)});
-    care_mix(2, B, h->XP.p, h->XP.rs, h->K.ldx, nullptr, 0, 0, 0);
+    care_encode({EncJob{2, B, B, h->XP.p, h->XP.rs, h->K.ldx, nullptr, 0, 0, 0}});
   }
   // ---- Phase D: actor pass through the updated critics ---------------------------------------
   for (int l = 0; l < Lc; ++l) {
@@ -1614,6 +1661,9 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
         break;
       case L_CARE_MIX:
         launch_k(care_mix_kernel, l.grid, l.block, 0, s, l.cmix);
+        break;
+      case L_CARE_MIXFWD:
+        launch_k(care_mixfwd_kernel, l.grid, l.block, l.smem, s, l.cmf);
         break;
       case L_CARE_MIXBWD:
         launch_k(care_mix_bwd_kernel, l.grid, l.block, 0, s, l.cmixb);
@@ -2459,6 +2509,7 @@ static const char* launch_name(const Launch& l, const std::vector<GemmProb>& hp,
     case L_POLICY_DOUT: return "policy_dout";
     case L_CARE_TAB: return "care_tables";
     case L_CARE_MIX: return "care_mix";
+    case L_CARE_MIXFWD: return "care_mixture_fwd+mix";
     case L_CARE_MIXBWD: return "care_mix_bwd";
     case L_CARE_TABRED: return "care_tab_reduce";
     case L_CARE_TABWG: return "care_tab_wgrad";

@@ -354,4 +354,204 @@ __global__ void __launch_bounds__(256) care_tab_wgrad_kernel(CareTabWgradArgs P)
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Fused mixture-of-encoders forward (+ the attention mix): state_encoder.py:98-129 for up to three encoder instances in one
+// launch.  As K grouped problems per layer on the GEMM engine the 39->50->50 encoders were 4 320 tiles of 32 x 32 whose
+// launch cost dwarfed their 40 k FMAs each (17 + 19 us for the two layers, + 6 + 6 us of care_mix, measured at B = 1 280).
+// Here a CTA keeps ALL mixture weights of its instance in shared memory (K * sum(in*out) floats = 107 KB at the reference's
+// dims), owns CMF_ROWS rows, and warp k walks encoder k through its layers with the activations in shared memory (input rows
+// transposed so that eight rows of one input column are two broadcast 128-bit loads; lane = output neuron, 8 x 2
+// accumulators; one warp per (encoder, 8-row group)).  Every layer's output is also stored for the backward pass (mixH / mixZ, same layout as before); the mix
+// [ctx[t] | sum_k att[t][k] Z_k / sum_k att[t][k]] is evaluated in k order exactly like care_mix_kernel and written
+// straight into the consumer MLPs' input buffers.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int CMF_ROWS = 32;               // rows per CTA
+constexpr int CMF_RP = CMF_ROWS + 4;       // row pitch of the transposed activation tiles (conflict-free 128-bit stores)
+constexpr int CMF_MAXL = 4;                // mixture layers
+constexpr int CMF_MAXJOBS = 3;
+constexpr int CMF_THREADS = 768;           // 24 warps: one (encoder, 8-row group) task each at K = 6 -- six warps per scheduler hide the
+                                           // shared-memory latency of the inner loop (6 busy warps of 8: 25 us per launch, measured)
+
+struct CareMixFwdJob {
+  long long inst_delta;                    // parameter offset of the encoder instance
+  int rows, xs_row0, out_row0, rows_buf;   // rows of the job; first XS row; first row / row count of the instance's buffers
+  int cta0;                                // first blockIdx.x of the job
+  const float* tab; long long rsTab;
+  float* H[CMF_MAXL]; long long rsH[CMF_MAXL];    // outputs of layers 0..nl-1 ([K][rows_buf][pitch4(out)]); the last one is Z
+  float* dst1; long long rsD1; int ld1;
+  float* dst2; long long rsD2; int ld2; int row_off2;
+};
+struct CareMixFwdArgs {
+  int njobs, nl, K, B;
+  const float* params; long long rsP;
+  long long w_off[CMF_MAXL], b_off[CMF_MAXL];
+  int in[CMF_MAXL], out[CMF_MAXL];
+  const float* XS; long long rsXS; int ldx;
+  const int* tid; long long rsR;
+  int row_w, off_att, off_ctx, mo, co;
+  int maxw;                                // widest hidden / output layer
+  CareMixFwdJob job[CMF_MAXJOBS];
+};
+
+// shared memory (floats): weights + biases of every layer, xs [in0][RP], ha / hb [K][maxw][RP] (ping-pong hidden tiles),
+// zs [K][ROWS][mo], att [ROWS][K + 1]
+static inline size_t care_mixfwd_smem_floats(const CareMixFwdArgs& A) {
+  size_t n = 0;
+  for (int l = 0; l < A.nl; ++l) n += (((size_t)A.K * A.out[l] * A.in[l] + 3) & ~(size_t)3) + (((size_t)A.K * A.out[l] + 3) & ~(size_t)3);
+  n += (size_t)A.in[0] * CMF_RP;
+  n += (size_t)(A.nl > 2 ? 2 : 1) * A.K * A.maxw * CMF_RP;
+  n += (size_t)A.K * CMF_ROWS * A.mo;
+  n += (size_t)CMF_ROWS * (A.K + 1);
+  return n + 8;
+}
+
+__global__ void __launch_bounds__(CMF_THREADS, 1) care_mixfwd_kernel(const __grid_constant__ CareMixFwdArgs A) {
+  extern __shared__ __align__(16) float cmf_sm[];
+  int ji = 0;
+  for (int j = 1; j < A.njobs; ++j)
+    if ((int)blockIdx.x >= A.job[j].cta0) ji = j;
+  const CareMixFwdJob& J = A.job[ji];
+  const int rep = blockIdx.y;
+  const int r0 = ((int)blockIdx.x - J.cta0) * CMF_ROWS;
+  const int nrows = J.rows - r0 < CMF_ROWS ? J.rows - r0 : CMF_ROWS;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int K = A.K;
+  // carve
+  float* Ws[CMF_MAXL]; float* bs[CMF_MAXL];
+  float* p = cmf_sm;
+  for (int l = 0; l < A.nl; ++l) { Ws[l] = p; p += (size_t)K * A.out[l] * A.in[l]; p = cmf_sm + (((p - cmf_sm) + 3) & ~3); }
+  for (int l = 0; l < A.nl; ++l) { bs[l] = p; p += ((K * A.out[l] + 3) & ~3); }
+  float* xs = p; p += A.in[0] * CMF_RP;
+  float* ha = p; p += (size_t)K * A.maxw * CMF_RP;
+  float* hb = ha;
+  if (A.nl > 2) { hb = p; p += (size_t)K * A.maxw * CMF_RP; }
+  float* zs = p; p += (size_t)K * CMF_ROWS * A.mo;
+  float* att = p;
+  // ---- weights: do not depend on the launch before this one (the optimizer step that wrote them is further back) ----------
+  const float* par = A.params + (long long)rep * A.rsP + J.inst_delta;
+  for (int l = 0; l < A.nl; ++l) {
+    const int nW = K * A.out[l] * A.in[l], nb = K * A.out[l];
+    const float* gW = par + A.w_off[l];
+    const float* gb = par + A.b_off[l];
+    if ((nW & 3) == 0) {
+      for (int e = tid; e < (nW >> 2); e += CMF_THREADS) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(Ws[l] + 4 * e);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gW + 4 * e) : "memory");
+      }
+    } else {
+      for (int e = tid; e < nW; e += CMF_THREADS) Ws[l][e] = __ldg(gW + e);
+    }
+    for (int e = tid; e < nb; e += CMF_THREADS) bs[l][e] = __ldg(gb + e);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  KStamp ks_;                              // XS / the task tables come from the launches before this one
+  // ---- input rows, transposed: xs[i][r] ------------------------------------------------------------------------------
+  {
+    const float* X = A.XS + (long long)rep * A.rsXS + (long long)(J.xs_row0 + r0) * A.ldx;
+    const int in0 = A.in[0];
+    for (int e = tid; e < CMF_ROWS * in0; e += CMF_THREADS) {
+      const int r = e / in0, i = e - r * in0;
+      xs[i * CMF_RP + r] = r < nrows ? X[(long long)r * A.ldx + i] : 0.f;
+    }
+    // attention weights of the rows' tasks (+ their sum, in k order like care_mix_kernel)
+    if (tid < CMF_ROWS) {
+      float den = 0.f;
+      if (tid < nrows) {
+        const int t = (A.tid + rep * A.rsR)[(J.out_row0 + r0 + tid) % A.B];
+        const float* trow = J.tab + rep * J.rsTab + (long long)t * A.row_w;
+        for (int k = 0; k < K; ++k) { const float a = trow[A.off_att + k]; att[tid * (K + 1) + k] = a; den += a; }
+      }
+      att[tid * (K + 1) + K] = den;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- one task = (encoder k, group of 8 rows): walks the encoder's layers for its rows; tasks are independent ------------
+  for (int task = w; task < K * (CMF_ROWS / 8); task += CMF_THREADS / 32) {
+    const int k = task / (CMF_ROWS / 8), g = (task - k * (CMF_ROWS / 8)) * 8;
+    const float* In = xs;                  // layer 0 reads the shared input tile; later layers this encoder's own hidden tile
+    int in_pitch_k = 0;                    // 0: shared tile; else per-encoder stride
+    float* Out = ha;
+    for (int l = 0; l < A.nl; ++l) {
+      const int in = A.in[l], out = A.out[l];
+      const bool last = l == A.nl - 1;
+      const float* Wk = Ws[l] + (size_t)k * out * in;
+      const float* bk = bs[l] + k * out;
+      const float* Ik = In + (size_t)in_pitch_k * k;
+      const int po = (out + 3) & ~3;
+      float* Hg = J.H[l] + (long long)rep * J.rsH[l] + ((long long)k * J.rows_buf + J.out_row0 + r0) * po;
+      for (int o0 = 0; o0 < out; o0 += 64) {
+        const int oa = o0 + lane, ob = o0 + 32 + lane;
+        const bool va = oa < out, vb = ob < out;
+        const float* wa = Wk + (size_t)(va ? oa : 0) * in;
+        const float* wb = Wk + (size_t)(vb ? ob : 0) * in;
+        const float ba = va ? bk[oa] : 0.f, bb = vb ? bk[ob] : 0.f;
+        float acc0[8], acc1[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { acc0[q] = 0.f; acc1[q] = 0.f; }
+#pragma unroll 2
+        for (int i = 0; i < in; ++i) {
+          const float4 x0 = *reinterpret_cast<const float4*>(Ik + i * CMF_RP + g);
+          const float4 x1 = *reinterpret_cast<const float4*>(Ik + i * CMF_RP + g + 4);
+          const float w0 = wa[i], w1 = wb[i];
+          acc0[0] = fmaf(x0.x, w0, acc0[0]); acc0[1] = fmaf(x0.y, w0, acc0[1]); acc0[2] = fmaf(x0.z, w0, acc0[2]); acc0[3] = fmaf(x0.w, w0, acc0[3]);
+          acc0[4] = fmaf(x1.x, w0, acc0[4]); acc0[5] = fmaf(x1.y, w0, acc0[5]); acc0[6] = fmaf(x1.z, w0, acc0[6]); acc0[7] = fmaf(x1.w, w0, acc0[7]);
+          acc1[0] = fmaf(x0.x, w1, acc1[0]); acc1[1] = fmaf(x0.y, w1, acc1[1]); acc1[2] = fmaf(x0.z, w1, acc1[2]); acc1[3] = fmaf(x0.w, w1, acc1[3]);
+          acc1[4] = fmaf(x1.x, w1, acc1[4]); acc1[5] = fmaf(x1.y, w1, acc1[5]); acc1[6] = fmaf(x1.z, w1, acc1[6]); acc1[7] = fmaf(x1.w, w1, acc1[7]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float v0 = acc0[q] + ba, v1 = acc1[q] + bb;
+          if (!last) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          acc0[q] = v0; acc1[q] = v1;
+          const int r = g + q;
+          if (r < nrows) {
+            if (va) Hg[(long long)r * po + oa] = v0;
+            if (vb) Hg[(long long)r * po + ob] = v1;
+          }
+        }
+        if (last) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (va) zs[((size_t)k * CMF_ROWS + g + q) * A.mo + oa] = acc0[q];
+            if (vb) zs[((size_t)k * CMF_ROWS + g + q) * A.mo + ob] = acc1[q];
+          }
+        } else {
+          float* Ok = Out + (size_t)k * A.maxw * CMF_RP;
+          if (va) {
+            *reinterpret_cast<float4*>(Ok + oa * CMF_RP + g) = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+            *reinterpret_cast<float4*>(Ok + oa * CMF_RP + g + 4) = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+          }
+          if (vb) {
+            *reinterpret_cast<float4*>(Ok + ob * CMF_RP + g) = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+            *reinterpret_cast<float4*>(Ok + ob * CMF_RP + g + 4) = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+          }
+        }
+      }
+      __syncwarp();                        // this warp's columns of layer l are complete before it reads them as layer l+1's input
+      In = Out; in_pitch_k = A.maxw * CMF_RP;
+      Out = (Out == ha) ? hb : ha;
+    }
+  }
+  __syncthreads();
+  // ---- mix: [ctx[t] | sum_k att_k Z_k / sum_k att_k], k ascending ------------------------------------------------------------
+  for (int e = tid; e < nrows * A.co; e += CMF_THREADS) {
+    const int r = e / A.co, j = e - r * A.co;
+    const int rg = J.out_row0 + r0 + r;
+    const int t = (A.tid + rep * A.rsR)[rg % A.B];
+    const float v = (J.tab + rep * J.rsTab + (long long)t * A.row_w)[A.off_ctx + j];
+    (J.dst1 + rep * J.rsD1 + (long long)rg * J.ld1)[j] = v;
+    if (J.dst2 != nullptr && rg >= J.row_off2) (J.dst2 + rep * J.rsD2 + (long long)(rg - J.row_off2) * J.ld2)[j] = v;
+  }
+  for (int e = tid; e < nrows * A.mo; e += CMF_THREADS) {
+    const int r = e / A.mo, j = e - r * A.mo;
+    const int rg = J.out_row0 + r0 + r;
+    float num = 0.f;
+    for (int k = 0; k < K; ++k) num += zs[((size_t)k * CMF_ROWS + r) * A.mo + j] * att[r * (K + 1) + k];
+    const float v = num / att[r * (K + 1) + K];
+    (J.dst1 + rep * J.rsD1 + (long long)rg * J.ld1)[A.co + j] = v;
+    if (J.dst2 != nullptr && rg >= J.row_off2) (J.dst2 + rep * J.rsD2 + (long long)(rg - J.row_off2) * J.ld2)[A.co + j] = v;
+  }
+}
+
 }  // namespace bsac

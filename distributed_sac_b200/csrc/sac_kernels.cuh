@@ -772,12 +772,21 @@ __global__ void __launch_bounds__(256) adam_kernel(StepConst K, AdamArgs P) {
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)nb * 256) {
       float4 pv = p4[i], mv = m4[i], vv = v4[i];
       float4 gv = g4[i];
-      for (int sx = 0; sx < P.nx; ++sx) {            // split-K slices, added in index order
-        const float4 ge = reinterpret_cast<const float4*>(P.gx + rep * P.rsM + (long long)sx * P.xs)[i];
+      // split-K slices, added in index order; the first three are requested together with everything else (a run-time loop
+      // kept each slice's load behind the previous slice's add: three extra round trips per element group)
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* __restrict__ gx4 = reinterpret_cast<const float4*>(P.gx + rep * P.rsM);
+      const long long xs4 = P.xs >> 2;               // (slice stride: a multiple of 4 floats like every arena)
+      const float4 ge0 = P.nx > 0 ? gx4[i] : z4, ge1 = P.nx > 1 ? gx4[xs4 + i] : z4, ge2 = P.nx > 2 ? gx4[2 * xs4 + i] : z4;
+      float4 tv = z4;
+      if (t4) tv = t4[i];
+      if (P.nx > 0) { gv.x += ge0.x; gv.y += ge0.y; gv.z += ge0.z; gv.w += ge0.w; }
+      if (P.nx > 1) { gv.x += ge1.x; gv.y += ge1.y; gv.z += ge1.z; gv.w += ge1.w; }
+      if (P.nx > 2) { gv.x += ge2.x; gv.y += ge2.y; gv.z += ge2.z; gv.w += ge2.w; }
+      for (int sx = 3; sx < P.nx; ++sx) {
+        const float4 ge = gx4[(long long)sx * xs4 + i];
         gv.x += ge.x; gv.y += ge.y; gv.z += ge.z; gv.w += ge.w;
       }
-      float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t4) tv = t4[i];
       adam_one(pv.x, mv.x, vv.x, gv.x, w1, b2, omb2, step_size, bc2_sqrt, eps);
       adam_one(pv.y, mv.y, vv.y, gv.y, w1, b2, omb2, step_size, bc2_sqrt, eps);
       adam_one(pv.z, mv.z, vv.z, gv.z, w1, b2, omb2, step_size, bc2_sqrt, eps);
