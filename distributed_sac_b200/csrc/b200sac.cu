@@ -1395,9 +1395,15 @@ static int build_plan(b200sac* h) {
     for (int net = 0; net < P.nets; ++net)
       if (P.dW[net] && h->grads_x) { P.dWx[net] = h->grads_x + (P.dW[net] - h->grads); P.dbx[net] = h->grads_x + (P.db[net] - h->grads); }
     const int rows_per = (B + P.row_slices - 1) / P.row_slices;
-    l.grid = dim3(((P.Kdim + kHbCols - 1) / kHbCols) * ((B + rows_per - 1) / rows_per), P.nets, R);
+    // 128-bit column mapping when every row pitch / tensor offset involved is a multiple of 4 floats (l.bn = 4 marks it)
+    // -- for the scalar critic heads; the policy head (NO = 2 x act outputs, one network) would be left with 28 CTAs and
+    // measured slower (12.6 vs 8.7 us at B = 1 024)
+    const bool wide = P.NO == 1 && (P.Kdim % 4) == 0 && (P.ldh % 4) == 0 && (P.lddh % 4) == 0 && getenv("B200SAC_HEADBWD_NARROW") == nullptr;
+    l.bn = wide ? 4 : 1;
+    const int cols = wide ? kHb4Cols : kHbCols;
+    l.grid = dim3(((P.Kdim + cols - 1) / cols) * ((B + rows_per - 1) / rows_per), P.nets, R);
     l.block = dim3(256);
-    l.smem = ((size_t)rows_per * P.NO + 256 * (size_t)P.NO) * sizeof(float);
+    l.smem = ((size_t)rows_per * P.NO + (wide ? 1024 : 256) * (size_t)P.NO) * sizeof(float);
     h->plan.push_back(l);
   };
   // ---- Phase C: critic backward + Adam/Polyak ----------------------------------------------
@@ -1600,6 +1606,7 @@ static int build_plan(b200sac* h) {
     if (l.kind == L_HEADBWD && l.smem > max_smem) max_smem = l.smem;
   if (max_smem > 200 * 1024) return fail(B200SAC_ERR_INVALID, "batch * head width too large for head_bwd smem");
   CU(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  CU(cudaFuncSetAttribute(head_bwd4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
   return 0;
 }
 
@@ -1697,7 +1704,8 @@ static int run_plan(b200sac* h, cudaStream_t st, bool use_eps_buf, cudaEvent_t* 
         launch_k(actor_q_heads_kernel, l.grid, l.block, 0, s, h->K, l.aq);
         break;
       case L_HEADBWD:
-        launch_k(head_bwd_kernel, l.grid, l.block, l.smem, s, h->K, l.hb);
+        if (l.bn == 4) launch_k(head_bwd4_kernel<1>, l.grid, l.block, l.smem, s, h->K, l.hb);
+        else launch_k(head_bwd_kernel, l.grid, l.block, l.smem, s, h->K, l.hb);
         break;
       case L_ADAM:
         launch_k(adam_kernel, l.grid, l.block, 0, s, h->K, l.ad);

@@ -694,6 +694,141 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(StepConst K, HeadBwdArgs 
   }
 }
 
+// The same backward with 128-bit column accesses: thread = 4 consecutive hidden columns x one of 16 row groups, CTA = 64
+// columns x one row slice.  The 8-column mapping above reads and writes 32 bytes per row per warp quarter (four sectors per
+// warp instruction) and needs 50 column blocks x 4 slices x 2 nets = 400 CTAs at the 400-wide shapes -- 10.4 us at B = 1 024,
+// 13 us at 1 280 (profiles/r2_bench_VS.json, round 2); here a warp instruction moves two full 256-byte row segments.  Used
+// when the hidden width is a multiple of 4 (row pitches then are too); same fixed-order reductions, different grouping.
+constexpr int kHb4Cols = 64;   // hidden columns per CTA (16 threads x float4)
+constexpr int kHb4Rows = 16;   // row groups per CTA
+
+template <int NOMAX>
+__global__ void __launch_bounds__(256) head_bwd4_kernel(StepConst K, HeadBwdArgs P) {
+  KStamp ks_;
+  extern __shared__ float sm[];
+  const int net = blockIdx.y, rep = blockIdx.z;
+  const int NO = P.NO, KD = P.Kdim;
+  const int ncb = (KD + kHb4Cols - 1) / kHb4Cols;
+  const int slice = blockIdx.x / ncb, cb = blockIdx.x - slice * ncb;
+  const int rows_per = (P.M + P.row_slices - 1) / P.row_slices;
+  const int r0 = slice * rows_per, r1 = (r0 + rows_per < P.M) ? r0 + rows_per : P.M;
+  const int M = r1 - r0;
+  if (M <= 0) return;
+  float* sd = sm;                                   // [M][NO]
+  float* red = sm + (size_t)rows_per * NO;          // [16 row groups][16 col quads][NO][4]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+  if (P.policy_mode) {
+    const int A = K.act;
+    __shared__ float s_alpha[64];
+    const int Teff = K.T > 0 ? K.T : 1;
+    if (tid < Teff) s_alpha[tid] = (float)exp((double)(P.log_alpha + rep * P.rsP)[tid]);
+    __syncthreads();
+    for (int e = tid; e < M * A; e += 256) {
+      const int ml = e / A, j = e % A, m = r0 + ml;
+      const float* __restrict__ sv = P.psave + rep * P.rsSave + ((long long)m * A + j) * kSaveW;
+      const float* __restrict__ dx0 = P.dx + rep * P.rsDxRep + (long long)m * P.lddx + K.in_w + j;
+      const float da = dx0[0] + dx0[P.rsDxNet];
+      const int tk = (P.tid + rep * P.rsR)[m];
+      float dmu, dls;
+      policy_dout_point(K, sv, da, s_alpha[tk], dmu, dls);
+      sd[ml * NO + j] = dmu;
+      sd[ml * NO + A + j] = dls;
+      if (P.dout_dbg && cb == 0) {
+        (P.dout_dbg + rep * P.rsDbg)[(long long)m * NO + j] = dmu;
+        (P.dout_dbg + rep * P.rsDbg)[(long long)m * NO + A + j] = dls;
+        (P.dact_dbg + rep * P.rsDbg)[(long long)m * A + j] = da;
+      }
+    }
+  } else {
+    const float* __restrict__ src = P.dout + rep * P.rsDoutRep + net * P.rsDoutNet + (long long)r0 * NO;
+    for (int e = tid; e < M * NO; e += 256) sd[e] = src[e];
+  }
+
+  const int kcol = cb * kHb4Cols + 4 * tx;          // first of this thread's four columns (KD % 4 == 0: all four valid or none)
+  const bool kin = kcol < KD;
+  const float* __restrict__ W = P.W[net] + rep * P.rsP;
+  float4 w[NOMAX], gw[NOMAX];
+#pragma unroll
+  for (int j = 0; j < NOMAX; ++j) {                 // head weights requested before the staging barrier
+    w[j] = (j < NO && kin) ? *reinterpret_cast<const float4*>(W + (long long)j * KD + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const float* __restrict__ h = P.h + rep * P.rsHrep + net * P.rsHnet + (long long)r0 * P.ldh;
+  float* __restrict__ dh = P.dh + rep * P.rsDhRep + net * P.rsDhNet + (long long)r0 * P.lddh;
+  constexpr int U = 8;                              // rows in flight per thread
+  for (int mb = ty; mb < M; mb += kHb4Rows * U) {
+    float4 hv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int m = mb + u * kHb4Rows;
+      hv[u] = (kin && m < M) ? *reinterpret_cast<const float4*>(h + (long long)m * P.ldh + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int m = mb + u * kHb4Rows;
+      if (m < M) {
+        float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NOMAX; ++j) {
+          if (j < NO) {
+            const float dv = sd[m * NO + j];
+            ds.x = fmaf(dv, w[j].x, ds.x); ds.y = fmaf(dv, w[j].y, ds.y); ds.z = fmaf(dv, w[j].z, ds.z); ds.w = fmaf(dv, w[j].w, ds.w);
+            gw[j].x = fmaf(dv, hv[u].x, gw[j].x); gw[j].y = fmaf(dv, hv[u].y, gw[j].y);
+            gw[j].z = fmaf(dv, hv[u].z, gw[j].z); gw[j].w = fmaf(dv, hv[u].w, gw[j].w);
+          }
+        }
+        if (kin)
+          *reinterpret_cast<float4*>(dh + (long long)m * P.lddh + kcol) =
+              make_float4(hv[u].x > 0.f ? ds.x : 0.f, hv[u].y > 0.f ? ds.y : 0.f, hv[u].z > 0.f ? ds.z : 0.f, hv[u].w > 0.f ? ds.w : 0.f);
+      }
+    }
+  }
+  if (P.dW[net] != nullptr) {
+    float* __restrict__ dWp = (slice == 0 ? P.dW[net] : P.dWx[net] + (long long)(slice - 1) * P.xs) + rep * P.rsG;
+    float* __restrict__ dbp = (slice == 0 ? P.db[net] : P.dbx[net] + (long long)(slice - 1) * P.xs) + rep * P.rsG;
+#pragma unroll
+    for (int j = 0; j < NOMAX; ++j)
+      if (j < NO) *reinterpret_cast<float4*>(red + ((size_t)(ty * 16 + tx) * NO + j) * 4) = gw[j];
+    __syncthreads();
+    for (int o = tid; o < NO * kHb4Cols; o += 256) {   // (output j, column cc): fixed-order sum over the 16 row groups
+      const int j = o / kHb4Cols, cc = o - j * kHb4Cols;
+      const int col = cb * kHb4Cols + cc;
+      if (col < KD) {
+        float ssum = 0.f;
+#pragma unroll
+        for (int q = 0; q < kHb4Rows; ++q) ssum += red[((size_t)(q * 16 + (cc >> 2)) * NO + j) * 4 + (cc & 3)];
+        dWp[(long long)j * KD + col] = ssum;
+      }
+    }
+    if (cb == 0) {                     // bias gradient: per-thread row sums -> warp shuffle tree -> 8 warp partials (fixed order)
+      __syncthreads();
+      float part[NOMAX];
+#pragma unroll
+      for (int j = 0; j < NOMAX; ++j) part[j] = 0.f;
+      for (int m = tid; m < M; m += 256) {
+#pragma unroll
+        for (int j = 0; j < NOMAX; ++j)
+          if (j < NO) part[j] += sd[m * NO + j];
+      }
+#pragma unroll
+      for (int j = 0; j < NOMAX; ++j)
+        if (j < NO) {
+          const float v = warp_sum(part[j]);
+          if ((tid & 31) == 0) red[(tid >> 5) * kMaxHeadOut + j] = v;
+        }
+      __syncthreads();
+      if (tid < NO) {
+        float ssum = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) ssum += red[wq * kMaxHeadOut + tid];
+        dbp[tid] = ssum;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Adam (torch.optim.adam._single_tensor_adam, defaults) over a contiguous slice of the
 // trainable arena, optionally fused with the Polyak update of the matching target slice
