@@ -81,16 +81,29 @@ def test_backward_intermediates_match_manual_oracle(cuda, precision):
     core.close()
 
 
+@pytest.mark.parametrize("state", ["fresh", "trained"])
 @pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "tc3xtf32"])
 @pytest.mark.parametrize("shape", ["LL", "VS", "MS"])
-def test_full_size_shapes_match_port(cuda, shape, precision):
+def test_full_size_shapes_match_port(cuda, shape, precision, state):
     """BASELINE.json config shapes at full size vs the autograd oracle, three steps, everything at 1e-4.
     ReLU kinks are PROVEN, not budgeted (tests/_golden.py::kink_checked_step): the masks the CUDA step used are forced
-    into the oracle, and every forced bit that differs from the oracle's own must sit on a numerically-zero pre-activation."""
+    into the oracle, and every forced bit that differs from the oracle's own must sit on a numerically-zero pre-activation.
+    state = "trained": the optimizers start deep into training -- step counts of the shipped checkpoints (3.3 M: bias
+    corrections == 1), non-zero first and second moments, a non-zero temperature -- the regime the oracle itself is pinned
+    to the reference in by tests/test_oracle_vs_reference.py (shipped MTSAC / CARE(M) checkpoints, container only)."""
     from distributed_sac_b200.core import SacCore
     spec = {"LL": sp.ll_spec, "VS": sp.vs_spec, "MS": sp.ms_spec}[shape]()
     p = sp.init_params(spec, seed=3)
-    port = sp.PortLearner(spec, p)
+    adam = None
+    if state == "trained":
+        g0 = torch.Generator().manual_seed(5)
+        p = {k: (v * 1.5 if v.dim() == 2 else v + 0.05 * torch.randn(v.shape, generator=g0)) for k, v in p.items()}
+        p["log_alpha"] = torch.full_like(p["log_alpha"], -1.2) + 0.3 * torch.randn(p["log_alpha"].shape, generator=g0)
+        names = sp.param_names(spec, sp.TRAINABLE_NETS)
+        m = {k: 1e-3 * torch.randn(p[k].shape, generator=g0) for k in names}
+        v = {k: m[k] ** 2 * (1.0 + torch.rand(p[k].shape, generator=g0)) + 1e-10 for k in names}
+        adam = {"m": m, "v": v, "step": (3300000, 3300000, 3300000)}
+    port = sp.PortLearner(spec, p, adam_state=adam)
     core = SacCore(core_config(spec, precision=precision), 0, seed=0)
     gen = torch.Generator().manual_seed(77)
     total_flips = 0

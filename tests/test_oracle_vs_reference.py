@@ -121,3 +121,100 @@ def test_reference_load_checkpoint_reads_the_keys_we_write():
     lrn.local_critic_1.load_state_dict(ck["local_critic_1"])
     lrn.critic_optimizer.load_state_dict(ck["critic_optimizer"])
     assert int(lrn.critic_optimizer.state_dict()["state"][0]["step"]) == 2
+
+
+def _shipped(rel):
+    import os
+    p = os.path.join(rh.REF_ROOT, "saved_models", rel)
+    if not os.path.exists(p):
+        pytest.skip(f"shipped checkpoint {rel} not in this checkout")
+    return p
+
+
+def test_port_follows_the_reference_from_the_shipped_mtsac_checkpoint():
+    """Full-size MTSAC (49/4, 400^3, B 1280, weighted loss) started from the reference's own trained checkpoint INCLUDING its
+    Adam moments and step counts (saved_models/MT10_Distributed_MTSAC/checkpoint_3300000.tar, loaded the way the reference's
+    load_checkpoint intends, MS/learner.py:176-190): two update() calls of the unmodified learner against the port."""
+    import gen_golden as gg
+    path = _shipped("MT10_Distributed_MTSAC/checkpoint_3300000.tar")
+    lrn, _ = rh.make_learner("MS", None, seed=0)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    lrn.local_critic.load_state_dict(ck["local_critic"]); lrn.critic_optimizer.load_state_dict(ck["critic_optimizer"])
+    lrn.target_critic.load_state_dict(ck["target_critic"])
+    lrn.actor.load_state_dict(ck["actor"]); lrn.actor_optimizer.load_state_dict(ck["actor_optimizer"])
+    lrn.log_alpha.data = ck["log_alpha"].data.clone(); lrn.log_alpha_optimizer.load_state_dict(ck["log_alpha_optimizer"])
+    weighted = bool(getattr(lrn, "use_weighted_loss", True))
+    spec = gg._spec_of(lrn, "MS", weighted)
+    named = gg._named_params(lrn, "MS")
+    params = {k: p.detach().clone() for k, p in named.items()}
+    m, v, step = gg._adam_snapshot(lrn, named, spec)
+    assert int(step[0]) > 1000 and int(step[1]) > 1000              # a trained state: the bias corrections are ~1
+    port = sp.PortLearner(spec, params, adam_state={"m": m, "v": v, "step": tuple(int(x) for x in step)})
+    g = torch.Generator().manual_seed(11)
+    for i in range(2):
+        b = sp.synthetic_batch(spec, seed=900 + i)
+        e1, e2 = torch.randn(spec.batch, spec.act_dim, generator=g), torch.randn(spec.batch, spec.act_dim, generator=g)
+        lrn.memory.sample = (lambda bb: (lambda: tuple(t.clone() for t in bb)))(b)
+        with rh.injected_eps([e1, e2]) as q:
+            res = lrn.update()
+            assert not q
+        o = port.update_SAC(*b, e1, e2)
+        assert rel_scalar(o["critic_loss"], res[0]) <= 1e-5 and rel_scalar(o["actor_loss"], res[1]) <= 1e-5, (i, o, res)
+    got, st = port.params(), port.adam_state()
+    m2, v2, step2 = gg._adam_snapshot(lrn, named, spec)
+    assert tuple(st["step"]) == tuple(int(x) for x in step2)
+    for k, p in named.items():
+        if k == "log_alpha":
+            assert (got[k] - p.detach()).abs().max().item() <= 1e-6
+            continue
+        assert rel_l2(got[k], p.detach()) <= 1e-5, (k, rel_l2(got[k], p.detach()))
+        if k in m2 and "_target" not in k:
+            assert rel_l2(st["m"][k], m2[k]) <= 1e-4 and rel_l2(st["v"][k], v2[k]) <= 1e-4, k
+
+
+def test_care_port_follows_the_reference_from_a_shipped_care_checkpoint():
+    """The same for CARE(M) at its configured shape (B 1280, K 6, 768-d task embeddings) from
+    saved_models/MT10_Distributed_CARE/CARE(M)/checkpoint_6300000.tar with its optimizer states (C10/learner.py:200-217)."""
+    import care_port as cp
+    import gen_golden as gg
+    path = _shipped("MT10_Distributed_CARE/CARE(M)/checkpoint_6300000.tar")
+    lrn, _ = rh.make_learner("C10", dict(use_modified_care=True), seed=0)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    lrn.context_encoder.load_state_dict(ck["context_encoder"])
+    lrn.local_critic.load_state_dict(ck["local_critic"]); lrn.critic_optimizer.load_state_dict(ck["critic_optimizer"])
+    lrn.target_critic.load_state_dict(ck["target_critic"])
+    lrn.actor.load_state_dict(ck["actor"]); lrn.actor_optimizer.load_state_dict(ck["actor_optimizer"])
+    lrn.log_alpha.data = ck["log_alpha"].data.clone(); lrn.log_alpha_optimizer.load_state_dict(ck["log_alpha_optimizer"])
+    spec = cp.CareSpec(modified=True, weighted_loss=True)
+    named = gg._care_named(lrn)
+    params = {k: p.detach().clone() for k, p in named.items()}
+    # the actor's own state encoder: the reference ties it to the critic's at the end of every update (learner.py:402), so the
+    # checkpoint holds equal copies; the port keeps one
+    ase, cse = dict(lrn.actor.state_encoder.named_parameters()), dict(lrn.local_critic.state_encoder.named_parameters())
+    assert all(torch.equal(ase[k], cse[k]) for k in ase)
+    port = cp.CarePortLearner(spec, params)
+    opts = {"critic": lrn.critic_optimizer, "actor": lrn.actor_optimizer, "alpha": lrn.log_alpha_optimizer}
+    mm, vv, steps = {}, {}, [0, 0, 0]
+    for k in port.trainable_names():
+        tag, slot = ("alpha", 2) if k == "log_alpha" else (("actor", 1) if k.startswith("actor.") else ("critic", 0))
+        stt = opts[tag].state[named[k]]
+        mm[k], vv[k] = stt["exp_avg"].clone(), stt["exp_avg_sq"].clone()
+        steps[slot] = int(stt["step"])
+    assert steps[0] > 1000
+    port.load_adam({"m": mm, "v": vv, "step": tuple(steps)})
+    g = torch.Generator().manual_seed(13)
+    for i in range(2):
+        b = cp.synthetic_batch(spec, seed=950 + i)
+        e1, e2 = torch.randn(spec.batch, spec.act_dim, generator=g), torch.randn(spec.batch, spec.act_dim, generator=g)
+        lrn.memory.sample = (lambda bb: (lambda: tuple(t.clone() for t in bb)))(b)
+        with rh.injected_eps([e1, e2]) as q:
+            res = lrn.update()
+            assert not q
+        o = port.update(*b, e1, e2)
+        assert rel_scalar(o["critic_loss"], res[0]) <= 1e-5 and rel_scalar(o["actor_loss"], res[1]) <= 1e-5, (i, o, res)
+    got = port.params()
+    for k, p in named.items():
+        if k == "log_alpha":
+            assert (got[k] - p.detach()).abs().max().item() <= 1e-6
+        else:
+            assert rel_l2(got[k], p.detach()) <= 1e-5, (k, rel_l2(got[k], p.detach()))
