@@ -20,8 +20,10 @@
  *                            LunarLander_Distributed_SAC/src/learner.py:100-124,144-163,272-276
  *   b200sac_soft_update      Learner.soft_update()            learner.py:126-137
  *   b200sac_publish_*        Learner.get_parameters()         learner.py:272-276 (called at :298-299)
+ *   b200sac_blob_*           server.set('parameters', _pickle.dumps(get_parameters())) in Learner.run()
+ *                            learner.py:298-299 (MT10_Distributed_CARE/src/learner.py:442-443): the byte string, device-assembled
  *   b200sac_act              Actor.get_action() for a batch of environments
- *                            LunarLander_Distributed_SAC/src/model.py:67-82
+ *                            LunarLander_Distributed_SAC/src/model.py:67-82; MT10_Distributed_CARE/src/player.py:199-209 (CARE handles)
  *
  * Conventions: plain pointers and sizes only (no torch types).  Every function
  * returns 0 on success or a negative b200sac_status; a message for the calling
