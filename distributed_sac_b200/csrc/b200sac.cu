@@ -1140,6 +1140,7 @@ static int build_plan(b200sac* h) {
     CareMixFwdArgs A;
     memset(&A, 0, sizeof(A));
     A.njobs = (int)jobs.size(); A.nl = nmix; A.K = Kenc; A.B = B;
+    if (const char* e = getenv("B200SAC_CMF_SKIP")) A.dbg_skip = atoi(e);
     A.params = h->params; A.rsP = rsP;
     A.XS = h->XS.p; A.rsXS = h->XS.rs; A.ldx = h->K.obs;
     A.tid = (const int*)h->tid.p; A.rsR = h->r.rs;
