@@ -588,7 +588,7 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
     l.chain.rsP = rsP;
     l.chain.pol = h->pol;
     l.chain.rw = rw;
-    l.block = dim3(CH_THREADS);
+    l.block = dim3(CH_BLOCK);
     l.smem = CH_SMEM_BYTES;
     return l;
   };
@@ -780,7 +780,7 @@ static int build_plan_fused(b200sac* h, const std::function<void(int, int)>& ada
       if ((long long)2 * ((B + rows - 1) / rows) * R <= 148) l.bn = rows;
     if (const char* e = getenv("B200SAC_CHAIN_ROWS")) { const int v = atoi(e); l.bn = (v == 2 || v == 4) ? v : 8; }
     l.grid = dim3((B + l.bn - 1) / l.bn, 2, R);
-    l.block = dim3(CH_THREADS);
+    l.block = dim3(CH_BLOCK);
     l.smem = C2_SMEM_BYTES;
     h->plan.push_back(l);
   };

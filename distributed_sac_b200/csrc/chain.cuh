@@ -23,6 +23,10 @@
 // 128 CTAs x 256 KB per 256x256 layer = 32 MB of L2 reads, ~2.7 us at the measured L2 rate -- the bound of this design.  Inside a chunk the 8 warps split K (warp w takes k = 4w..4w+3 of the 32), each lane holds an 8-row x
 // 8-column accumulator tile (40 shared-memory wavefronts per 256 FFMA), and the eight partial tiles are added in warp
 // order in shared memory: a fixed summation order, bit-reproducible run to run and replica to replica.
+// The chunk pipeline is warp-specialised: a ninth warp issues the TMA requests and refills a slot as soon as the eight compute
+// warps have released it (mbarrier with 8 arrivals); the compute warps neither issue copies (a cp.async.bulk issue costs
+// the issuing warp ~250 cycles, measured) nor meet at a CTA-wide barrier per chunk (measured: chunk time = ~480 cycles of
+// fixed cost + 110 per row with the issue and the barrier inside the compute loop, profiles/README.md round 2).
 //
 // Weight gradients (the reduction over the batch) are a separate kernel, wgrad_kernel below: 32x32 output tiles, the
 // 8 warps split the batch rows, lanes hold 4x8 accumulators, fixed-order reduction.
@@ -37,8 +41,9 @@ constexpr int CH_MAXW = 256;               // widest layer / widest reduction
 constexpr int CH_KC = 32;                  // k rows per weight chunk
 constexpr int CH_NSTAGE = 3;               // weight chunks in flight
 constexpr int CH_MAXL = 8;                 // dense stages per job
-constexpr int CH_THREADS = 256;
+constexpr int CH_THREADS = 256;             // compute threads (8 warps)
 constexpr int CH_WARPS = CH_THREADS / 32;
+constexpr int CH_BLOCK = CH_THREADS + 32;   // + one producer warp: issues every weight chunk, waits on the slots' "empty" barriers
 constexpr int CH_INP = CH_MAXW + 4;        // row pitch of the activation buffers
 constexpr int CH_CHUNK_FLOATS = CH_MAXW * CH_KC;                     // 8192 floats = 32 KB: [256 n][32 k] swizzled | [32 k][256 n]
 constexpr int CH_MAXJOBS = 3;
@@ -49,7 +54,7 @@ constexpr int CH_SM_HEADW = kMaxHeadOut * CH_INP;
 constexpr int CH_SM_SD = CH_ROWS * kMaxHeadOut;
 constexpr int CH_SM_W0A = CH_MAXW * kMaxAct;
 constexpr int CH_SM_PART = CH_WARPS * CH_ROWS * CH_MAXW;
-constexpr int CH_SM_BARS = 16;             // mbarriers (64 B)
+constexpr int CH_SM_BARS = 16;             // mbarriers (64 B): full[3], empty[3]
 constexpr int CH_SMEM_FLOATS = CH_NSTAGE * CH_CHUNK_FLOATS + CH_SM_BARS + 2 * CH_SM_ACT + CH_SM_HEADW + CH_SM_SD + CH_SM_W0A + CH_SM_PART;
 constexpr size_t CH_SMEM_BYTES = (size_t)CH_SMEM_FLOATS * sizeof(float) + 1024;     // + slack to align the stage buffers to 1 KB
 
@@ -119,8 +124,10 @@ B200_D void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+B200_D void ch_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }      // the eight compute warps (the producer warp is not part of it)
+
 template <bool FWD, int ROWS>
-__global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainArgs A, StepConst K) {
+__global__ void __launch_bounds__(CH_BLOCK, 1) chain_kernel(const __grid_constant__ ChainArgs A, StepConst K) {
   long long* const dbg = (A.dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0) ? A.dbg : nullptr;
   int dbg_i = 0;
 #define CH_STAMP() do { if (dbg != nullptr && dbg_i < CH_DBG_SLOTS) dbg[dbg_i++] = clock64(); } while (0)
@@ -153,21 +160,27 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   // partials, no reduction (measured: ~2200 cycles of chunk wait + partial-tile epilogue for 80 FMAs per thread).
   const bool direct0 = FWD && J.nstages > 1 && J.st[0].K <= CH_KC;
   int is = direct0 ? 1 : 0, ic = 0, issued = 0;        // next chunk to issue: stage, chunk within the stage, running count
-  auto issue_next = [&]() {
-    if (tid == 0 && is < J.nstages) {
+  // who: the thread that executes it (0: the early requests before griddepcontrol.wait; CH_THREADS: the producer warp's lane 0);
+  // dry: advance the iterator only (the producer skips what thread 0 already requested)
+  auto issue_next = [&](int who, bool dry) {
+    if (tid == who && is < J.nstages) {
       const ChainStage& S = J.st[is];
       const int K4 = (S.K + 3) & ~3;
       const int k0 = ic * CH_KC;
       const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
       const int slot = issued % CH_NSTAGE;
-      const uint32_t bar = smem_u32(bars + slot), dst = smem_u32(wst + slot * CH_CHUNK_FLOATS);
-      if constexpr (FWD) {
-        mbar_expect_tx(bar, (uint32_t)S.N * CH_KC * 4u);
-        tma_load_2d(dst, S.tm + (long long)rep * S.rsTm, k0, 0, bar);
-      } else {
-        const uint32_t bytes = (uint32_t)kc * (uint32_t)S.N * 4u;
-        mbar_expect_tx(bar, bytes);
-        bulk_load_1d(dst, S.W + po + (long long)k0 * S.ldw, bytes, bar);
+      if (!dry) {
+        // a slot is refilled when all eight compute warps have released its previous chunk
+        if (issued >= CH_NSTAGE) mbar_wait(smem_u32(bars + CH_NSTAGE + slot), (uint32_t)((issued / CH_NSTAGE - 1) & 1));
+        const uint32_t bar = smem_u32(bars + slot), dst = smem_u32(wst + slot * CH_CHUNK_FLOATS);
+        if constexpr (FWD) {
+          mbar_expect_tx(bar, (uint32_t)S.N * CH_KC * 4u);
+          tma_load_2d(dst, S.tm + (long long)rep * S.rsTm, k0, 0, bar);
+        } else {
+          const uint32_t bytes = (uint32_t)kc * (uint32_t)S.N * 4u;
+          mbar_expect_tx(bar, bytes);
+          bulk_load_1d(dst, S.W + po + (long long)k0 * S.ldw, bytes, bar);
+        }
       }
       ++issued;
       if (k0 + CH_KC >= K4) { ic = 0; ++is; } else { ++ic; }
@@ -201,17 +214,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     if (tid == 0) {
       if constexpr (FWD) asm volatile("prefetch.tensormap [%0];" ::"l"(J.st[0].tm + (long long)rep * J.st[0].rsTm) : "memory");
 #pragma unroll
-      for (int i = 0; i < CH_NSTAGE; ++i) mbar_init(smem_u32(bars + i), 1);
+      for (int i = 0; i < CH_NSTAGE; ++i) { mbar_init(smem_u32(bars + i), 1); mbar_init(smem_u32(bars + CH_NSTAGE + i), CH_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      if (A.early_weights) { issue_next(); issue_next(); }
+      if (A.early_weights) { issue_next(0, false); issue_next(0, false); }
     }
-    if (A.early_weights) request_weights();
+    if (A.early_weights && tid < CH_THREADS) request_weights();
   }
   KStamp ks_;
   CH_STAMP();                              // 1: predecessor complete (griddepcontrol.wait)
   if (!live) return;
-  __syncthreads();                         // barriers initialised
-  if (!A.early_weights) { issue_next(); issue_next(); request_weights(); }
+  __syncthreads();                         // barriers initialised (all nine warps)
+  if (tid >= CH_THREADS) {                 // ---- producer warp: every remaining weight chunk, in order ----
+    if (A.early_weights) { issue_next(CH_THREADS, true); issue_next(CH_THREADS, true); }     // thread 0 requested these before the wait
+    while (tid == CH_THREADS && is < J.nstages) issue_next(CH_THREADS, false);
+    return;
+  }
+  if (!A.early_weights) request_weights();
 
   float* In = actA;
   float* Out = actB;
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     }
     CH_STAMP();                                    // (bwd) per-row scalars -> d(head output) done by warp 0
     cp_async_wait<0>();                            // the head weights have landed
-    __syncthreads();
+    ch_sync();      
     CH_STAMP();                                    // (bwd) head weights landed, every warp's d(head output) visible
     if (tid < J.Hh) {
       float* __restrict__ dyl = J.dylast ? J.dylast + (long long)rep * J.rsDy + (long long)row0 * J.lddy : nullptr;
@@ -345,7 +363,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
 #pragma unroll
       for (int i = 0; i < CH_MAXW * kMaxAct / CH_THREADS; ++i) w0a[tid + i * CH_THREADS] = w0r[i];
     }
-    __syncthreads();                               // In (and the staged action columns) visible to every warp
+    ch_sync();                                     // In (and the staged action columns) visible to every warp
   }
 
   CH_STAMP();                              // 3: backward prologue done (forward: == 2)
@@ -358,7 +376,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       const float4 (&wr)[CH_KC / 4] = wr0;          // this thread's row of W0, requested in the prologue
       const float b0 = b00;
       cp_async_wait<0>();
-      __syncthreads();                  // the input rows are in shared memory
+      ch_sync();                        // the input rows are in shared memory
       if (tid < N) {
         float* __restrict__ go = S.out ? S.out + (long long)rep * S.rsOut + (long long)row0 * S.ldo : nullptr;
 #pragma unroll
@@ -375,7 +393,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           if (go && m < nrows) go[(long long)m * S.ldo + tid] = v;
         }
       }
-      __syncthreads();
+      ch_sync();      
       CH_STAMP();                       // input layer done (direct)
       float* t_ = In; In = Out; Out = t_;
     }
@@ -401,11 +419,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       for (int i = 0; i < 8; ++i) acc[m][i] = 0.f;
 
     for (int k0 = 0; k0 < K4; k0 += CH_KC, ++g) {
-      if (g == 0) cp_async_wait<0>();   // forward: the input rows (this thread's pieces; the barrier below publishes them)
+      if (g == 0) { cp_async_wait<0>(); ch_sync(); }   // forward: the input rows (every thread's pieces) are visible to all
       mbar_wait(smem_u32(bars + g % CH_NSTAGE), (uint32_t)((g / CH_NSTAGE) & 1));
-      __syncthreads();                  // everyone is done with chunk g-1: its buffer is refilled next
-      CH_STAMP();                       // per chunk: data landed + barrier passed
-      issue_next();
+      CH_STAMP();                       // per chunk: data landed
       const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
       const float* __restrict__ Wc = wst + (g % CH_NSTAGE) * CH_CHUNK_FLOATS;
       if (4 * w < kc) {
@@ -453,6 +469,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bars + CH_NSTAGE + g % CH_NSTAGE));   // this warp is done with the slot
     }
     CH_STAMP();                         // per stage: last chunk computed
     // ---- stage epilogue: the 8 partial tiles -> fixed-order sum -> bias+ReLU | ReLU' gate -> next input -----------------
@@ -471,7 +489,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         }
       }
     }
-    __syncthreads();
+    ch_sync();      
     if (tid < N) {
       float* __restrict__ go = S.out ? S.out + (long long)rep * S.rsOut + (long long)row0 * S.ldo : nullptr;
 #pragma unroll
@@ -488,12 +506,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
 #pragma unroll
       for (int m = 0; m < ROWS; ++m) Out[m * CH_INP + tid] = 0.f;
     }
-    __syncthreads();
+    ch_sync();      
     CH_STAMP();                         // per stage: epilogue done
     float* t = In; In = Out; Out = t;
   }
   cp_async_wait<0>();
-  __syncthreads();                         // (jobs without dense stages: head weights / inputs visible)
+  ch_sync();                               // (jobs without dense stages: head weights / inputs visible)
 
   // ---- head / tail: warp w owns row w ----------------------------------------------------------------------------------
   const int row = row0 + w;
@@ -530,7 +548,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       for (int o = G >> 1; o > 0; o >>= 1) accj += __shfl_xor_sync(0xffffffffu, accj, o);
       if (jj < NO && part_ == 0) sd[w * kMaxHeadOut + jj] = accj + __ldg(bias + jj);
     }
-    __syncthreads();
+    ch_sync();      
     CH_STAMP();                                    // (policy head) GEMVs done
     if (w == 0) {
       const PolicyHeadArgs& P = A.pol;

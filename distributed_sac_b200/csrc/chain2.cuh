@@ -56,7 +56,7 @@ B200_D float ld_peer_f32(const float* my_smem_addr, uint32_t peer_rank) {
 }
 
 template <int ROWS>
-__global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_constant__ Chain2Args A, StepConst K) {
+__global__ void __launch_bounds__(CH_BLOCK, 1) chain2_kernel(const __grid_constant__ Chain2Args A, StepConst K) {
   long long* const dbg = (A.dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0) ? A.dbg : nullptr;
   int dbg_i = 0;
 #define C2_STAMP() do { if (dbg != nullptr && dbg_i < CH_DBG_SLOTS) dbg[dbg_i++] = clock64(); } while (0)
@@ -88,22 +88,26 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
   const int nst = J.nfwd + J.nbwd;
   const bool direct0 = J.nfwd > 1 && J.fst[0].K <= CH_KC;
   int is = direct0 ? 1 : 0, ic = 0, issued = 0;
-  auto issue_next = [&]() {
-    if (tid == 0 && is < nst) {
+  // (who / dry: see chain_kernel -- thread 0 requests the first two chunks before griddepcontrol.wait, the producer warp the rest)
+  auto issue_next = [&](int who, bool dry) {
+    if (tid == who && is < nst) {
       const bool f = is < J.nfwd;
       const ChainStage& S = f ? J.fst[is] : J.bst[is - J.nfwd];
       const int K4 = (S.K + 3) & ~3;
       const int k0 = ic * CH_KC;
       const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
       const int slot = issued % CH_NSTAGE;
-      const uint32_t bar = smem_u32(bars + slot), dst = smem_u32(wst + slot * CH_CHUNK_FLOATS);
-      if (f) {
-        mbar_expect_tx(bar, (uint32_t)S.N * CH_KC * 4u);
-        tma_load_2d(dst, S.tm + (long long)rep * S.rsTm, k0, 0, bar);
-      } else {
-        const uint32_t bytes = (uint32_t)kc * (uint32_t)S.N * 4u;
-        mbar_expect_tx(bar, bytes);
-        bulk_load_1d(dst, S.W + po + (long long)k0 * S.ldw, bytes, bar);
+      if (!dry) {
+        if (issued >= CH_NSTAGE) mbar_wait(smem_u32(bars + CH_NSTAGE + slot), (uint32_t)((issued / CH_NSTAGE - 1) & 1));
+        const uint32_t bar = smem_u32(bars + slot), dst = smem_u32(wst + slot * CH_CHUNK_FLOATS);
+        if (f) {
+          mbar_expect_tx(bar, (uint32_t)S.N * CH_KC * 4u);
+          tma_load_2d(dst, S.tm + (long long)rep * S.rsTm, k0, 0, bar);
+        } else {
+          const uint32_t bytes = (uint32_t)kc * (uint32_t)S.N * 4u;
+          mbar_expect_tx(bar, bytes);
+          bulk_load_1d(dst, S.W + po + (long long)k0 * S.ldw, bytes, bar);
+        }
       }
       ++issued;
       if (k0 + CH_KC >= K4) { ic = 0; ++is; } else { ++ic; }
@@ -127,15 +131,27 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(J.fst[direct0 ? 1 : 0].tm + (long long)rep * J.fst[direct0 ? 1 : 0].rsTm) : "memory");
 #pragma unroll
-    for (int i = 0; i < CH_NSTAGE; ++i) mbar_init(smem_u32(bars + i), 1);
+    for (int i = 0; i < CH_NSTAGE; ++i) { mbar_init(smem_u32(bars + i), 1); mbar_init(smem_u32(bars + CH_NSTAGE + i), CH_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (A.early_weights) { issue_next(); issue_next(); }
+    if (A.early_weights) { issue_next(0, false); issue_next(0, false); }
   }
-  if (A.early_weights) request_weights();
+  if (A.early_weights && tid < CH_THREADS) request_weights();
   KStamp ks_;
   C2_STAMP();
-  __syncthreads();
-  if (!A.early_weights) { issue_next(); issue_next(); request_weights(); }
+  __syncthreads();                         // barriers initialised (all nine warps)
+  if (tid >= CH_THREADS) {
+    // ---- producer warp: every remaining weight chunk of the forward AND the backward part, in order.  It takes part in the
+    // cluster barriers without ever blocking the twins' exchange: it arrives for the exchange phase right away (it needs
+    // nothing from it) and collects that phase when its work is done.
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (A.early_weights) { issue_next(CH_THREADS, true); issue_next(CH_THREADS, true); }
+    while (tid == CH_THREADS && is < nst) issue_next(CH_THREADS, false);
+    __syncwarp();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    cluster_sync_all();                    // the final one (nobody leaves while its twin may still read its shared memory)
+    return;
+  }
+  if (!A.early_weights) request_weights();
 
   float* In = actA;
   float* Out = actB;
@@ -201,11 +217,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[m][i] = 0.f;
     for (int k0 = 0; k0 < K4; k0 += CH_KC, ++g) {
-      if (g == 0) cp_async_wait<0>();
+      if (g == 0) { cp_async_wait<0>(); ch_sync(); }
       mbar_wait(smem_u32(bars + g % CH_NSTAGE), (uint32_t)((g / CH_NSTAGE) & 1));
-      __syncthreads();
       C2_STAMP();
-      issue_next();
       const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
       const float* __restrict__ Wc = wst + (g % CH_NSTAGE) * CH_CHUNK_FLOATS;
       if (4 * w < kc) {
@@ -249,6 +263,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bars + CH_NSTAGE + g % CH_NSTAGE));     // this warp is done with the slot
     }
     {
       float* __restrict__ pw = part + w * (ROWS * CH_MAXW);
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
         }
       }
     }
-    __syncthreads();
+    ch_sync();      
     if (tid < N) {
       float* __restrict__ go = S.out ? S.out + (long long)rep * S.rsOut + (long long)row0 * S.ldo : nullptr;
 #pragma unroll
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
         if (go && m < nrows) go[(long long)m * S.ldo + tid] = v;
       }
     }
-    __syncthreads();
+    ch_sync();      
     C2_STAMP();
     float* t_ = In; In = Out; Out = t_;
   };
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
     const ChainStage& S = J.fst[0];
     const int N = S.N, K4 = (S.K + 3) & ~3;
     cp_async_wait<0>();
-    __syncthreads();
+    ch_sync();      
     if (tid < N) {
       float* __restrict__ go = S.out ? S.out + (long long)rep * S.rsOut + (long long)row0 * S.ldo : nullptr;
 #pragma unroll
@@ -306,13 +322,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
         if (go && m < nrows) go[(long long)m * S.ldo + tid] = v;
       }
     }
-    __syncthreads();
+    ch_sync();      
     C2_STAMP();
     float* t_ = In; In = Out; Out = t_;
   }
   for (int s = direct0 ? 1 : 0; s < J.nfwd; ++s) run_stage(J.fst[s], std::true_type{});
   cp_async_wait<0>();
-  __syncthreads();
+  ch_sync();      
   // forward scalar head: warp w owns row w
   float q_own = 0.f;
   // gate activations of the backward part: requested before the head so that their latency hides behind it (critic
@@ -374,7 +390,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
   }
   // ================================ backward part ================================
   {
-    __syncthreads();                       // sd visible
+    ch_sync();                             // sd visible
     if (tid < J.Hhb) {
       float* __restrict__ dyl = J.dylast ? J.dylast + (long long)rep * J.rsDy + (long long)row0 * J.lddy : nullptr;
       const float wh = headB[tid];
@@ -393,7 +409,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain2_kernel(const __grid_cons
 #pragma unroll
       for (int i = 0; i < CH_MAXW * kMaxAct / CH_THREADS; ++i) w0a[tid + i * CH_THREADS] = w0r[i];
     }
-    __syncthreads();
+    ch_sync();      
     C2_STAMP();
   }
   for (int s = 0; s < J.nbwd; ++s) run_stage(J.bst[s], std::false_type{});
