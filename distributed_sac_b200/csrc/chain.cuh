@@ -24,7 +24,7 @@
 // 8-column accumulator tile (40 shared-memory wavefronts per 256 FFMA), and the eight partial tiles are added in warp
 // order in shared memory: a fixed summation order, bit-reproducible run to run and replica to replica.
 // The chunk pipeline is warp-specialised: a ninth warp issues the TMA requests and refills a slot as soon as the eight compute
-// warps have released it (mbarrier with 8 arrivals); the compute warps neither issue copies (a cp.async.bulk issue costs
+// warps have released it (a named hardware barrier per slot: bar.arrive by the compute threads, bar.sync by the producer); the compute warps neither issue copies (a cp.async.bulk issue costs
 // the issuing warp ~250 cycles, measured) nor meet at a CTA-wide barrier per chunk (measured: chunk time = ~480 cycles of
 // fixed cost + 110 per row with the issue and the barrier inside the compute loop, profiles/README.md round 2).
 //
@@ -54,7 +54,7 @@ constexpr int CH_SM_HEADW = kMaxHeadOut * CH_INP;
 constexpr int CH_SM_SD = CH_ROWS * kMaxHeadOut;
 constexpr int CH_SM_W0A = CH_MAXW * kMaxAct;
 constexpr int CH_SM_PART = CH_WARPS * CH_ROWS * CH_MAXW;
-constexpr int CH_SM_BARS = 16;             // mbarriers (64 B): full[3], empty[3]
+constexpr int CH_SM_BARS = 16;             // mbarriers (64 B): full[3]
 constexpr int CH_SMEM_FLOATS = CH_NSTAGE * CH_CHUNK_FLOATS + CH_SM_BARS + 2 * CH_SM_ACT + CH_SM_HEADW + CH_SM_SD + CH_SM_W0A + CH_SM_PART;
 constexpr size_t CH_SMEM_BYTES = (size_t)CH_SMEM_FLOATS * sizeof(float) + 1024;     // + slack to align the stage buffers to 1 KB
 
@@ -125,6 +125,10 @@ B200_D void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t
 }
 
 B200_D void ch_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }      // the eight compute warps (the producer warp is not part of it)
+// slot hand-back: the 256 compute threads ARRIVE (non-blocking) on the slot's named barrier once their reads of the chunk are
+// done, the producer warp SYNCs on it before the refill -- hardware barriers 2..4, one per slot, 288 participants
+B200_D void ch_slot_release(int slot) { asm volatile("bar.arrive %0, 288;" ::"r"(2 + slot) : "memory"); }
+B200_D void ch_slot_acquire(int slot) { asm volatile("bar.sync %0, 288;" ::"r"(2 + slot) : "memory"); }
 
 template <bool FWD, int ROWS>
 __global__ void __launch_bounds__(CH_BLOCK, 1) chain_kernel(const __grid_constant__ ChainArgs A, StepConst K) {
@@ -163,29 +167,33 @@ __global__ void __launch_bounds__(CH_BLOCK, 1) chain_kernel(const __grid_constan
   // who: the thread that executes it (0: the early requests before griddepcontrol.wait; CH_THREADS: the producer warp's lane 0);
   // dry: advance the iterator only (the producer skips what thread 0 already requested)
   auto issue_next = [&](int who, bool dry) {
-    if (tid == who && is < J.nstages) {
+    const bool mine = who == 0 ? tid == 0 : tid >= CH_THREADS;        // thread 0 (early requests) | the whole producer warp
+    if (mine && is < J.nstages) {
       const ChainStage& S = J.st[is];
       const int K4 = (S.K + 3) & ~3;
       const int k0 = ic * CH_KC;
       const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
       const int slot = issued % CH_NSTAGE;
       if (!dry) {
-        // a slot is refilled when all eight compute warps have released its previous chunk
-        if (issued >= CH_NSTAGE) mbar_wait(smem_u32(bars + CH_NSTAGE + slot), (uint32_t)((issued / CH_NSTAGE - 1) & 1));
-        const uint32_t bar = smem_u32(bars + slot), dst = smem_u32(wst + slot * CH_CHUNK_FLOATS);
-        if constexpr (FWD) {
-          mbar_expect_tx(bar, (uint32_t)S.N * CH_KC * 4u);
-          tma_load_2d(dst, S.tm + (long long)rep * S.rsTm, k0, 0, bar);
-        } else {
-          const uint32_t bytes = (uint32_t)kc * (uint32_t)S.N * 4u;
-          mbar_expect_tx(bar, bytes);
-          bulk_load_1d(dst, S.W + po + (long long)k0 * S.ldw, bytes, bar);
+        if (issued >= CH_NSTAGE) ch_slot_acquire(slot);               // every compute thread is done with the slot's previous chunk
+        if (tid == who) {
+          const uint32_t bar = smem_u32(bars + slot), dst = smem_u32(wst + slot * CH_CHUNK_FLOATS);
+          if constexpr (FWD) {
+            mbar_expect_tx(bar, (uint32_t)S.N * CH_KC * 4u);
+            tma_load_2d(dst, S.tm + (long long)rep * S.rsTm, k0, 0, bar);
+          } else {
+            const uint32_t bytes = (uint32_t)kc * (uint32_t)S.N * 4u;
+            mbar_expect_tx(bar, bytes);
+            bulk_load_1d(dst, S.W + po + (long long)k0 * S.ldw, bytes, bar);
+          }
         }
       }
       ++issued;
       if (k0 + CH_KC >= K4) { ic = 0; ++is; } else { ++ic; }
     }
   };
+  int total_chunks = 0;                      // (the compute warps hand a slot back only if a later chunk will refill it)
+  for (int s_ = direct0 ? 1 : 0; s_ < J.nstages; ++s_) total_chunks += (((J.st[s_].K + 3) & ~3) + CH_KC - 1) / CH_KC;
   // weights that do not depend on the launch right before this one: the head matrix (cp.async) and, for a directly
   // evaluated input layer, this thread's row of W0 + its bias (registers)
   float4 wr0[CH_KC / 4];
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(CH_BLOCK, 1) chain_kernel(const __grid_constan
     if (tid == 0) {
       if constexpr (FWD) asm volatile("prefetch.tensormap [%0];" ::"l"(J.st[0].tm + (long long)rep * J.st[0].rsTm) : "memory");
 #pragma unroll
-      for (int i = 0; i < CH_NSTAGE; ++i) { mbar_init(smem_u32(bars + i), 1); mbar_init(smem_u32(bars + CH_NSTAGE + i), CH_WARPS); }
+      for (int i = 0; i < CH_NSTAGE; ++i) mbar_init(smem_u32(bars + i), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       if (A.early_weights) { issue_next(0, false); issue_next(0, false); }
     }
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(CH_BLOCK, 1) chain_kernel(const __grid_constan
   __syncthreads();                         // barriers initialised (all nine warps)
   if (tid >= CH_THREADS) {                 // ---- producer warp: every remaining weight chunk, in order ----
     if (A.early_weights) { issue_next(CH_THREADS, true); issue_next(CH_THREADS, true); }     // thread 0 requested these before the wait
-    while (tid == CH_THREADS && is < J.nstages) issue_next(CH_THREADS, false);
+    while (is < J.nstages) issue_next(CH_THREADS, false);
     return;
   }
   if (!A.early_weights) request_weights();
@@ -469,8 +477,7 @@ __global__ void __launch_bounds__(CH_BLOCK, 1) chain_kernel(const __grid_constan
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(bars + CH_NSTAGE + g % CH_NSTAGE));   // this warp is done with the slot
+      if (g + CH_NSTAGE < total_chunks) ch_slot_release(g % CH_NSTAGE);         // this thread is done with the slot
     }
     CH_STAMP();                         // per stage: last chunk computed
     // ---- stage epilogue: the 8 partial tiles -> fixed-order sum -> bias+ReLU | ReLU' gate -> next input -----------------

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(CH_BLOCK, 1) chain2_kernel(const __grid_consta
   int is = direct0 ? 1 : 0, ic = 0, issued = 0;
   // (who / dry: see chain_kernel -- thread 0 requests the first two chunks before griddepcontrol.wait, the producer warp the rest)
   auto issue_next = [&](int who, bool dry) {
-    if (tid == who && is < nst) {
+    const bool mine = who == 0 ? tid == 0 : tid >= CH_THREADS;        // thread 0 (early requests) | the whole producer warp
+    if (mine && is < nst) {
       const bool f = is < J.nfwd;
       const ChainStage& S = f ? J.fst[is] : J.bst[is - J.nfwd];
       const int K4 = (S.K + 3) & ~3;
@@ -98,21 +99,28 @@ __global__ void __launch_bounds__(CH_BLOCK, 1) chain2_kernel(const __grid_consta
       const int kc = (K4 - k0 < CH_KC) ? K4 - k0 : CH_KC;
       const int slot = issued % CH_NSTAGE;
       if (!dry) {
-        if (issued >= CH_NSTAGE) mbar_wait(smem_u32(bars + CH_NSTAGE + slot), (uint32_t)((issued / CH_NSTAGE - 1) & 1));
-        const uint32_t bar = smem_u32(bars + slot), dst = smem_u32(wst + slot * CH_CHUNK_FLOATS);
-        if (f) {
-          mbar_expect_tx(bar, (uint32_t)S.N * CH_KC * 4u);
-          tma_load_2d(dst, S.tm + (long long)rep * S.rsTm, k0, 0, bar);
-        } else {
-          const uint32_t bytes = (uint32_t)kc * (uint32_t)S.N * 4u;
-          mbar_expect_tx(bar, bytes);
-          bulk_load_1d(dst, S.W + po + (long long)k0 * S.ldw, bytes, bar);
+        if (issued >= CH_NSTAGE) ch_slot_acquire(slot);
+        if (tid == who) {
+          const uint32_t bar = smem_u32(bars + slot), dst = smem_u32(wst + slot * CH_CHUNK_FLOATS);
+          if (f) {
+            mbar_expect_tx(bar, (uint32_t)S.N * CH_KC * 4u);
+            tma_load_2d(dst, S.tm + (long long)rep * S.rsTm, k0, 0, bar);
+          } else {
+            const uint32_t bytes = (uint32_t)kc * (uint32_t)S.N * 4u;
+            mbar_expect_tx(bar, bytes);
+            bulk_load_1d(dst, S.W + po + (long long)k0 * S.ldw, bytes, bar);
+          }
         }
       }
       ++issued;
       if (k0 + CH_KC >= K4) { ic = 0; ++is; } else { ++ic; }
     }
   };
+  int total_chunks = 0;
+  for (int s_ = direct0 ? 1 : 0; s_ < nst; ++s_) {
+    const ChainStage& S_ = s_ < J.nfwd ? J.fst[s_] : J.bst[s_ - J.nfwd];
+    total_chunks += (((S_.K + 3) & ~3) + CH_KC - 1) / CH_KC;
+  }
   float4 wr0[CH_KC / 4];
   float b00 = 0.f, bq = 0.f;
   auto request_weights = [&]() {
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(CH_BLOCK, 1) chain2_kernel(const __grid_consta
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(J.fst[direct0 ? 1 : 0].tm + (long long)rep * J.fst[direct0 ? 1 : 0].rsTm) : "memory");
 #pragma unroll
-    for (int i = 0; i < CH_NSTAGE; ++i) { mbar_init(smem_u32(bars + i), 1); mbar_init(smem_u32(bars + CH_NSTAGE + i), CH_WARPS); }
+    for (int i = 0; i < CH_NSTAGE; ++i) mbar_init(smem_u32(bars + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (A.early_weights) { issue_next(0, false); issue_next(0, false); }
   }
@@ -145,8 +153,7 @@ __global__ void __launch_bounds__(CH_BLOCK, 1) chain2_kernel(const __grid_consta
     // nothing from it) and collects that phase when its work is done.
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     if (A.early_weights) { issue_next(CH_THREADS, true); issue_next(CH_THREADS, true); }
-    while (tid == CH_THREADS && is < nst) issue_next(CH_THREADS, false);
-    __syncwarp();
+    while (is < nst) issue_next(CH_THREADS, false);
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     cluster_sync_all();                    // the final one (nobody leaves while its twin may still read its shared memory)
     return;
@@ -263,8 +270,7 @@ __global__ void __launch_bounds__(CH_BLOCK, 1) chain2_kernel(const __grid_consta
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(bars + CH_NSTAGE + g % CH_NSTAGE));     // this warp is done with the slot
+      if (g + CH_NSTAGE < total_chunks) ch_slot_release(g % CH_NSTAGE);
     }
     {
       float* __restrict__ pw = part + w * (ROWS * CH_MAXW);
